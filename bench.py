@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- GOLF-ss synthesis throughput (audio samples/s) on N B200s, one process per GPU.
+
+Workload (BASELINE.json metric / configs[2] at N=1): the full GOLF-ss decoder forward
+(cfg/ae/decoder/golf-precise.yaml: DownsampledIndexedGlottalFlowTable 4x oversampled ->
+StandardNormalNoise -> LTVZeroPhaseFIRFilter(n_mag 256) -> LTVMinimumPhaseFilterPrecise(M=22)
+-> LTIAcousticFilter(128)), batch 32 x 2 s @ 24 kHz PER GPU (weak scaling; utterances are
+independent, so ranks shard the batch and there is no data-path collective), training-mode
+inputs (sample-rate f0), controls = the real encoder's output on the reference's sample
+wavs (tests/golden/controls_gt.npz) tiled to the batch.
+
+A step = one decoder pass over one batch.  Sample-count convention: B x 48 000
+nominal samples per pass on both arms.
+
+  value     whole-job samples/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       same through the public nn.Module API with HOST (pinned) inputs: H2D of the
+            step's controls and D2H of the waveform inside the timed region
+  roofline  dominant kernel (GOLF-ss chunk-response pass), timed alone with CUDA events
+  cpu_baseline / --impl reference
+            the oracle port of the reference decoder (torch-CPU ops + OpenMP C recurrence,
+            the shape of the reference's own CPU path) on this box's host cores
+
+usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl golf|reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR, SECONDS, BATCH, HOP, ORDER, N_MAG, OS = 24000, 2.0, 32, 240, 22, 256, 4
+T = int(SR * SECONDS)
+FRAMES = T // HOP  # 200: training-mode control frames (models/unet.py:160-162)
+N_SETS = 8         # rotating input sets: 8 x ~26 MB > 126 MB L2
+
+
+# ----------------------------------------------------------------------------- inputs
+def make_inputs(n_sets: int, batch: int, seed: int = 2434):
+    """host float32 tensors for n_sets batches: phase [B,T] (cycles/sample, hop 1), w [B,21]@2400,
+    log_mag [B,F,256], gain [B,F], a [B,F,M] @240."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "controls_gt.npz"))
+    gen = torch.Generator().manual_seed(seed)
+    sets = []
+    n_utt = g["gain"].shape[0]
+    for s in range(n_sets):
+        idx = (torch.arange(batch) + s) % n_utt
+        # f0: random walk in [80, 400] Hz at sample rate; 20 % of 0.1 s segments "unvoiced" ->
+        # replaced by one U(50, 500) draw per item (ltng/ae.py:96-101)
+        walk = torch.cumsum(torch.randn(batch, T // 240, generator=gen) * 4, 1) + torch.empty(batch, 1).uniform_(120, 300, generator=gen)
+        f0 = torch.nn.functional.interpolate(walk.clamp(80, 400)[:, None], T, mode="linear", align_corners=True)[:, 0]
+        unv = (torch.rand(batch, T // 2400, generator=gen) < 0.2).repeat_interleave(2400, 1)
+        f0 = torch.where(unv, torch.empty(batch, 1).uniform_(50, 500, generator=gen).expand(-1, T), f0)
+        sets.append(dict(
+            phase=(f0 / SR).contiguous(),
+            w=torch.tensor(g["w"])[idx].contiguous(),
+            log_mag=torch.tensor(g["log_mag"])[idx, :FRAMES].contiguous(),
+            gain=torch.tensor(g["gain"])[idx, :FRAMES].contiguous(),
+            a=torch.tensor(g["a"])[idx, :FRAMES].contiguous(),
+        ))
+    return sets
+
+
+def room_kernel():
+    return torch.tensor(np.load(os.path.join(ROOT, "tests", "golden", "table.npz"))["room_kernel_ss"])
+
+
+# ------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_decoder_pass(O, s, table, rk, noise):
+    return O.source_filter_synth(s["phase"], 1, s["w"], 2400, s["log_mag"], s["gain"], s["a"], HOP, noise, table, rk,
+                                 variant="ss", oversampling=OS)
+
+
+def run_cpu(steps: int, warmup: int, batch: int):
+    """the reference's CPU path, restated (oracle port): returns (samples/s, cores, seconds/pass)"""
+    from oracle import golf_oracle as O
+
+    O.build()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    O.set_num_threads(cores)
+    table, _ = O.glottal_table()
+    rk = room_kernel()
+    sets = make_inputs(2, batch)
+    noise = torch.randn(batch, T)
+    for i in range(warmup):
+        cpu_decoder_pass(O, sets[i % 2], table, rk, noise)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        noise = torch.randn(batch, T)  # the reference draws noise inside the decoder
+        cpu_decoder_pass(O, sets[i % 2], table, rk, noise)
+    dt = (time.perf_counter() - t0) / steps
+    return batch * T / dt, cores, dt
+
+
+def cpu_line(args):
+    val, cores, dt = run_cpu(args.steps, max(args.warmup, 1), BATCH)
+    sample = f"{args.steps} full decoder passes of {BATCH} x {SECONDS:g} s ({dt:.3f} s each) after {max(args.warmup, 1)} warm-up"
+    return {
+        "impl": "reference", "metric": "audio samples/sec, GOLF-ss synthesis 24 kHz batch 32 x 2 s", "value": val,
+        "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference = Python + torchlpc/kazane (absent, not installable): timed arm is the oracle port of its CPU path",
+    }
+
+
+def workload_config(n):
+    return {"workload": "GOLF-ss decoder forward (SourceFilterSynth, cfg/ae/decoder/golf-precise.yaml), training-mode inputs",
+            "batch_per_gpu": BATCH, "global_batch": BATCH * n, "seconds": SECONDS, "sample_rate": SR, "hop": HOP,
+            "lpc_order": ORDER, "n_mag": N_MAG, "oversampling": OS, "room_taps": 128, "parallelism": f"batch-shard x{n}, no collective",
+            "l2": f"{N_SETS} rotating input sets (~{N_SETS * 26} MB) > 126 MB L2",
+            "checks": "value: input-range asserts off; e2e: on (reference behaviour, one host sync per call)"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def build_decoder(dev):
+    from golf_b200 import filters, noise, sf, synth
+
+    dec = sf.SourceFilterSynth(
+        synth.DownsampledIndexedGlottalFlowTable(hop_rate=10, in_channels=64, oversampling=OS, equal_energy=True,
+                                                 table_type="derivative", normalize_method="constant_power", align_peak=True,
+                                                 trainable=False, min_R_d=0.3, max_R_d=2.7, lf_v2=True, points=2048),
+        noise.StandardNormalNoise(), filters.LTVZeroPhaseFIRFilter("hanning", conv_method="direct", n_mag=N_MAG),
+        filters.LTVMinimumPhaseFilterPrecise(lpc_order=ORDER, lpc_parameterisation="rc2lpc"),
+        filters.LTIAcousticFilter(128, "fft"), subtract_harmonics=False)
+    dec.room_filter.kernel.data = room_kernel()
+    return dec.to(dev).eval()
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+
+    import golf_b200
+    from golf_b200 import functional as G
+    from golf_b200.audiotensor import AudioTensor
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- golf_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(2434 + rank)
+
+    dec = build_decoder(dev)
+    host_sets = [{k: v.pin_memory() for k, v in s.items()} for s in make_inputs(N_SETS, BATCH, seed=2434 + rank)]
+    dev_sets = [{k: v.to(dev) for k, v in s.items()} for s in host_sets]
+
+    def step_dev(s):
+        return dec(phase=AudioTensor(s["phase"], hop_length=1), harm_oscillator_params=(AudioTensor(s["w"], hop_length=2400),),
+                   noise_generator_params=(), noise_filter_params=(AudioTensor(s["log_mag"], hop_length=HOP),),
+                   end_filter_params=(AudioTensor(s["gain"], hop_length=HOP), AudioTensor(s["a"], hop_length=HOP)))
+
+    out_host = torch.empty(BATCH, T, dtype=torch.float32).pin_memory()
+
+    def step_e2e(s):
+        d = {k: v.to(dev, non_blocking=True) for k, v in s.items()}
+        y = step_dev(d).as_tensor()
+        out_host[:, : y.shape[1]].copy_(y, non_blocking=True)
+        return y
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    def timed(fn, sets, steps, warmup):
+        with torch.no_grad():
+            for i in range(warmup):
+                fn(sets[i % len(sets)])
+            barrier()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            l0 = golf_b200.launch_count()
+            ev[0].record()
+            for i in range(steps):
+                out = fn(sets[(warmup + i) % len(sets)])
+            ev[1].record()
+            barrier()
+            ms = ev[0].elapsed_time(ev[1])
+            launches = golf_b200.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, out
+
+    from golf_b200 import synth as gsynth
+
+    with ClockSampler(local) as clocks:
+        gsynth.CHECK_INPUTS = "off"   # device-resident arm: no host-side range asserts (no sync in the step)
+        ms, launches, out = timed(step_dev, dev_sets, args.steps, args.warmup)
+        gsynth.CHECK_INPUTS = "sync"  # end-to-end arm: the public API exactly as a caller gets it
+        ms_e2e, _, out_h = timed(step_e2e, host_sets, args.steps, args.warmup)
+    n_out = out.shape[1]
+    total = world * BATCH * T
+    value = total * args.steps / (ms * 1e-3)
+    e2e = total * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(v.numel() * 4 for v in host_sets[0].values())
+    d2h = BATCH * n_out * 4
+
+    # ---- dominant kernel alone: GOLF-ss chunk-response pass
+    roof = None
+    if rank == 0:
+        s = dev_sets[0]
+        src = torch.randn(BATCH, T - HOP, device=dev)
+        L = G.lpc_ss_length(src.shape[1], FRAMES, HOP)
+        with torch.no_grad():
+            for _ in range(3):
+                G._lpc_ss_fwd(src, s["gain"], s["a"], None, HOP, 0, passes=1)
+            torch.cuda.synchronize()
+            n = 20
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(n):
+                sd = dev_sets[i % N_SETS]
+                G._lpc_ss_fwd(src, sd["gain"], sd["a"], None, HOP, 0, passes=1)
+            e1.record()
+            torch.cuda.synchronize()
+        k_ms = e0.elapsed_time(e1) / n
+        alg_bytes = (8 + 4 * (ORDER + 1) / HOP) * BATCH * L
+        peak, src_peak = 6650.0, "fallback"
+        try:
+            peak, src_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))["ss_response_kernel"]["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        ach = alg_bytes / (k_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "ss_response_kernel<24,0> (GOLF-ss pass 1, timed alone, includes the per-call workspace alloc)",
+                "achieved": ach, "peak": peak, "peak_source": src_peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
+                "note": "FP32-issue/latency bound by design (M(M+1) FMA per sample for the time-parallel split), see DESIGN.md"}
+
+    if rank != 0:
+        return None
+    line = {
+        "metric": "audio samples/sec, GOLF-ss synthesis 24 kHz batch 32 x 2 s", "value": value, "unit": "samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(world), "clocks": clocks.summary(),
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "roofline": roof, "output_samples_per_utterance": int(n_out),
+        "rtf": (ms / args.steps * 1e-3) / (BATCH * SECONDS),
+    }
+    if world == 1 and not args.no_cpu:
+        val, cores, dt = run_cpu(args.cpu_steps, 1, BATCH)
+        line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_steps} full decoder passes of {BATCH} x {SECONDS:g} s on the host ({dt:.3f} s each), oracle port of the reference CPU path"}
+    if world > 1:
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="golf", choices=["golf", "reference"])
+    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", 0)) != 0:
+            return
+        args.steps = min(args.steps, 20)  # ~0.7 s per pass on 8 cores: keep the arm within minutes
+        print(json.dumps(cpu_line(args)))
+        return
+    line = run_gpu(args)
+    if line is not None:
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,168 @@
+// fir.cu -- the FIR stages of the GOLF decoder and two frame-rate helpers.
+//
+//   golf_noise_fir_fwd   models/filters.py:350-384  LTVZeroPhaseFIRFilter.forward: block k
+//                        (hop samples) = valid cross-correlation of the zero-padded input
+//                        with that frame's 510-tap kernel.  The reference unfolds to
+//                        [B*F, 749] and runs a grouped conv1d with B*F groups.
+//   golf_room_fir_fwd    models/filters.py:443-450  LTIAcousticFilter.forward.
+//   golf_linear_upsample models/audiotensor/audiotensor.py:11-17.
+//   golf_rc2lpc_fwd      models/utils.py:581-593 (+ tanh*max_abs of models/filters.py:80).
+//
+// Both FIRs are register-tiled correlations: a thread owns R=8 consecutive outputs, keeps
+// a 12-deep sliding input window in registers, and per 4 taps issues one LDS.128 of taps
+// (warp broadcast) and one LDS.128 of new input for 32 FMAs.  Input segment and taps are
+// staged once per CTA in shared memory (coalesced), so HBM sees each sample once:
+// algorithmic bytes per output sample = 4 (in) + 4 (out) + 4*K/hop (kernels) (+4 `add`).
+#include "fir_tile.cuh"
+
+namespace golf {
+
+// ---- time-varying block FIR ---------------------------------------------------------
+// grid (n_blocks, B), 32*ceil(hop/256) threads.  smem: xs[hop + K12 + 32] | ks[K12]
+__global__ void __launch_bounds__(256) noise_fir_kernel(const float* __restrict__ ex, int64_t ex_stride,
+                                                        const float* __restrict__ kernel, const float* __restrict__ add,
+                                                        int64_t add_stride, float* __restrict__ y, int T, int F, int K,
+                                                        int hop, int n_blocks, int K12, int xs_len) {
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;
+  float* ks = smem + xs_len;
+  const int k = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int p = (K - 1) / 2;
+  const float* exb = ex + (size_t)b * ex_stride;
+  const float* kb = kernel + ((size_t)b * F + k) * K;
+  const int start = k * hop - p;  // signal position of xs[0]
+  for (int i = tid; i < xs_len; i += blockDim.x) {
+    const int pos = start + i;
+    xs[i] = (pos >= 0 && pos < T && i < hop + K - 1) ? exb[pos] : 0.f;
+  }
+  for (int i = tid; i < K12; i += blockDim.x) ks[i] = i < K ? kb[i] : 0.f;
+  __syncthreads();
+  const int r0 = tid * kR;
+  if (r0 >= hop) return;
+  float acc[kR];
+#pragma unroll
+  for (int i = 0; i < kR; ++i) acc[i] = 0.f;
+  fir_tile8(xs + r0, ks, K12, acc);
+  float* yb = y + (size_t)b * n_blocks * hop + (size_t)k * hop;
+  const float* ab = add ? add + (size_t)b * add_stride + (size_t)k * hop : nullptr;
+#pragma unroll
+  for (int i = 0; i < kR; ++i)
+    if (r0 + i < hop) yb[r0 + i] = ab ? ab[r0 + i] + acc[i] : acc[i];
+}
+
+// ---- room FIR: out[t] = x[t] + sum_{j<n} k[j] x[t-n+j] ---------------------------------
+// grid (ceil(T/TILE), B), 128 threads, TILE = 1024 outputs.  Taps are staged as
+// [k_0 .. k_{n-1}, 1, 0...] so the direct path is tap n.
+constexpr int kRoomTile = 1024;
+__global__ void __launch_bounds__(128) room_fir_kernel(const float* __restrict__ x, const float* __restrict__ k,
+                                                       float* __restrict__ out, int T, int n, int K12, int xs_len) {
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;
+  float* ks = smem + xs_len;
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int t0 = blockIdx.x * kRoomTile;
+  const float* xb = x + (size_t)b * T;
+  for (int i = tid; i < xs_len; i += blockDim.x) {
+    const int pos = t0 - n + i;
+    // the reference pads x[:-1]: the last sample never feeds the taps (it is never needed:
+    // tap j < n reaches at most t-1 <= T-2), only the direct path
+    xs[i] = (pos >= 0 && pos < T) ? xb[pos] : 0.f;
+  }
+  for (int i = tid; i < K12; i += blockDim.x) ks[i] = i < n ? k[i] : (i == n ? 1.f : 0.f);
+  __syncthreads();
+  const int r0 = tid * kR;
+  float acc[kR];
+#pragma unroll
+  for (int i = 0; i < kR; ++i) acc[i] = 0.f;
+  fir_tile8(xs + r0, ks, K12, acc);
+  float* ob = out + (size_t)b * T;
+#pragma unroll
+  for (int i = 0; i < kR; ++i)
+    if (t0 + r0 + i < T) ob[t0 + r0 + i] = acc[i];
+}
+
+// ---- linear upsample -----------------------------------------------------------------
+__global__ void linear_upsample_kernel(const float* __restrict__ x, float* __restrict__ out, int n, int hop, int L,
+                                       float scale) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (d >= L) return;
+  const Lerp w = lerp_at(d, scale, n);
+  const float* xr = x + (size_t)r * n;
+  out[(size_t)r * L + d] = lerp_apply(w, xr[w.i0], xr[w.i1]);
+}
+
+// ---- reflection coefficients -> LPC (step-up), one thread per frame ----------------------
+constexpr int kMaxOrder = 64;
+__global__ void rc2lpc_kernel(const float* __restrict__ logits, float* __restrict__ a, int N, int M, float max_abs) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N) return;
+  float cur[kMaxOrder + 1], nxt[kMaxOrder + 1];
+  const float* lg = logits + (size_t)idx * M;
+  cur[0] = 1.f;
+  for (int n = 0; n < M; ++n) {
+    const float kn = __fmul_rn(tanhf(lg[n]), max_abs);
+    // poly (degree n) extended by a zero, plus kn * reversed
+    for (int i = 0; i <= n + 1; ++i) {
+      const float pi_ = i <= n ? cur[i] : 0.f;
+      const float pr = (n + 1 - i) <= n ? cur[n + 1 - i] : 0.f;
+      nxt[i] = __fadd_rn(pi_, __fmul_rn(kn, pr));
+    }
+    for (int i = 0; i <= n + 1; ++i) cur[i] = nxt[i];
+  }
+  for (int i = 0; i < M; ++i) a[(size_t)idx * M + i] = cur[i + 1];
+}
+
+}  // namespace golf
+
+using namespace golf;
+
+GOLF_API int golf_noise_fir_fwd(const float* ex, int64_t ex_stride, const float* kernel, const float* add,
+                                int64_t add_stride, float* y, int B, int T, int F, int K, int hop, void* stream) {
+  if (!ex || !kernel || !y || B <= 0 || T <= 0 || F <= 0 || K <= 0 || hop <= 0) return GOLF_ERR_INVALID;
+  const int p = (K - 1) / 2;
+  if (T + 2 * p < K + hop - 1) return GOLF_ERR_INVALID;
+  int n_blocks = (T + 2 * p - (K + hop - 1)) / hop + 1;
+  if (n_blocks > F) n_blocks = F;
+  if (hop > 2048) return GOLF_ERR_UNSUPPORTED;
+  const int K12 = ceil_div(K, 12) * 12;
+  const int threads = 32 * ceil_div(hop, 32 * kR);
+  const int xs_len = (int)align_up((size_t)threads * kR + K12 + 24, 4);
+  const size_t sm = (size_t)(xs_len + K12) * sizeof(float);
+  if (sm > 48 * 1024) return GOLF_ERR_UNSUPPORTED;
+  dim3 grid(n_blocks, B);
+  noise_fir_kernel<<<grid, threads, sm, (cudaStream_t)stream>>>(ex, ex_stride, kernel, add, add_stride, y, T, F, K, hop,
+                                                              n_blocks, K12, xs_len);
+  GOLF_CHECK_LAUNCH();
+  return GOLF_OK;
+}
+
+GOLF_API int golf_room_fir_fwd(const float* x, const float* k, float* out, int B, int T, int n, void* stream) {
+  if (!x || !k || !out || B <= 0 || T <= 0 || n <= 0) return GOLF_ERR_INVALID;
+  const int K12 = ceil_div(n + 1, 12) * 12;
+  const int xs_len = (int)align_up((size_t)kRoomTile + K12 + 24, 4);
+  const size_t sm = (size_t)(xs_len + K12) * sizeof(float);
+  if (sm > 48 * 1024) return GOLF_ERR_UNSUPPORTED;
+  dim3 grid(ceil_div(T, kRoomTile), B);
+  room_fir_kernel<<<grid, 128, sm, (cudaStream_t)stream>>>(x, k, out, T, n, K12, xs_len);
+  GOLF_CHECK_LAUNCH();
+  return GOLF_OK;
+}
+
+GOLF_API int golf_linear_upsample(const float* x, float* out, int R, int n, int hop, void* stream) {
+  if (!x || !out || R <= 0 || n <= 0 || hop <= 0) return GOLF_ERR_INVALID;
+  const int64_t L = (int64_t)(n - 1) * hop + 1;
+  if (L > INT32_MAX || R > 65535) return GOLF_ERR_UNSUPPORTED;
+  dim3 grid(ceil_div((int)L, 256), R);
+  linear_upsample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, out, n, hop, (int)L, lerp_scale(n, hop));
+  GOLF_CHECK_LAUNCH();
+  return GOLF_OK;
+}
+
+GOLF_API int golf_rc2lpc_fwd(const float* logits, float* a, int N, int M, float max_abs, void* stream) {
+  if (!logits || !a || N <= 0 || M <= 0) return GOLF_ERR_INVALID;
+  if (M > kMaxOrder) return GOLF_ERR_UNSUPPORTED;
+  rc2lpc_kernel<<<ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(logits, a, N, M, max_abs);
+  GOLF_CHECK_LAUNCH();
+  return GOLF_OK;
+}

@@ -1,0 +1,275 @@
+// lpc_ss.cu -- host side of GOLF-ss (plan, workspace, C ABI) plus the kernels that do
+// not depend on the tap-count bucket: the chunk stitch and the coefficient gradients.
+// The algorithm is described at the top of lpc_ss.cuh.
+#include "lpc_ss.cuh"
+
+namespace golf {
+// ------------------------------------------------------------------ pass 2 --------
+// One warp per sequence.  s_{p+1} = z_p + Phi_p s_p for p = 0..C-2; S[b][p] = s_p.
+// Phi_p/z_p ((M+1) x MP floats) stream through a ring of shared-memory stages
+// filled by the TMA unit (1-D cp.async.bulk, completion on an mbarrier per stage).
+
+__global__ void __launch_bounds__(32) ss_stitch_kernel(SsParams p, int MP) {
+  extern __shared__ __align__(128) float smem[];
+  const int lane = threadIdx.x, b = blockIdx.x;
+  const int slot = (MP + 1) * MP;           // floats per chunk block (multiple of 4)
+  const uint32_t bytes = (uint32_t)((p.M + 1) * MP * sizeof(float));
+  float* ring = smem;                        // [stages][slot]
+  float* svec = ring + kStitchStages * slot; // [MP] current state (broadcast reads)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(svec + ((MP + 3) / 4) * 4 + 4);
+  const int nresp = p.C - 1;
+  const float* wb = p.W + (size_t)b * nresp * slot;
+  float* sb = p.S + (size_t)b * p.C * MP;
+
+  if (lane == 0) {
+    for (int s = 0; s < kStitchStages; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  // initial state: zi (FORM0 only) or zeros
+  for (int k = lane; k < MP; k += 32) {
+    float v = (p.zi && k < p.M) ? p.zi[(size_t)b * p.M + k] : 0.f;
+    svec[k] = v;
+    sb[k] = v;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    for (int s = 0; s < kStitchStages && s < nresp; ++s) {
+      mbar_expect_tx(&bars[s], bytes);
+      bulk_g2s(ring + s * slot, wb + (size_t)s * slot, bytes, &bars[s]);
+    }
+  }
+  for (int pi = 0; pi < nresp; ++pi) {
+    const int stg = pi % kStitchStages;
+    mbar_wait(&bars[stg], (uint32_t)((pi / kStitchStages) & 1));
+    const float* blk = ring + stg * slot;
+    float nxt[2] = {0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int k = lane + 32 * q;  // state component computed by this lane
+      if (k < MP) {
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        int j = 0;
+        for (; j + 3 < p.M; j += 4) {
+          acc0 = __fmaf_rn(blk[(j + 0) * MP + k], svec[j + 0], acc0);
+          acc1 = __fmaf_rn(blk[(j + 1) * MP + k], svec[j + 1], acc1);
+          acc2 = __fmaf_rn(blk[(j + 2) * MP + k], svec[j + 2], acc2);
+          acc3 = __fmaf_rn(blk[(j + 3) * MP + k], svec[j + 3], acc3);
+        }
+        for (; j < p.M; ++j) acc0 = __fmaf_rn(blk[j * MP + k], svec[j], acc0);
+        nxt[q] = blk[p.M * MP + k] + ((acc0 + acc1) + (acc2 + acc3));
+      }
+    }
+    __syncwarp();  // everyone is done reading svec and this stage
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int k = lane + 32 * q;
+      if (k < MP) {
+        svec[k] = nxt[q];
+        sb[(size_t)(pi + 1) * MP + k] = nxt[q];
+      }
+    }
+    if (lane == 0 && pi + kStitchStages < nresp) {
+      mbar_expect_tx(&bars[stg], bytes);
+      bulk_g2s(ring + stg * slot, wb + (size_t)(pi + kStitchStages) * slot, bytes, &bars[stg]);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------- coefficient gradients ----
+// d_a[b,k,i]  = sum_t wk(t) * (-u[t] * y[t-1-i]),  d_gain[b,k] = sum_t wk(t) * u[t]*ex[t]
+// where wk(t) is the weight ATen's upsample gives frame k at time t (l0 on the i0
+// side, l1 on the i1 side).  One warp per (b, frame); lanes = taps (+ lane M for gain).
+__global__ void __launch_bounds__(128) ss_grad_kernel(const float* __restrict__ u, const float* __restrict__ y,
+                                                      const float* __restrict__ ex, int64_t ex_stride,
+                                                      const float* __restrict__ zi, float* __restrict__ d_gain,
+                                                      float* __restrict__ d_a, int B, int L, int F, int M, int hop,
+                                                      float scale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (wg >= B * F) return;
+  const int b = wg / F, k = wg % F;
+  const float* ub = u + (size_t)b * L;
+  const float* yb = y + (size_t)b * L;
+  const float* xb = ex + (size_t)b * ex_stride;
+  const float* zb = zi ? zi + (size_t)b * M : nullptr;
+  // support of frame k: t in ((k-1)*hop, (k+1)*hop); one extra sample each side covers
+  // ATen's floor() landing one frame low at t % hop == 0.
+  const int t_lo = max(0, (k - 1) * hop), t_hi = min(L - 1, (k + 1) * hop);
+  for (int i0 = 0; i0 <= M; i0 += 32) {  // taps in batches of 32 lanes; index M = gain
+    const int i = i0 + lane;
+    float acc = 0.f;
+    for (int t = t_lo; t <= t_hi; ++t) {
+      const Lerp w = lerp_at(t, scale, F);
+      float wk = 0.f;
+      if (w.i0 == k) wk += w.l0;
+      if (w.i1 == k) wk += w.l1;  // i0 == i1 == F-1 at the clamped end: both weights count
+      if (wk == 0.f) continue;
+      const float ut = ub[t];
+      if (i < M) {
+        const int ty = t - 1 - i;
+        const float yv = ty >= 0 ? yb[ty] : (zb ? zb[-ty - 1] : 0.f);
+        acc = __fmaf_rn(wk, -ut * yv, acc);
+      } else if (i == M) {
+        acc = __fmaf_rn(wk, ut * xb[t], acc);
+      }
+    }
+    if (i < M && d_a) d_a[((size_t)b * F + k) * M + i] = acc;
+    if (i == M && d_gain) d_gain[(size_t)b * F + k] = acc;
+  }
+}
+
+// d_zi[b,j] = -sum_{t<=j... } a_up[t, t+j] u[t]   (y[-1-j] enters sample t through tap t+j)
+__global__ void ss_dzi_kernel(const float* __restrict__ u, const float* __restrict__ a, float* __restrict__ d_zi, int B,
+                              int L, int F, int M, float scale) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * M) return;
+  const int b = idx / M, j = idx % M;
+  float acc = 0.f;
+  for (int t = 0; t + j < M && t < L; ++t) {
+    const Lerp w = lerp_at(t, scale, F);
+    const float c = lerp_apply(w, a[((size_t)b * F + w.i0) * M + t + j], a[((size_t)b * F + w.i1) * M + t + j]);
+    acc = __fmaf_rn(-c, u[(size_t)b * L + t], acc);
+  }
+  d_zi[idx] = acc;
+}
+
+// ------------------------------------------------------------------ host side -----
+struct SsPlan {
+  int MP, Lc, C, HB;
+  bool generic;
+  size_t w_floats, s_floats;
+};
+
+static const int kMPs[] = {4, 8, 12, 16, 20, 24, 32, 40};
+
+static bool make_plan(int B, int L, int M, int hop, int chunk, SsPlan* pl) {
+  if (B <= 0 || L <= 0 || M <= 0 || hop <= 0 || M > 40) return false;
+  int mp = 0, mp_any = 0;
+  for (int c : kMPs) {
+    if (c < M) continue;
+    if (!mp_any) mp_any = c;
+    if (hop % c == 0) { mp = c; break; }
+  }
+  pl->generic = (mp == 0);
+  pl->MP = mp ? mp : mp_any;
+  const int target = 240;
+  int Lc;
+  if (chunk > 0) {
+    Lc = chunk;
+    if (Lc % pl->MP != 0) return false;
+    if (!pl->generic && !(Lc % hop == 0 || hop % Lc == 0)) pl->generic = true;
+  } else if (!pl->generic) {
+    Lc = hop >= target ? hop : hop * ((target + hop - 1) / hop);
+    if (hop > 2 * target) {  // long frames: subdivide, keeping Lc | hop and MP | Lc
+      Lc = hop;
+      for (int d = 2; d <= hop / pl->MP; ++d)
+        if (hop % d == 0 && (hop / d) % pl->MP == 0 && hop / d >= target) Lc = hop / d;
+    }
+  } else {
+    Lc = pl->MP * ((target + pl->MP - 1) / pl->MP);
+  }
+  pl->Lc = Lc;
+  pl->HB = hop < Lc ? hop : Lc;
+  if (!pl->generic && pl->HB % pl->MP != 0) pl->generic = true;
+  pl->C = (L + Lc - 1) / Lc;
+  pl->w_floats = (size_t)B * (pl->C > 1 ? pl->C - 1 : 0) * (pl->MP + 1) * pl->MP;
+  pl->s_floats = (size_t)B * pl->C * pl->MP;
+  return true;
+}
+
+static size_t plan_bytes(const SsPlan& pl) { return align_up(pl.w_floats * 4, 256) + align_up(pl.s_floats * 4, 256); }
+
+
+// defined in lpc_ss_mp.cu, one translation unit per MP
+#define GOLF_DECL(MPV)                                                             \
+  extern template int launch_mp<MPV, 0>(const SsParams&, bool, int, cudaStream_t);      \
+  extern template int launch_mp<MPV, 1>(const SsParams&, bool, int, cudaStream_t);
+GOLF_DECL(4) GOLF_DECL(8) GOLF_DECL(12) GOLF_DECL(16) GOLF_DECL(20) GOLF_DECL(24) GOLF_DECL(32) GOLF_DECL(40)
+#undef GOLF_DECL
+template <int FORM>
+static int launch_form(const SsParams& p, int MP, bool generic, int passes, cudaStream_t st) {
+  switch (MP) {
+#define GOLF_CASE(MPV) \
+  case MPV:            \
+    return launch_mp<MPV, FORM>(p, generic, passes, st);
+    GOLF_CASE(4) GOLF_CASE(8) GOLF_CASE(12) GOLF_CASE(16) GOLF_CASE(20) GOLF_CASE(24) GOLF_CASE(32) GOLF_CASE(40)
+#undef GOLF_CASE
+  }
+  return GOLF_ERR_UNSUPPORTED;
+}
+
+}  // namespace golf
+
+using namespace golf;
+
+GOLF_API size_t golf_lpc_ss_workspace_bytes(int B, int L, int M, int hop, int chunk) {
+  SsPlan pl;
+  if (!make_plan(B, L, M, hop, chunk, &pl)) return 0;
+  return plan_bytes(pl);
+}
+
+GOLF_API int golf_lpc_ss_fwd_passes(const float* ex, int64_t ex_stride, const float* gain, const float* a, const float* zi,
+                                    float* y, int B, int L, int F, int M, int hop, int chunk, void* workspace,
+                                    size_t workspace_bytes, int passes, void* stream) {
+  if (!ex || !a || !y || B <= 0 || L <= 0 || F <= 0 || M <= 0 || hop <= 0) return GOLF_ERR_INVALID;
+  if (ex_stride < L || (int64_t)L > (int64_t)(F - 1) * hop + 1) return GOLF_ERR_INVALID;
+  SsPlan pl;
+  if (!make_plan(B, L, M, hop, chunk, &pl)) return GOLF_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes < plan_bytes(pl)) return GOLF_ERR_WORKSPACE;
+  if (((uintptr_t)workspace & 15) != 0) return GOLF_ERR_INVALID;
+  SsParams p{};
+  p.in = ex, p.in_stride = ex_stride, p.gain = gain, p.a = a, p.out = y, p.out2 = nullptr, p.zi = zi;
+  p.W = reinterpret_cast<float*>(workspace);
+  p.S = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(pl.w_floats * 4, 256));
+  p.B = B, p.L = L, p.F = F, p.M = M, p.hop = hop, p.Lc = pl.Lc, p.C = pl.C, p.HB = pl.HB;
+  p.scale = lerp_scale(F, hop);
+  return launch_form<0>(p, pl.MP, pl.generic, passes, (cudaStream_t)stream);
+}
+
+GOLF_API int golf_lpc_ss_fwd(const float* ex, int64_t ex_stride, const float* gain, const float* a, const float* zi,
+                             float* y, int B, int L, int F, int M, int hop, int chunk, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  return golf_lpc_ss_fwd_passes(ex, ex_stride, gain, a, zi, y, B, L, F, M, hop, chunk, workspace, workspace_bytes, 7, stream);
+}
+
+GOLF_API size_t golf_lpc_ss_bwd_workspace_bytes(int B, int L, int M, int hop, int chunk) {
+  SsPlan pl;
+  if (!make_plan(B, L, M, hop, chunk, &pl)) return 0;
+  return plan_bytes(pl) + align_up((size_t)B * L * 4, 256);  // + u
+}
+
+GOLF_API int golf_lpc_ss_bwd(const float* gy, const float* y, const float* ex, int64_t ex_stride, const float* gain,
+                             const float* a, const float* zi, float* d_ex, float* d_gain, float* d_a, float* d_zi,
+                             int B, int L, int F, int M, int hop, int chunk, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  if (!gy || !y || !ex || !a || B <= 0 || L <= 0 || F <= 0 || M <= 0 || hop <= 0) return GOLF_ERR_INVALID;
+  if (ex_stride < L || (int64_t)L > (int64_t)(F - 1) * hop + 1) return GOLF_ERR_INVALID;
+  SsPlan pl;
+  if (!make_plan(B, L, M, hop, chunk, &pl)) return GOLF_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes < plan_bytes(pl) + align_up((size_t)B * L * 4, 256)) return GOLF_ERR_WORKSPACE;
+  if (((uintptr_t)workspace & 15) != 0) return GOLF_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = reinterpret_cast<char*>(workspace);
+  SsParams p{};
+  p.in = gy, p.in_stride = L, p.gain = gain, p.a = a, p.zi = nullptr;
+  p.W = reinterpret_cast<float*>(ws);
+  p.S = reinterpret_cast<float*>(ws + align_up(pl.w_floats * 4, 256));
+  float* u = reinterpret_cast<float*>(ws + plan_bytes(pl));
+  p.out = u, p.out2 = d_ex;
+  p.B = B, p.L = L, p.F = F, p.M = M, p.hop = hop, p.Lc = pl.Lc, p.C = pl.C, p.HB = pl.HB;
+  p.scale = lerp_scale(F, hop);
+  int rc = launch_form<1>(p, pl.MP, pl.generic, 7, st);
+  if (rc) return rc;
+  if (d_gain || d_a) {
+    const int warps = 4;
+    ss_grad_kernel<<<ceil_div(B * F, warps), warps * 32, 0, st>>>(u, y, ex, ex_stride, zi, gain ? d_gain : nullptr, d_a,
+                                                                 B, L, F, M, hop, p.scale);
+    GOLF_CHECK_LAUNCH();
+  }
+  if (d_zi && zi) {
+    ss_dzi_kernel<<<ceil_div(B * M, 128), 128, 0, st>>>(u, a, d_zi, B, L, F, M, p.scale);
+    GOLF_CHECK_LAUNCH();
+  }
+  return GOLF_OK;
+}

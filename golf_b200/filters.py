@@ -1,0 +1,190 @@
+"""Drop-in filter modules of the GOLF decoder, backed by the sm_100a kernels.
+
+Same constructor arguments, `.ctrl` protocol, buffers/parameters and forward signatures as
+the reference classes of the same name (models/filters.py), so they are selected by
+`class_path: golf_b200.filters.<Name>` in the reference's YAML and load its checkpoints:
+
+  LTVMinimumPhaseFilterPrecise   models/filters.py:64-113   (GOLF-ss end filter)
+  LTVMinimumPhaseFilter          models/filters.py:116-195  (GOLF-ff end filter)
+  LTVZeroPhaseFIRFilter          models/filters.py:340-384  (noise filter)
+  LTIAcousticFilter              models/filters.py:426-456  (room filter)
+
+Inputs must live on a CUDA device (GolfError otherwise; no CPU fallback).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import functional as G
+from ._lib import GolfError
+from .audiotensor import AudioTensor, hop_of, like, plain
+from .ctrl import Controllable, wrap_ctrl_fn
+from .utils import biquads2lpc, get_logits2biquads, get_window_fn, rc2lpc
+
+__all__ = [
+    "FilterInterface",
+    "LTVFilterInterface",
+    "LTVMinimumPhaseFilterPrecise",
+    "LTVMinimumPhaseFilter",
+    "LTVZeroPhaseFIRFilter",
+    "LTIAcousticFilter",
+    "convert2samplewise",
+]
+
+
+class FilterInterface(Controllable):
+    def forward(self, ex, *args, **kwargs):
+        raise NotImplementedError
+
+
+class LTVFilterInterface(FilterInterface):
+    def reverse(self, ex, *args, **kwargs):
+        raise NotImplementedError
+
+
+def _logits2lpc(kind: str, max_abs: float):
+    if kind in ("coef", "conj", "real"):
+        to_bq = get_logits2biquads(kind, max_abs)
+        return lambda lg: biquads2lpc(to_bq(lg.view(lg.shape[0], lg.shape[1], -1, 2))), 0
+    if kind == "rc2lpc":
+        return lambda lg: rc2lpc(lg.tanh() * max_abs), 0
+    if kind == "lsp2lpc":
+
+        def fn(lg):
+            from diffsptk.functional import lsp2lpc  # optional third-party, as in the reference
+
+            return lsp2lpc(lg.softmax(-1).cumsum(-1).roll(1, -1) * torch.pi)[..., 1:]
+
+        return fn, 1
+    raise ValueError(f"Unknown lpc_parameterisation: {kind}")
+
+
+class LTVMinimumPhaseFilterPrecise(LTVFilterInterface):
+    """Sample-wise time-varying all-pole filter: y[t] = ex[t]*gain(t) - sum_i a_i(t) y[t-1-i]
+    with gain and a linearly interpolated from frame rate.  One fused CUDA path
+    (golf_lpc_ss_fwd/_bwd); the [B,T,M] coefficient tensor is never materialised."""
+
+    def __init__(self, lpc_order: int = None, lpc_parameterisation: str = "rc2lpc", max_abs_value: float = 1.0):
+        super().__init__()
+        to_lpc, extra = _logits2lpc(lpc_parameterisation, max_abs_value)
+        if lpc_order is not None:
+            self.ctrl = wrap_ctrl_fn(
+                split_size=(1, lpc_order + extra),
+                trsfm_fn=lambda log_gain, logits: (torch.exp(log_gain), logits.new_tensor(to_lpc(plain(logits)))),
+            )
+
+    def forward(self, ex, gain, a):
+        assert ex.ndim == 2 and gain.ndim == 2 and a.ndim == 3
+        assert a.shape[1] == gain.shape[1]
+        hop, ex_hop = hop_of(gain), hop_of(ex)
+        assert hop % ex_hop == 0 and hop_of(a, hop) == hop, (ex_hop, hop, hop_of(a))
+        y = G.lpc_ss(plain(ex), plain(gain), plain(a), hop // ex_hop)
+        return like(ex, y, ex_hop)
+
+    def reverse(self, ex, y, gain, a) -> Tuple[AudioTensor, AudioTensor]:
+        """inverse-filter the target (models/filters.py:186-195): returns (ex*gain, A(z) y)"""
+        return _reverse(ex, y, gain, a)
+
+
+def _reverse(ex, y, gain, a):
+    resid = G.lpc_inverse(plain(y), plain(a), hop_of(a) // hop_of(y))
+    return ex * gain, like(y, resid, hop_of(y))
+
+
+class LTVMinimumPhaseFilter(LTVMinimumPhaseFilterPrecise):
+    """Frame-wise variant: windows of `window_length` every hop, per-frame LTI all-pole from
+    zero state, windowed overlap-add, normalised (golf_lpc_ff_fwd).  The reference keeps a
+    dense diag(window) buffer `_kernel` (non-persistent); only the window itself is kept
+    here, under the same non-persistent status so state dicts stay interchangeable."""
+
+    def __init__(self, window: str, window_length: int, centred: bool = True, **kwargs):
+        super().__init__(**kwargs)
+        self.register_buffer("_window", get_window_fn(window)(window_length).float(), persistent=False)
+        self.centred = centred
+
+    def forward(self, ex, gain, a):
+        assert a.shape[1] == gain.shape[1]
+        hop = hop_of(gain) // hop_of(ex)
+        W = self._window.shape[0]
+        assert W >= hop * 2, f"{W} < {hop * 2}"
+        x = plain(ex)
+        if not self.centred:
+            x = x[..., hop // 2 :]
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (ex, gain, a)):
+            raise GolfError(
+                "LTVMinimumPhaseFilter: the frame-wise CUDA path is forward-only in this build; "
+                "train with LTVMinimumPhaseFilterPrecise (differentiable) or wrap the call in torch.no_grad()"
+            )
+        y = G.lpc_ff(x, plain(gain), plain(a), self._window, hop)
+        if not self.centred:
+            y = F.pad(y[:, None], (hop // 2, 0), "reflect")[:, 0]
+        return like(ex, y, hop_of(ex))
+
+
+class LTVZeroPhaseFIRFilter(LTVFilterInterface):
+    """Time-varying zero-phase FIR from log-magnitudes: kernel_k = window * fftshift(irfft(exp(
+    log_mag_k))) (frame rate, cuFFT) applied block-wise by golf_noise_fir_fwd.  `add` fuses
+    the following `harm + filtered_noise` (models/sf.py:53-56)."""
+
+    def __init__(self, window: str, conv_method: str = "direct", n_mag: int = None):
+        super().__init__()
+        if conv_method not in ("direct", "fft"):
+            raise ValueError(f"Unknown conv_method: {conv_method}")
+        self.window_fn = get_window_fn(window)
+        if n_mag is not None:
+            self.ctrl = wrap_ctrl_fn(split_size=(n_mag,), trsfm_fn=lambda x: (x,))
+
+    @staticmethod
+    def get_zero_phase_fir(log_mag: torch.Tensor) -> torch.Tensor:
+        fir = torch.fft.irfft(torch.exp(log_mag) + 0j, dim=-1)
+        return torch.fft.fftshift(fir, dim=-1)
+
+    def windowing(self, kernel: torch.Tensor) -> torch.Tensor:
+        return kernel * self.window_fn(kernel.shape[-1], device=kernel.device, dtype=kernel.dtype)
+
+    def forward(self, ex, log_mag, add=None):
+        hop = hop_of(log_mag) // hop_of(ex)
+        kernel = self.windowing(self.get_zero_phase_fir(plain(log_mag)))
+        if torch.is_grad_enabled() and (kernel.requires_grad or ex.requires_grad):
+            raise GolfError("LTVZeroPhaseFIRFilter: forward-only in this build (wrap in torch.no_grad())")
+        y = G.ltv_fir_blocks(plain(ex), kernel, hop, None if add is None else plain(add))
+        return like(ex, y, hop_of(ex))
+
+
+class LTIAcousticFilter(FilterInterface):
+    """Learned room response: out = ex + conv(ex delayed, kernel) with `length-1` free taps
+    (parameter name `kernel`, as in the checkpoints)."""
+
+    def __init__(self, length: int, conv_method: str = "direct"):
+        super().__init__()
+        if conv_method not in ("direct", "fft"):
+            raise ValueError(f"Unknown conv_method: {conv_method}")
+        self.kernel = nn.Parameter(torch.zeros(length - 1))
+        self._padding = length - 1
+
+    def forward(self, ex):
+        if torch.is_grad_enabled() and (self.kernel.requires_grad or ex.requires_grad):
+            raise GolfError("LTIAcousticFilter: forward-only in this build (wrap in torch.no_grad())")
+        return like(ex, G.room_fir(plain(ex), self.kernel), hop_of(ex))
+
+    @property
+    def impulse_response(self):
+        return torch.cat([self.kernel, torch.ones(1, device=self.kernel.device)]).flip(0)
+
+
+def convert2samplewise(config: dict) -> dict:
+    """Rewrite a decoder config so frame-wise filters become their sample-wise twins
+    (models/filters.py:793-809): GOLF-ff weights evaluated as GOLF-ss ("GOLF-fs")."""
+    for key, value in list(config.items()):
+        if key == "class_path" and ".LTVMinimumPhaseFilter" in value and not value.endswith("Precise"):
+            config["class_path"] = value.rsplit(".", 1)[0] + ".LTVMinimumPhaseFilterPrecise"
+            for k in ("window", "window_length", "centred"):
+                config.get("init_args", {}).pop(k, None)
+            return config
+        if isinstance(value, dict):
+            config[key] = convert2samplewise(value)
+    return config

@@ -1,0 +1,286 @@
+"""Tensor-level entry points over the C ABI (include/golf_b200.h).
+
+Functional twins of what the reference's hot path calls:
+  sample_wise_lpc(x, a, zi)       torchlpc.sample_wise_lpc        (models/filters.py:112)
+  lpc_ss(ex, gain, a, hop)        LTVMinimumPhaseFilterPrecise    (models/filters.py:99-113)
+  lpc_ff(ex, gain, a, hop, win)   LTVMinimumPhaseFilter           (models/filters.py:131-184)
+  biquad_ff(...)                  BatchSecondOrderLPCSynth        (models/lpc.py:94-131)
+  lpc_inverse(y, a, hop)          reverse()/fir_filt              (models/filters.py:186-195)
+  ltv_fir_blocks(ex, kernel, hop) LTVZeroPhaseFIRFilter           (models/filters.py:360-384)
+  room_fir(x, k)                  LTIAcousticFilter               (models/filters.py:443-450)
+  glottal_osc(...)                IndexedGlottalFlowTable         (models/synth.py:213-263)
+  wavetable_read(...)             GlottalFlowTable.generate       (models/synth.py:124-177)
+
+Every function requires CUDA float32 tensors and raises otherwise -- there is no
+CPU path in this package (the CPU restatement lives in oracle/, test-only).
+Kernels are enqueued on torch's current stream.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import GolfError, check
+
+
+def _cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise GolfError(f"{name}: expected a CUDA tensor (golf_b200 has no CPU path), got {getattr(t, 'device', type(t))}")
+    if t.dtype != torch.float32:
+        raise GolfError(f"{name}: expected float32, got {t.dtype}")
+    t = t.detach()
+    if type(t) is not torch.Tensor:  # AudioTensor and friends: plain view of the same storage
+        t = t.as_subclass(torch.Tensor)
+    return t.contiguous()
+
+
+def _rows(t: torch.Tensor, name: str) -> torch.Tensor:
+    """[B,T] with unit inner stride; the row stride may exceed T (views are fine)."""
+    t = _cuda_f32_view(t, name)
+    return t if t.stride(1) == 1 and t.stride(0) >= t.shape[1] else t.contiguous()
+
+
+def _cuda_f32_view(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise GolfError(f"{name}: expected a CUDA tensor (golf_b200 has no CPU path), got {getattr(t, 'device', type(t))}")
+    if t.dtype != torch.float32:
+        raise GolfError(f"{name}: expected float32, got {t.dtype}")
+    t = t.detach()
+    return t.as_subclass(torch.Tensor) if type(t) is not torch.Tensor else t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------- GOLF-ss
+def lpc_ss_length(t_ex: int, frames: int, hop: int) -> int:
+    return min(int(t_ex), (int(frames) - 1) * int(hop) + 1)
+
+
+def _lpc_ss_fwd(ex, gain, a, zi, hop: int, chunk: int = 0, passes: int = 7):
+    ex = _rows(ex, "ex")
+    a = _cuda_f32(a, "a")
+    gain = None if gain is None else _cuda_f32(gain, "gain")
+    zi = None if zi is None else _cuda_f32(zi, "zi")
+    B, Tex = ex.shape
+    Fr, M = a.shape[1], a.shape[2]
+    if a.shape[0] != B or (gain is not None and tuple(gain.shape) != (B, Fr)) or (zi is not None and tuple(zi.shape) != (B, M)):
+        raise GolfError(f"lpc_ss: inconsistent shapes ex{tuple(ex.shape)} gain{None if gain is None else tuple(gain.shape)} a{tuple(a.shape)}")
+    L = lpc_ss_length(Tex, Fr, hop)
+    y = torch.empty(B, L, dtype=torch.float32, device=ex.device)
+    lib = _lib.lib()
+    nbytes = lib.golf_lpc_ss_workspace_bytes(B, L, M, hop, chunk)
+    if nbytes == 0:
+        raise GolfError(f"lpc_ss: unsupported configuration B={B} L={L} M={M} hop={hop} chunk={chunk}")
+    ws = _workspace(nbytes, ex.device)
+    with torch.cuda.device(ex.device):
+        rc = lib.golf_lpc_ss_fwd_passes(_ptr(ex), ex.stride(0), _ptr(gain), _ptr(a), _ptr(zi), _ptr(y), B, L, Fr, M, hop, chunk,
+                                        _ptr(ws), ws.numel(), passes, _stream())
+    check(rc, "golf_lpc_ss_fwd")
+    return y
+
+
+def _lpc_ss_bwd(gy, y, ex, gain, a, zi, hop: int, need, chunk: int = 0):
+    """need = (ex, gain, a, zi) booleans -> gradients (None where not needed)."""
+    gy = _cuda_f32(gy, "gy")
+    y = _cuda_f32(y, "y")
+    ex = _rows(ex, "ex")
+    a = _cuda_f32(a, "a")
+    gain = None if gain is None else _cuda_f32(gain, "gain")
+    zi = None if zi is None else _cuda_f32(zi, "zi")
+    B, L = y.shape
+    Fr, M = a.shape[1], a.shape[2]
+    dev = y.device
+    d_ex = torch.empty(B, L, dtype=torch.float32, device=dev) if need[0] else None
+    d_gain = torch.empty(B, Fr, dtype=torch.float32, device=dev) if (need[1] and gain is not None) else None
+    d_a = torch.empty(B, Fr, M, dtype=torch.float32, device=dev) if need[2] else None
+    d_zi = torch.empty(B, M, dtype=torch.float32, device=dev) if (need[3] and zi is not None) else None
+    lib = _lib.lib()
+    ws = _workspace(lib.golf_lpc_ss_bwd_workspace_bytes(B, L, M, hop, chunk), dev)
+    with torch.cuda.device(dev):
+        rc = lib.golf_lpc_ss_bwd(_ptr(gy), _ptr(y), _ptr(ex), ex.stride(0), _ptr(gain), _ptr(a), _ptr(zi), _ptr(d_ex),
+                                 _ptr(d_gain), _ptr(d_a), _ptr(d_zi), B, L, Fr, M, hop, chunk, _ptr(ws), ws.numel(), _stream())
+    check(rc, "golf_lpc_ss_bwd")
+    return d_ex, d_gain, d_a, d_zi
+
+
+class _LpcSS(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ex, gain, a, zi, hop, chunk):
+        y = _lpc_ss_fwd(ex, gain, a, zi, hop, chunk)
+        ctx.save_for_backward(ex, gain, a, zi, y)
+        ctx.hop, ctx.chunk = hop, chunk
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        ex, gain, a, zi, y = ctx.saved_tensors
+        need = ctx.needs_input_grad[:4]
+        d_ex, d_gain, d_a, d_zi = _lpc_ss_bwd(gy, y, ex, gain, a, zi, ctx.hop, need, ctx.chunk)
+        if d_ex is not None and d_ex.shape[1] < ex.shape[1]:  # ex was longer than the filtered span
+            d_ex = torch.nn.functional.pad(d_ex, (0, ex.shape[1] - d_ex.shape[1]))
+        return d_ex, d_gain, d_a, d_zi, None, None
+
+
+def lpc_ss(ex, gain, a, hop: int, zi=None, chunk: int = 0) -> torch.Tensor:
+    """y[t] = ex[t]*up(gain)[t] - sum_i up(a)[t,i] y[t-1-i]; ex [B,T], gain [B,F], a [B,F,M] at
+    `hop`; returns [B, min(T,(F-1)*hop+1)].  Differentiable in ex, gain, a, zi."""
+    return _LpcSS.apply(ex, gain, a, zi, int(hop), int(chunk))
+
+
+def sample_wise_lpc(x, a, zi=None) -> torch.Tensor:
+    """torchlpc.sample_wise_lpc: x [B,T], a [B,T,M] sample-rate coefficients, zi [B,M]."""
+    if x.ndim != 2 or a.ndim != 3 or a.shape[:2] != x.shape:
+        raise GolfError(f"sample_wise_lpc: x{tuple(x.shape)} a{tuple(a.shape)}")
+    return _LpcSS.apply(x, None, a, zi, 1, 0)
+
+
+# ------------------------------------------------------------------------- GOLF-ff
+def lpc_ff(ex, gain, a, window, hop: int) -> torch.Tensor:
+    """Frame-wise filter + Hann OLA (forward only for now)."""
+    ex = _rows(ex, "ex")
+    gain, a, window = _cuda_f32(gain, "gain"), _cuda_f32(a, "a"), _cuda_f32(window, "window")
+    B, Tex = ex.shape
+    Fr, M = a.shape[1], a.shape[2]
+    win = window.numel()
+    Le = lpc_ss_length(Tex, Fr, hop)
+    n_frames = (Le + 2 * (win // 2) - win) // hop + 1
+    if n_frames > Fr:
+        raise AssertionError(f"{n_frames} frames but only {Fr} control frames")  # filters.py:157
+    out_len = (n_frames - 1) * hop + win - 2 * (win // 2)
+    y = torch.empty(B, out_len, dtype=torch.float32, device=ex.device)
+    with torch.cuda.device(ex.device):
+        rc = _lib.lib().golf_lpc_ff_fwd(_ptr(ex), ex.stride(0), _ptr(gain), _ptr(a), _ptr(window), _ptr(y), B, Tex, Fr, M,
+                                        hop, win, _stream())
+    check(rc, "golf_lpc_ff_fwd")
+    return y
+
+
+def biquad_ff(ex, gain, biquads, window, hop: int) -> torch.Tensor:
+    ex = _rows(ex, "ex")
+    gain, biquads, window = _cuda_f32(gain, "gain"), _cuda_f32(biquads, "biquads"), _cuda_f32(window, "window")
+    B, Tex = ex.shape
+    Fr, K = biquads.shape[1], biquads.shape[2]
+    win = window.numel()
+    pad = (win - hop) // 2
+    n_frames = (Tex + 2 * pad - win) // hop + 1
+    if n_frames > Fr:
+        raise AssertionError(f"{n_frames} frames but only {Fr} control frames")  # lpc.py:102-104
+    y = torch.empty(B, (n_frames - 1) * hop + win - 2 * pad, dtype=torch.float32, device=ex.device)
+    with torch.cuda.device(ex.device):
+        rc = _lib.lib().golf_biquad_ff_fwd(_ptr(ex), ex.stride(0), _ptr(gain), _ptr(biquads), _ptr(window), _ptr(y), B, Tex,
+                                           Fr, K, hop, win, _stream())
+    check(rc, "golf_biquad_ff_fwd")
+    return y
+
+
+def lpc_inverse(y, a, hop: int) -> torch.Tensor:
+    y = _rows(y, "y")
+    a = _cuda_f32(a, "a")
+    B, T = y.shape
+    Fr, M = a.shape[1], a.shape[2]
+    L = lpc_ss_length(T, Fr, hop)
+    r = torch.empty(B, L, dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        rc = _lib.lib().golf_lpc_inverse_fwd(_ptr(y), y.stride(0), _ptr(a), _ptr(r), B, L, Fr, M, hop, _stream())
+    check(rc, "golf_lpc_inverse_fwd")
+    return r
+
+
+# ---------------------------------------------------------------------- FIR stages
+def ltv_fir_blocks(ex, kernel, hop: int, add=None) -> torch.Tensor:
+    """Block FIR with per-frame kernels [B,F,K]; optional fused `add + result`."""
+    ex = _rows(ex, "ex")
+    kernel = _cuda_f32(kernel, "kernel")
+    B, T = ex.shape
+    Fr, K = kernel.shape[1], kernel.shape[2]
+    p = (K - 1) // 2
+    n_blocks = min((T + 2 * p - (K + hop - 1)) // hop + 1, Fr)
+    if add is not None:
+        add = _rows(add, "add")
+        if add.shape[1] < n_blocks * hop:
+            raise GolfError("ltv_fir_blocks: `add` shorter than the output")
+    y = torch.empty(B, n_blocks * hop, dtype=torch.float32, device=ex.device)
+    with torch.cuda.device(ex.device):
+        rc = _lib.lib().golf_noise_fir_fwd(_ptr(ex), ex.stride(0), _ptr(kernel), _ptr(add), 0 if add is None else add.stride(0),
+                                           _ptr(y), B, T, Fr, K, hop, _stream())
+    check(rc, "golf_noise_fir_fwd")
+    return y
+
+
+def room_fir(x, k) -> torch.Tensor:
+    x, k = _cuda_f32(x, "x"), _cuda_f32(k, "k")
+    B, T = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().golf_room_fir_fwd(_ptr(x), _ptr(k), _ptr(out), B, T, k.numel(), _stream())
+    check(rc, "golf_room_fir_fwd")
+    return out
+
+
+# ---------------------------------------------------------------------- oscillator
+def glottal_osc(phase, phase_hop: int, w, w_hop: int, table, dec_kernel=None, oversampling: int = 1,
+                equal_energy: bool = False, accumulate: str = "fp64") -> torch.Tensor:
+    phase, w, table = _cuda_f32(phase, "phase"), _cuda_f32(w, "w"), _cuda_f32(table, "table")
+    dec_kernel = None if dec_kernel is None else _cuda_f32(dec_kernel, "dec_kernel")
+    B, Np = phase.shape
+    Fw = w.shape[1]
+    n_tab, P = table.shape
+    os_ = int(oversampling)
+    zeros = 0 if dec_kernel is None else (dec_kernel.numel() - 1) // (2 * os_)
+    N = (Np - 1) * phase_hop * os_ + 1
+    out = torch.empty(B, (N - 1) // os_ + 1, dtype=torch.float32, device=phase.device)
+    lib = _lib.lib()
+    ws = _workspace(lib.golf_glottal_osc_workspace_bytes(B, Np, phase_hop, Fw, P, os_), phase.device)
+    mode = {"fp64": 0, "aten_cpu": 1}[accumulate]
+    with torch.cuda.device(phase.device):
+        rc = lib.golf_glottal_osc_fwd(_ptr(phase), _ptr(w), _ptr(table), _ptr(dec_kernel), _ptr(out), B, Np, phase_hop, Fw,
+                                      w_hop, n_tab, P, os_, zeros, mode, 1 if equal_energy else 0, _ptr(ws), ws.numel(), _stream())
+    check(rc, "golf_glottal_osc_fwd")
+    return out
+
+
+def wavetable_read(wrapped, tables, hop_tab: int) -> torch.Tensor:
+    wrapped, tables = _cuda_f32(wrapped, "wrapped_phase"), _cuda_f32(tables, "tables")
+    B, N = wrapped.shape
+    R, P = tables.shape[1], tables.shape[2]
+    out = torch.empty_like(wrapped)
+    with torch.cuda.device(wrapped.device):
+        rc = _lib.lib().golf_wavetable_read_fwd(_ptr(wrapped), _ptr(tables), _ptr(out), B, N, R, P, hop_tab, _stream())
+    check(rc, "golf_wavetable_read_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------- helpers
+def linear_upsample(x, hop: int) -> torch.Tensor:
+    """F.interpolate(linear, align_corners=True) along the last dim (ATen arithmetic)."""
+    x = _cuda_f32(x, "x")
+    n = x.shape[-1]
+    rows = x.numel() // n
+    out = torch.empty(x.shape[:-1] + ((n - 1) * hop + 1,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().golf_linear_upsample(_ptr(x), _ptr(out), rows, n, hop, _stream())
+    check(rc, "golf_linear_upsample")
+    return out
+
+
+def rc2lpc(logits, max_abs: float = 1.0) -> torch.Tensor:
+    """a = step_up(tanh(logits)*max_abs), last dim = order (inference path, no autograd)."""
+    logits = _cuda_f32(logits, "logits")
+    M = logits.shape[-1]
+    a = torch.empty_like(logits)
+    with torch.cuda.device(logits.device):
+        rc = _lib.lib().golf_rc2lpc_fwd(_ptr(logits), _ptr(a), logits.numel() // M, M, float(max_abs), _stream())
+    check(rc, "golf_rc2lpc_fwd")
+    return a

@@ -1,0 +1,143 @@
+/*
+ * golf_b200.h -- C ABI of libgolf_b200.so: the B200 (sm_100a) implementation of
+ * GOLF's sample-recurrent synthesis hot path.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain device pointers,
+ * sizes and a CUDA stream (passed as void* == cudaStream_t); none allocates,
+ * none synchronises the device, all enqueue on the given stream and are
+ * CUDA-graph capturable.  Return value: 0 on success, a negative GOLF_ERR_* code
+ * otherwise (golf_strerror() names it).  All tensors are contiguous float32,
+ * row-major, in the layouts the reference's Python passes around.
+ *
+ * Reference interfaces replaced (paths under the reference repo iamycy/golf):
+ *   golf_lpc_ss_*            models/filters.py:99-113  LTVMinimumPhaseFilterPrecise.forward
+ *                            (ex*gain, upsample a, torchlpc.sample_wise_lpc) and its autograd
+ *                            with hop == 1, gain == NULL: torchlpc.sample_wise_lpc(x, a, zi)
+ *                            as called at models/filters.py:112,789 and models/lru/lru.py:15
+ *   golf_lpc_ff_*            models/filters.py:131-184 LTVMinimumPhaseFilter.forward
+ *                            (unfold, models/lpc.py:11-16 lpc_synthesis -> torchaudio lfilter, Hann OLA)
+ *   golf_biquad_ff_fwd       models/lpc.py:94-131     BatchSecondOrderLPCSynth.forward
+ *   golf_lpc_inverse_fwd     models/filters.py:186-195 reverse() + models/utils.py:433-441 fir_filt
+ *   golf_noise_fir_*         models/filters.py:350-384 LTVZeroPhaseFIRFilter.forward (block FIR)
+ *   golf_room_fir_*          models/filters.py:443-450 LTIAcousticFilter.forward
+ *   golf_glottal_osc_fwd     models/synth.py:213-263   IndexedGlottalFlowTable.forward
+ *   golf_wavetable_read_fwd  models/synth.py:124-177   GlottalFlowTable.generate
+ *   golf_linear_upsample     models/audiotensor/audiotensor.py:11-17 linear_upsample
+ *   golf_rc2lpc_fwd          models/utils.py:581-593   rc2lpc (with the tanh*max_abs of filters.py:80)
+ */
+#ifndef GOLF_B200_H_
+#define GOLF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GOLF_B200_ABI_VERSION 1
+
+enum {
+  GOLF_OK = 0,
+  GOLF_ERR_INVALID = -1,      /* bad shape / null pointer / misaligned buffer            */
+  GOLF_ERR_UNSUPPORTED = -2,  /* valid request outside what the kernels are built for    */
+  GOLF_ERR_WORKSPACE = -3,    /* workspace too small (ask golf_*_workspace_bytes)        */
+  GOLF_ERR_CUDA = -4          /* a CUDA runtime call or launch failed (see golf_last_cuda_error) */
+};
+
+int golf_abi_version(void);
+const char *golf_strerror(int code);
+/* last cudaError_t seen by this library on the calling thread (0 = none) */
+int golf_last_cuda_error(void);
+/* number of kernel launches issued by this library since load (all threads) */
+uint64_t golf_launch_count(void);
+
+/* ------------------------------------------------------------------ GOLF-ss ---- */
+/* Time-varying all-pole filter on FRAME-RATE controls, coefficients interpolated
+ * to sample rate in-kernel with ATen's align_corners=True arithmetic:
+ *   e[t] = ex[t] * up(gain)[t];  y[t] = e[t] - sum_{i<M} up(a)[t,i] * y[t-1-i]
+ * ex [B,T_ex] (row stride ex_stride), gain [B,F] (may be NULL == 1), a [B,F,M],
+ * zi [B,M] or NULL (zi[:,j] = y[-1-j]), y [B,L] with L = min(T_ex,(F-1)*hop+1)
+ * (pass L; it is checked).  hop == 1 gives torchlpc.sample_wise_lpc exactly.
+ * chunk = 0 lets the library pick the time-chunk length. */
+size_t golf_lpc_ss_workspace_bytes(int B, int L, int M, int hop, int chunk);
+int golf_lpc_ss_fwd(const float *ex, int64_t ex_stride, const float *gain, const float *a,
+                    const float *zi, float *y, int B, int L, int F, int M, int hop,
+                    int chunk, void *workspace, size_t workspace_bytes, void *stream);
+/* Same, running only the selected passes (bit 0: chunk responses, bit 1: stitch, bit 2:
+ * solve) -- for per-kernel timing in bench.py; passes == 7 is golf_lpc_ss_fwd. */
+int golf_lpc_ss_fwd_passes(const float *ex, int64_t ex_stride, const float *gain,
+                           const float *a, const float *zi, float *y, int B, int L, int F,
+                           int M, int hop, int chunk, void *workspace, size_t workspace_bytes,
+                           int passes, void *stream);
+/* Adjoint.  Inputs: gy = dL/dy [B,L], saved y, ex, gain, a, zi.  Outputs (any may
+ * be NULL): d_ex [B,L], d_gain [B,F], d_a [B,F,M], d_zi [B,M]. */
+size_t golf_lpc_ss_bwd_workspace_bytes(int B, int L, int M, int hop, int chunk);
+int golf_lpc_ss_bwd(const float *gy, const float *y, const float *ex, int64_t ex_stride,
+                    const float *gain, const float *a, const float *zi, float *d_ex,
+                    float *d_gain, float *d_a, float *d_zi, int B, int L, int F, int M,
+                    int hop, int chunk, void *workspace, size_t workspace_bytes,
+                    void *stream);
+
+/* ------------------------------------------------------------------ GOLF-ff ---- */
+/* Frame-wise filter: e = ex*up(gain); frames of `win` samples every `hop` from
+ * e zero-padded by win/2 each side; per-frame LTI all-pole from zero state with
+ * a[b,k,:]; Hann(periodic) overlap-add, divided by the overlap-added window.
+ * n_frames = (L_e + 2*(win/2) - win)/hop + 1 <= F where L_e = min(T_ex,(F-1)*hop+1);
+ * y [B, (n_frames-1)*hop].  Requires win == 4*hop (the reference's shipped ratio).
+ * window: [win] device array (the module's window buffer). */
+int golf_lpc_ff_fwd(const float *ex, int64_t ex_stride, const float *gain, const float *a,
+                    const float *window, float *y, int B, int T_ex, int F, int M, int hop,
+                    int win, void *stream);
+/* Cascade of K second-order all-pole sections per frame (biquads [B,F,K,3]),
+ * gain applied per frame, zero-pad (win-hop)/2, Hann OLA + normalise. */
+int golf_biquad_ff_fwd(const float *ex, int64_t ex_stride, const float *gain,
+                       const float *biquads, const float *window, float *y, int B, int T_ex,
+                       int F, int K, int hop, int win, void *stream);
+
+/* Inverse (analysis) filter: r[t] = y[t] + sum_i up(a)[t,i] y[t-1-i], [B,L]. */
+int golf_lpc_inverse_fwd(const float *y, int64_t y_stride, const float *a, float *r, int B,
+                         int L, int F, int M, int hop, void *stream);
+
+/* -------------------------------------------------------------- FIR stages ---- */
+/* Block-wise time-varying FIR: output block k (hop samples) is the valid
+ * cross-correlation of ex zero-padded by (K-1)/2 with kernel[b,k,:];
+ * n_blocks = min((T + 2*((K-1)/2) - (K+hop-1))/hop + 1, F); y [B, n_blocks*hop].
+ * If add != NULL ([B, >= n_blocks*hop], row stride add_stride) it is added to the
+ * result (fuses `harm + noise_filter(noise)`, models/sf.py:53-56). */
+int golf_noise_fir_fwd(const float *ex, int64_t ex_stride, const float *kernel,
+                       const float *add, int64_t add_stride, float *y, int B, int T, int F,
+                       int K, int hop, void *stream);
+/* out[t] = x[t] + sum_{j<n} k[j] x[t-n+j]   (n = length-1 learned taps) */
+int golf_room_fir_fwd(const float *x, const float *k, float *out, int B, int T, int n,
+                      void *stream);
+
+/* -------------------------------------------------------------- oscillator ---- */
+/* Glottal-flow wavetable oscillator at `os`x oversampling.
+ * phase [B,Np] cycles/sample at hop phase_hop; w [B,Fw] in [0,1] at hop w_hop;
+ * table [n_tab, P]; dec_kernel [2*zeros*os+1] (os > 1).  N_os = (Np-1)*phase_hop*os+1
+ * oversampled samples, out [B, (N_os-1)/os+1].
+ * accumulate: 0 = float64 running phase, wrapped in float64 (default; closer to exact
+ * than the reference), 1 = "aten_cpu": float64 running sum rounded to float32
+ * before `% 1`, the arithmetic of ATen's CPU cumsum (parity checks).
+ * flags bit0: equal_energy (multiply by rsqrt(upsampled phase)). */
+size_t golf_glottal_osc_workspace_bytes(int B, int Np, int phase_hop, int Fw, int P, int os);
+int golf_glottal_osc_fwd(const float *phase, const float *w, const float *table,
+                         const float *dec_kernel, float *out, int B, int Np, int phase_hop,
+                         int Fw, int w_hop, int n_tab, int P, int os, int zeros,
+                         int accumulate, int flags, void *workspace, size_t workspace_bytes,
+                         void *stream);
+/* GlottalFlowTable.generate: wrapped [B,N] in [0,1), tables [B,R,P] at hop hop_tab. */
+int golf_wavetable_read_fwd(const float *wrapped, const float *tables, float *out, int B,
+                            int N, int R, int P, int hop_tab, void *stream);
+
+/* ------------------------------------------------------- frame-rate helpers ---- */
+/* x [R,n] -> out [R,(n-1)*hop+1], F.interpolate(linear, align_corners=True) */
+int golf_linear_upsample(const float *x, float *out, int R, int n, int hop, void *stream);
+/* a = step_up(tanh(logits) * max_abs); logits, a: [N, M] */
+int golf_rc2lpc_fwd(const float *logits, float *a, int N, int M, float max_abs, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOLF_B200_H_ */

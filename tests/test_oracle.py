@@ -1,0 +1,146 @@
+"""CPU: pin the oracle (oracle/golf_oracle.py + .c) against the reference's outputs.
+
+* committed golden vectors produced by the UNMODIFIED reference (tests/golden/make_golden.py)
+* bit-exactness against the installed third-party ops the reference calls (torchaudio lfilter,
+  ATen linear interpolation)
+* live comparison with the reference modules when /root/reference is present
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import REL_TOL, T, golden, rel_rms, smooth, synthetic_controls
+
+
+def test_lti_matches_torchaudio_bitwise(oracle):
+    from torchaudio.functional import lfilter
+
+    g = torch.Generator().manual_seed(0)
+    _, a = synthetic_controls(1, 7, 22, seed=3)
+    a = a[0]
+    x = torch.randn(7, 960, generator=g)
+    A = torch.cat([torch.ones(7, 1), a], 1)
+    Bc = torch.zeros(7, 23)
+    Bc[:, 0] = 1
+    ref = lfilter(x, A, Bc, False)
+    assert torch.equal(oracle.allpole_lti(x, a), ref)
+
+
+def test_upsample_matches_aten_bitwise(oracle):
+    x = torch.randn(3, 201, generator=torch.Generator().manual_seed(1))
+    for hop in (240, 120, 4, 480):
+        ref = F.interpolate(x[:, None], (201 - 1) * hop + 1, mode="linear", align_corners=True)[:, 0]
+        assert torch.equal(oracle.linear_upsample_c(x, hop), ref)
+
+
+def test_ss_fused_equals_materialised(oracle):
+    gain, a = synthetic_controls(2, 41, 22, seed=5)
+    ex = torch.randn(2, 9700, generator=torch.Generator().manual_seed(2))
+    assert torch.equal(oracle.lpc_ss(ex, gain, a, 240), oracle.lpc_ss_fused(ex, gain, a, 240))
+
+
+def test_ss_constant_coefficients_equal_lfilter(oracle):
+    """cross-check (i) of SURVEY 8c: time-invariant coefficients must reduce to lfilter"""
+    from torchaudio.functional import lfilter
+
+    _, a = synthetic_controls(2, 1, 22, seed=7)
+    x = torch.randn(2, 5000, generator=torch.Generator().manual_seed(3))
+    A = a.expand(2, 5000, 22).contiguous()
+    y = oracle.sample_wise_lpc(x, A)
+    ref = lfilter(x, torch.cat([torch.ones(2, 1), a[:, 0]], 1), F.pad(torch.ones(2, 1), (0, 22)), False)
+    assert rel_rms(y, ref) < 2e-5  # same maths, opposite tap order: float32 rounding only
+
+
+def test_order1_is_leaky_integrator(oracle):
+    """cross-check (ii): sample_wise_lpc(u, -lambda, zi) == h_t = lambda_t h_{t-1} + u_t (lru.py:9-15)"""
+    g = torch.Generator().manual_seed(4)
+    u = torch.randn(2, 300, generator=g, dtype=torch.float64)
+    lam = torch.rand(2, 300, 1, generator=g, dtype=torch.float64) * 0.9
+    h0 = torch.randn(2, 1, generator=g, dtype=torch.float64)
+    y = oracle.sample_wise_lpc(u, -lam, h0)
+    h = h0[:, 0].clone()
+    for t in range(300):
+        h = lam[:, t, 0] * h + u[:, t]
+        assert torch.allclose(y[:, t], h, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("M", [8, 20, 22])
+def test_filters_against_reference_golden(oracle, M):
+    g = golden("filters_rand")
+    H = int(g["hop"])
+    ex, gain, a = T(g[f"ex_{M}"]), T(g[f"gain_{M}"]), T(g[f"a_{M}"])
+    assert torch.equal(oracle.lpc_ss(ex, gain, a, H), T(g[f"ss_{M}"]))  # same C loop as the golden run's stub
+    assert rel_rms(oracle.lpc_ff(ex, gain, a, H, 4 * H), T(g[f"ff_{M}"])) < 1e-6
+    assert rel_rms(oracle.lpc_ff(ex, gain, a, H, 4 * H, centred=False), T(g[f"ffnc_{M}"])) < 1e-6
+    assert rel_rms(oracle.lpc_inverse(T(g[f"target_{M}"]), a, H), T(g[f"inverse_{M}"])) < 1e-6
+
+
+def test_biquad_cascade_against_reference_golden(oracle):
+    g = golden("filters_rand")
+    y = oracle.biquad_ff(T(g["ex_8"]), T(g["gain_8"]), T(g["biquads_8"]), int(g["hop"]))
+    # 4 near-coincident pole pairs at radius 0.99: float32 itself is only good to ~1e-3 here
+    assert rel_rms(y, T(g["bq_cascade_8"])) < 5e-3
+    assert y.shape == g["bq_cascade_8"].shape
+
+
+@pytest.mark.parametrize("variant", ["ss", "ff"])
+def test_decoder_stages_against_reference_golden(oracle, variant):
+    g = golden(f"stages_{variant}")
+    table, Rd = oracle.glottal_table()
+    tb = golden("table")
+    assert np.abs(table[::9].numpy() - tb["table_rows"]).max() < 2e-6
+    assert np.abs(Rd.numpy() - tb["R_d_values"]).max() == 0
+    st = {}
+    out = oracle.source_filter_synth(
+        T(g["phase"]), int(g["phase_hop"]), T(g["w"]), int(g["w_hop"]), T(g["log_mag"]), T(g["gain"]), T(g["a"]),
+        int(g["hop"]), T(g["noise"]), table, T(g["room_kernel"]), variant=variant, stages=st)
+    assert rel_rms(st["harm"], T(g["harm"])) < 1e-6
+    assert rel_rms(st["noise_filtered"], T(g["noise_filtered"])) < 2e-6
+    # identical-input stage checks (the stage's own golden input)
+    src = T(g["harm"])[:, : g["noise_filtered"].shape[1]] + T(g["noise_filtered"])
+    lpc = oracle.lpc_ss(src, T(g["gain"]), T(g["a"]), int(g["hop"])) if variant == "ss" else \
+        oracle.lpc_ff(src, T(g["gain"]), T(g["a"]), int(g["hop"]), int(g["window_length"]))
+    assert rel_rms(lpc, T(g["lpc"])) < 1e-6
+    assert rel_rms(oracle.room_fir(T(g["lpc"]), T(g["room_kernel"])), T(g["out"])) < 1e-6
+    # end to end (errors of the early stages pass through a resonant filter)
+    assert rel_rms(out, T(g["out"])) < REL_TOL
+    assert out.shape == g["out"].shape
+
+
+def test_control_transforms(oracle):
+    from golf_b200 import utils as U
+
+    lg = torch.randn(2, 9, 22, generator=torch.Generator().manual_seed(0))
+    assert torch.equal(oracle.rc2lpc(torch.tanh(lg)), U.rc2lpc(torch.tanh(lg)))
+    bq_l = torch.randn(2, 9, 4, 2, generator=torch.Generator().manual_seed(1))
+    for rep in ("coef", "conj", "real"):
+        bq = oracle.logits2biquads(bq_l, rep, 0.99)
+        assert torch.allclose(bq, U.get_logits2biquads(rep, 0.99)(bq_l), atol=1e-7)
+        assert torch.allclose(oracle.biquads2lpc(bq), U.biquads2lpc(bq), atol=2e-6)
+
+
+@pytest.mark.reference
+def test_oracle_against_live_reference(oracle, reference):
+    """build container only: the restatement vs the reference modules on fresh inputs"""
+    from models.audiotensor import AudioTensor
+    from models.filters import LTIAcousticFilter, LTVMinimumPhaseFilter, LTVMinimumPhaseFilterPrecise, LTVZeroPhaseFIRFilter
+    from models.utils import rc2lpc
+
+    H, M, B, Tn = 120, 12, 2, 6000
+    Fr = Tn // H + 1
+    g = torch.Generator().manual_seed(11)
+    a = rc2lpc(torch.tanh(0.15 * smooth(torch.randn(B, Fr, M, generator=g))))
+    gain = torch.exp(smooth(torch.randn(B, Fr, generator=g)) - 6)
+    ex = torch.randn(B, Tn, generator=g)
+    A = (AudioTensor(ex), AudioTensor(gain, hop_length=H), AudioTensor(a, hop_length=H))
+    with torch.no_grad():
+        assert torch.equal(LTVMinimumPhaseFilterPrecise(lpc_order=M)(*A).as_tensor(), oracle.lpc_ss(ex, gain, a, H))
+        ff = LTVMinimumPhaseFilter(window="hanning", window_length=4 * H, lpc_order=M)(*A).as_tensor()
+        assert rel_rms(oracle.lpc_ff(ex, gain, a, H, 4 * H), ff) < 1e-6
+        lm = smooth(torch.randn(B, Fr, 65, generator=g)) - 4
+        nf = LTVZeroPhaseFIRFilter(window="hanning", n_mag=65)(AudioTensor(ex), AudioTensor(lm, hop_length=H)).as_tensor()
+        assert rel_rms(oracle.noise_fir(ex, lm, H), nf) < 2e-6
+        room = LTIAcousticFilter(128, "fft")
+        room.kernel.data = torch.randn(127, generator=g) * 0.05
+        assert rel_rms(oracle.room_fir(ex, room.kernel.data), room(AudioTensor(ex)).as_tensor()) < 1e-6
