@@ -120,6 +120,11 @@ class _AudioTensor(torch.Tensor):
     @classmethod
     def __torch_function__(cls, func, types, args=(), kwargs=None):
         kwargs = kwargs or {}
+        if not kwargs and len(args) == 1:  # attribute getters and unary ops: nothing to align
+            ret = super().__torch_function__(func, types, args, kwargs)
+            if isinstance(ret, _AudioTensor):
+                ret.hop_length = args[0].__dict__.get("hop_length", -1) if ret.ndim > 1 else -1
+            return ret
         leaves, spec = tree_flatten((args, kwargs))
         rated = [i for i, v in enumerate(leaves) if isinstance(v, _AudioTensor) and getattr(v, "hop_length", -1) > 0]
         if len(rated) > 1:
@@ -139,15 +144,22 @@ AudioTensor = _interop.ref_audiotensor.AudioTensor if _interop.INTEROP else _Aud
 
 
 def hop_of(x, default: int = 1) -> int:
-    return int(getattr(x, "hop_length", default))
+    return int(x.__dict__.get("hop_length", default)) if hasattr(x, "__dict__") else default
+
+
+_NoTF = torch._C.DisableTorchFunctionSubclass
 
 
 def plain(x: torch.Tensor) -> torch.Tensor:
-    """the underlying torch.Tensor (keeps autograd history)"""
-    return x.as_subclass(torch.Tensor) if type(x) is not torch.Tensor else x
+    """the underlying torch.Tensor (keeps autograd history); no __torch_function__ round trip"""
+    if type(x) is torch.Tensor:
+        return x
+    with _NoTF():
+        return x.as_subclass(torch.Tensor)
 
 
 def like(ref, data: torch.Tensor, hop_length: int = 1):
     """wrap `data` in the same AudioTensor class the caller handed us"""
-    cls = type(ref) if hasattr(ref, "hop_length") and isinstance(ref, torch.Tensor) and type(ref) is not torch.Tensor else AudioTensor
-    return cls(data, hop_length=hop_length)
+    cls = type(ref) if (type(ref) is not torch.Tensor and isinstance(ref, torch.Tensor) and "hop_length" in getattr(ref, "__dict__", {})) else AudioTensor
+    with _NoTF():
+        return cls(data, hop_length=hop_length)

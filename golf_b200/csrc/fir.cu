@@ -20,9 +20,10 @@ namespace golf {
 // ---- time-varying block FIR ---------------------------------------------------------
 // grid (n_blocks, B), 32*ceil(hop/256) threads.  smem: xs[hop + K12 + 32] | ks[K12]
 __global__ void __launch_bounds__(256) noise_fir_kernel(const float* __restrict__ ex, int64_t ex_stride,
-                                                        const float* __restrict__ kernel, const float* __restrict__ add,
-                                                        int64_t add_stride, float* __restrict__ y, int T, int F, int K,
-                                                        int hop, int n_blocks, int K12, int xs_len) {
+                                                        const float* __restrict__ kernel, const float* __restrict__ window,
+                                                        const float* __restrict__ add, int64_t add_stride,
+                                                        float* __restrict__ y, int T, int F, int K, int hop, int n_blocks,
+                                                        int K12, int xs_len) {
   extern __shared__ __align__(16) float smem[];
   float* xs = smem;
   float* ks = smem + xs_len;
@@ -35,7 +36,12 @@ __global__ void __launch_bounds__(256) noise_fir_kernel(const float* __restrict_
     const int pos = start + i;
     xs[i] = (pos >= 0 && pos < T && i < hop + K - 1) ? exb[pos] : 0.f;
   }
-  for (int i = tid; i < K12; i += blockDim.x) ks[i] = i < K ? kb[i] : 0.f;
+  // taps: either final, or (window given) the raw irfft output: fftshift + windowing fused here
+  for (int i = tid; i < K12; i += blockDim.x) {
+    float v = 0.f;
+    if (i < K) v = window ? __fmul_rn(kb[(i + K / 2) % K], window[i]) : kb[i];
+    ks[i] = v;
+  }
   __syncthreads();
   const int r0 = tid * kR;
   if (r0 >= hop) return;
@@ -81,6 +87,143 @@ __global__ void __launch_bounds__(128) room_fir_kernel(const float* __restrict__
     if (t0 + r0 + i < T) ob[t0 + r0 + i] = acc[i];
 }
 
+
+// ---- adjoints of the block FIR --------------------------------------------------------
+// d_kernel[b,k,j] = sum_r gy[k*hop + r] * xpad[k*hop + r + j]: the same correlation with gy as
+// the taps.  One CTA per (block, utterance), threads own 8 consecutive j.
+__global__ void __launch_bounds__(128) noise_fir_dkernel_kernel(const float* __restrict__ gy, const float* __restrict__ ex,
+                                                                int64_t ex_stride, float* __restrict__ d_kernel, int T, int F,
+                                                                int K, int hop, int n_blocks, int H12, int xs_len) {
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;
+  float* gs = smem + xs_len;
+  const int k = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int p = (K - 1) / 2;
+  const float* exb = ex + (size_t)b * ex_stride;
+  const float* gb = gy + (size_t)b * n_blocks * hop + (size_t)k * hop;
+  const int start = k * hop - p;
+  for (int i = tid; i < xs_len; i += blockDim.x) {
+    const int pos = start + i;
+    xs[i] = (pos >= 0 && pos < T && i < hop + K - 1) ? exb[pos] : 0.f;
+  }
+  for (int i = tid; i < H12; i += blockDim.x) gs[i] = i < hop ? gb[i] : 0.f;
+  __syncthreads();
+  for (int j0 = tid * kR; j0 < K; j0 += blockDim.x * kR) {
+    float acc[kR];
+#pragma unroll
+    for (int i = 0; i < kR; ++i) acc[i] = 0.f;
+    fir_tile8(xs + j0, gs, H12, acc);
+    float* dk = d_kernel + ((size_t)b * F + k) * K;
+#pragma unroll
+    for (int i = 0; i < kR; ++i)
+      if (j0 + i < K) dk[j0 + i] = acc[i];
+  }
+}
+
+// d_ex[u - p] = sum_v kernel[block(v)][u - v] gy[v]: every input-gradient sample gathers from the
+// (up to ceil((K+hop-1)/hop)) blocks whose windows cover it.  One CTA per hop-sized tile of u (padded
+// coordinates); per contributing block one register-tiled correlation of the block's gy (zero
+// outside) with the reversed taps.  Deterministic (no atomics).
+__global__ void __launch_bounds__(256) noise_fir_dex_kernel(const float* __restrict__ gy, const float* __restrict__ kernel,
+                                                            float* __restrict__ d_ex, int T, int F, int K, int hop, int n_blocks,
+                                                            int K12, int gs_len) {
+  extern __shared__ __align__(16) float smem[];
+  float* gs = smem;           // gy of one block, zero-padded by K12 in front and 24 behind
+  float* ks = smem + gs_len;  // reversed taps
+  const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int p = (K - 1) / 2;
+  const int u0 = tile * hop;  // padded coordinate of the first output of this tile
+  const int r0 = tid * kR;
+  float acc[kR];
+#pragma unroll
+  for (int i = 0; i < kR; ++i) acc[i] = 0.f;
+  const int k_lo = max(0, (u0 - (K - 1)) / hop - 1), k_hi = min(n_blocks - 1, (u0 + hop - 1) / hop);
+  for (int k = k_lo; k <= k_hi; ++k) {
+    // out[u] += sum_j kern_k[j] * gy_k[u - k*hop - j],  0 <= u - k*hop - j < hop
+    // as a correlation: x[m] = gy_k[m - K12 + (u0 - k*hop)] ... taps t[jj] = kern_k[K12 - 1 - jj]
+    __syncthreads();
+    const float* gk = gy + (size_t)b * n_blocks * hop + (size_t)k * hop;
+    const int off = u0 - k * hop - (K12 - 1);  // gy index seen by x[0]
+    for (int i = tid; i < gs_len; i += blockDim.x) {
+      const int r = off + i;
+      gs[i] = (r >= 0 && r < hop) ? gk[r] : 0.f;
+    }
+    const float* kb = kernel + ((size_t)b * F + k) * K;
+    for (int i = tid; i < K12; i += blockDim.x) {
+      const int j = K12 - 1 - i;
+      ks[i] = j < K ? kb[j] : 0.f;
+    }
+    __syncthreads();
+    if (r0 < hop) fir_tile8(gs + r0, ks, K12, acc);
+  }
+  if (r0 < hop) {
+#pragma unroll
+    for (int i = 0; i < kR; ++i) {
+      const int t = u0 + r0 + i - p;
+      if (r0 + i < hop && t >= 0 && t < T) d_ex[(size_t)b * T + t] = acc[i];
+    }
+  }
+}
+
+// ---- adjoints of the room FIR -----------------------------------------------------------
+// d_x[t] = gy[t] + sum_j k[j] gy[t + n - j]   (anti-causal); taps staged reversed with the direct
+// path first: ks = [1, k_{n-1}, ..., k_0].
+__global__ void __launch_bounds__(128) room_fir_dx_kernel(const float* __restrict__ gy, const float* __restrict__ k,
+                                                          float* __restrict__ d_x, int T, int n, int K12, int xs_len) {
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;
+  float* ks = smem + xs_len;
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int t0 = blockIdx.x * kRoomTile;
+  const float* gb = gy + (size_t)b * T;
+  for (int i = tid; i < xs_len; i += blockDim.x) {
+    const int pos = t0 + i;
+    xs[i] = pos < T ? gb[pos] : 0.f;
+  }
+  for (int i = tid; i < K12; i += blockDim.x) ks[i] = i == 0 ? 1.f : (i <= n ? k[n - i] : 0.f);
+  __syncthreads();
+  const int r0 = tid * kR;
+  float acc[kR];
+#pragma unroll
+  for (int i = 0; i < kR; ++i) acc[i] = 0.f;
+  fir_tile8(xs + r0, ks, K12, acc);
+  float* ob = d_x + (size_t)b * T;
+#pragma unroll
+  for (int i = 0; i < kR; ++i)
+    if (t0 + r0 + i < T) ob[t0 + r0 + i] = acc[i];
+}
+
+// d_k[j] = sum_{b,t} gy[b,t] x[b,t-n+j]: per CTA a tile of t for one utterance, 8 taps per thread
+// via the same correlation (gy as taps), partial sums added atomically (float adds: the order,
+// hence the last bit, is not reproducible run to run).
+__global__ void __launch_bounds__(32) room_fir_dk_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                                                         float* __restrict__ d_k, int T, int n, int tile_len, int G12,
+                                                         int xs_len) {
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;
+  float* gs = smem + xs_len;
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int t0 = blockIdx.x * tile_len;
+  const float* xb = x + (size_t)b * T;
+  const float* gb = gy + (size_t)b * T;
+  for (int i = tid; i < xs_len; i += blockDim.x) {
+    const int pos = t0 - n + i;
+    xs[i] = (pos >= 0 && pos < T) ? xb[pos] : 0.f;
+  }
+  for (int i = tid; i < G12; i += blockDim.x) gs[i] = (i < tile_len && t0 + i < T) ? gb[t0 + i] : 0.f;
+  __syncthreads();
+  // d_k[j] += sum_r gs[r] * xs[r + j]
+  for (int j0 = tid * kR; j0 < n; j0 += blockDim.x * kR) {
+    float acc[kR];
+#pragma unroll
+    for (int i = 0; i < kR; ++i) acc[i] = 0.f;
+    fir_tile8(xs + j0, gs, G12, acc);
+#pragma unroll
+    for (int i = 0; i < kR; ++i)
+      if (j0 + i < n) atomicAdd(d_k + j0 + i, acc[i]);
+  }
+}
+
 // ---- linear upsample -----------------------------------------------------------------
 __global__ void linear_upsample_kernel(const float* __restrict__ x, float* __restrict__ out, int n, int hop, int L,
                                        float scale) {
@@ -117,8 +260,9 @@ __global__ void rc2lpc_kernel(const float* __restrict__ logits, float* __restric
 
 using namespace golf;
 
-GOLF_API int golf_noise_fir_fwd(const float* ex, int64_t ex_stride, const float* kernel, const float* add,
-                                int64_t add_stride, float* y, int B, int T, int F, int K, int hop, void* stream) {
+GOLF_API int golf_noise_fir_fwd(const float* ex, int64_t ex_stride, const float* kernel, const float* window,
+                                const float* add, int64_t add_stride, float* y, int B, int T, int F, int K, int hop,
+                                void* stream) {
   if (!ex || !kernel || !y || B <= 0 || T <= 0 || F <= 0 || K <= 0 || hop <= 0) return GOLF_ERR_INVALID;
   const int p = (K - 1) / 2;
   if (T + 2 * p < K + hop - 1) return GOLF_ERR_INVALID;
@@ -131,8 +275,9 @@ GOLF_API int golf_noise_fir_fwd(const float* ex, int64_t ex_stride, const float*
   const size_t sm = (size_t)(xs_len + K12) * sizeof(float);
   if (sm > 48 * 1024) return GOLF_ERR_UNSUPPORTED;
   dim3 grid(n_blocks, B);
-  noise_fir_kernel<<<grid, threads, sm, (cudaStream_t)stream>>>(ex, ex_stride, kernel, add, add_stride, y, T, F, K, hop,
-                                                              n_blocks, K12, xs_len);
+  if (window && (K & 1)) return GOLF_ERR_UNSUPPORTED;  // fused fftshift assumes an even tap count (2*(n_mag-1))
+  noise_fir_kernel<<<grid, threads, sm, (cudaStream_t)stream>>>(ex, ex_stride, kernel, window, add, add_stride, y, T, F, K,
+                                                              hop, n_blocks, K12, xs_len);
   GOLF_CHECK_LAUNCH();
   return GOLF_OK;
 }
@@ -146,6 +291,69 @@ GOLF_API int golf_room_fir_fwd(const float* x, const float* k, float* out, int B
   dim3 grid(ceil_div(T, kRoomTile), B);
   room_fir_kernel<<<grid, 128, sm, (cudaStream_t)stream>>>(x, k, out, T, n, K12, xs_len);
   GOLF_CHECK_LAUNCH();
+  return GOLF_OK;
+}
+
+
+GOLF_API int golf_noise_fir_bwd(const float* gy, const float* ex, int64_t ex_stride, const float* kernel, float* d_ex,
+                                float* d_kernel, int B, int T, int F, int K, int hop, void* stream) {
+  if (!gy || !ex || !kernel || B <= 0 || T <= 0 || F <= 0 || K <= 0 || hop <= 0) return GOLF_ERR_INVALID;
+  const int p = (K - 1) / 2;
+  if (T + 2 * p < K + hop - 1) return GOLF_ERR_INVALID;
+  int n_blocks = (T + 2 * p - (K + hop - 1)) / hop + 1;
+  if (n_blocks > F) n_blocks = F;
+  if (hop > 2048) return GOLF_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K12 = ceil_div(K, 12) * 12;
+  if (d_kernel) {
+    // frames beyond n_blocks receive no gradient
+    if (n_blocks < F) {
+      for (int b = 0; b < B; ++b)
+        GOLF_CUDA(cudaMemsetAsync(d_kernel + ((size_t)b * F + n_blocks) * K, 0, (size_t)(F - n_blocks) * K * sizeof(float), st));
+    }
+    const int H12 = ceil_div(hop, 12) * 12;
+    const int threads = 128;
+    const int xs_len = (int)align_up((size_t)ceil_div(K, threads * kR) * threads * kR + H12 + 24, 4);
+    const size_t sm = (size_t)(xs_len + H12) * sizeof(float);
+    if (sm > 48 * 1024) return GOLF_ERR_UNSUPPORTED;
+    noise_fir_dkernel_kernel<<<dim3(n_blocks, B), threads, sm, st>>>(gy, ex, ex_stride, d_kernel, T, F, K, hop, n_blocks, H12,
+                                                                    xs_len);
+    GOLF_CHECK_LAUNCH();
+  }
+  if (d_ex) {
+    const int threads = 32 * ceil_div(hop, 32 * kR);
+    const int gs_len = (int)align_up((size_t)threads * kR + K12 + 24, 4);
+    const size_t sm = (size_t)(gs_len + K12) * sizeof(float);
+    if (sm > 48 * 1024) return GOLF_ERR_UNSUPPORTED;
+    const int tiles = ceil_div(T + p, hop);  // padded coordinates u = t + p, t in [0, T)
+    noise_fir_dex_kernel<<<dim3(tiles, B), threads, sm, st>>>(gy, kernel, d_ex, T, F, K, hop, n_blocks, K12, gs_len);
+    GOLF_CHECK_LAUNCH();
+  }
+  return GOLF_OK;
+}
+
+GOLF_API int golf_room_fir_bwd(const float* gy, const float* x, const float* k, float* d_x, float* d_k, int B, int T, int n,
+                               void* stream) {
+  if (!gy || !x || !k || B <= 0 || T <= 0 || n <= 0) return GOLF_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K12 = ceil_div(n + 1, 12) * 12;
+  if (d_x) {
+    const int xs_len = (int)align_up((size_t)kRoomTile + K12 + 24, 4);
+    const size_t sm = (size_t)(xs_len + K12) * sizeof(float);
+    if (sm > 48 * 1024) return GOLF_ERR_UNSUPPORTED;
+    room_fir_dx_kernel<<<dim3(ceil_div(T, kRoomTile), B), 128, sm, st>>>(gy, k, d_x, T, n, K12, xs_len);
+    GOLF_CHECK_LAUNCH();
+  }
+  if (d_k) {
+    GOLF_CUDA(cudaMemsetAsync(d_k, 0, (size_t)n * sizeof(float), st));
+    const int tile_len = 1536;
+    const int G12 = ceil_div(tile_len, 12) * 12;
+    const int xs_len = (int)align_up((size_t)ceil_div(n, 32 * kR) * 32 * kR + G12 + 24, 4);
+    const size_t sm = (size_t)(xs_len + G12) * sizeof(float);
+    if (sm > 48 * 1024) return GOLF_ERR_UNSUPPORTED;
+    room_fir_dk_kernel<<<dim3(ceil_div(T, tile_len), B), 32, sm, st>>>(gy, x, d_k, T, n, tile_len, G12, xs_len);
+    GOLF_CHECK_LAUNCH();
+  }
   return GOLF_OK;
 }
 

@@ -1,81 +1,9 @@
 // lpc_ss.cu -- host side of GOLF-ss (plan, workspace, C ABI) plus the kernels that do
-// not depend on the tap-count bucket: the chunk stitch and the coefficient gradients.
+// not depend on the tap-count bucket: the coefficient gradients.
 // The algorithm is described at the top of lpc_ss.cuh.
 #include "lpc_ss.cuh"
 
 namespace golf {
-// ------------------------------------------------------------------ pass 2 --------
-// One warp per sequence.  s_{p+1} = z_p + Phi_p s_p for p = 0..C-2; S[b][p] = s_p.
-// Phi_p/z_p ((M+1) x MP floats) stream through a ring of shared-memory stages
-// filled by the TMA unit (1-D cp.async.bulk, completion on an mbarrier per stage).
-
-__global__ void __launch_bounds__(32) ss_stitch_kernel(SsParams p, int MP) {
-  extern __shared__ __align__(128) float smem[];
-  const int lane = threadIdx.x, b = blockIdx.x;
-  const int slot = (MP + 1) * MP;           // floats per chunk block (multiple of 4)
-  const uint32_t bytes = (uint32_t)((p.M + 1) * MP * sizeof(float));
-  float* ring = smem;                        // [stages][slot]
-  float* svec = ring + kStitchStages * slot; // [MP] current state (broadcast reads)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(svec + ((MP + 3) / 4) * 4 + 4);
-  const int nresp = p.C - 1;
-  const float* wb = p.W + (size_t)b * nresp * slot;
-  float* sb = p.S + (size_t)b * p.C * MP;
-
-  if (lane == 0) {
-    for (int s = 0; s < kStitchStages; ++s) mbar_init(&bars[s], 1);
-    mbar_fence_init();
-  }
-  // initial state: zi (FORM0 only) or zeros
-  for (int k = lane; k < MP; k += 32) {
-    float v = (p.zi && k < p.M) ? p.zi[(size_t)b * p.M + k] : 0.f;
-    svec[k] = v;
-    sb[k] = v;
-  }
-  __syncwarp();
-  if (lane == 0) {
-    for (int s = 0; s < kStitchStages && s < nresp; ++s) {
-      mbar_expect_tx(&bars[s], bytes);
-      bulk_g2s(ring + s * slot, wb + (size_t)s * slot, bytes, &bars[s]);
-    }
-  }
-  for (int pi = 0; pi < nresp; ++pi) {
-    const int stg = pi % kStitchStages;
-    mbar_wait(&bars[stg], (uint32_t)((pi / kStitchStages) & 1));
-    const float* blk = ring + stg * slot;
-    float nxt[2] = {0.f, 0.f};
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int k = lane + 32 * q;  // state component computed by this lane
-      if (k < MP) {
-        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-        int j = 0;
-        for (; j + 3 < p.M; j += 4) {
-          acc0 = __fmaf_rn(blk[(j + 0) * MP + k], svec[j + 0], acc0);
-          acc1 = __fmaf_rn(blk[(j + 1) * MP + k], svec[j + 1], acc1);
-          acc2 = __fmaf_rn(blk[(j + 2) * MP + k], svec[j + 2], acc2);
-          acc3 = __fmaf_rn(blk[(j + 3) * MP + k], svec[j + 3], acc3);
-        }
-        for (; j < p.M; ++j) acc0 = __fmaf_rn(blk[j * MP + k], svec[j], acc0);
-        nxt[q] = blk[p.M * MP + k] + ((acc0 + acc1) + (acc2 + acc3));
-      }
-    }
-    __syncwarp();  // everyone is done reading svec and this stage
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int k = lane + 32 * q;
-      if (k < MP) {
-        svec[k] = nxt[q];
-        sb[(size_t)(pi + 1) * MP + k] = nxt[q];
-      }
-    }
-    if (lane == 0 && pi + kStitchStages < nresp) {
-      mbar_expect_tx(&bars[stg], bytes);
-      bulk_g2s(ring + stg * slot, wb + (size_t)(pi + kStitchStages) * slot, bytes, &bars[stg]);
-    }
-    __syncwarp();
-  }
-}
-
 // ------------------------------------------------------- coefficient gradients ----
 // d_a[b,k,i]  = sum_t wk(t) * (-u[t] * y[t-1-i]),  d_gain[b,k] = sum_t wk(t) * u[t]*ex[t]
 // where wk(t) is the weight ATen's upsample gives frame k at time t (l0 on the i0
@@ -178,7 +106,14 @@ static bool make_plan(int B, int L, int M, int hop, int chunk, SsPlan* pl) {
   return true;
 }
 
-static size_t plan_bytes(const SsPlan& pl) { return align_up(pl.w_floats * 4, 256) + align_up(pl.s_floats * 4, 256); }
+// workspace layout: W | S | E
+static size_t plan_bytes(const SsPlan& pl) { return align_up(pl.w_floats * 4, 256) + 2 * align_up(pl.s_floats * 4, 256); }
+static void plan_pointers(const SsPlan& pl, void* workspace, SsParams* p) {
+  char* ws = reinterpret_cast<char*>(workspace);
+  p->W = reinterpret_cast<float*>(ws);
+  p->S = reinterpret_cast<float*>(ws + align_up(pl.w_floats * 4, 256));
+  p->E = reinterpret_cast<float*>(ws + align_up(pl.w_floats * 4, 256) + align_up(pl.s_floats * 4, 256));
+}
 
 
 // defined in lpc_ss_mp.cu, one translation unit per MP
@@ -220,8 +155,7 @@ GOLF_API int golf_lpc_ss_fwd_passes(const float* ex, int64_t ex_stride, const fl
   if (((uintptr_t)workspace & 15) != 0) return GOLF_ERR_INVALID;
   SsParams p{};
   p.in = ex, p.in_stride = ex_stride, p.gain = gain, p.a = a, p.out = y, p.out2 = nullptr, p.zi = zi;
-  p.W = reinterpret_cast<float*>(workspace);
-  p.S = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(pl.w_floats * 4, 256));
+  plan_pointers(pl, workspace, &p);
   p.B = B, p.L = L, p.F = F, p.M = M, p.hop = hop, p.Lc = pl.Lc, p.C = pl.C, p.HB = pl.HB;
   p.scale = lerp_scale(F, hop);
   return launch_form<0>(p, pl.MP, pl.generic, passes, (cudaStream_t)stream);
@@ -230,7 +164,7 @@ GOLF_API int golf_lpc_ss_fwd_passes(const float* ex, int64_t ex_stride, const fl
 GOLF_API int golf_lpc_ss_fwd(const float* ex, int64_t ex_stride, const float* gain, const float* a, const float* zi,
                              float* y, int B, int L, int F, int M, int hop, int chunk, void* workspace,
                              size_t workspace_bytes, void* stream) {
-  return golf_lpc_ss_fwd_passes(ex, ex_stride, gain, a, zi, y, B, L, F, M, hop, chunk, workspace, workspace_bytes, 7, stream);
+  return golf_lpc_ss_fwd_passes(ex, ex_stride, gain, a, zi, y, B, L, F, M, hop, chunk, workspace, workspace_bytes, 15, stream);
 }
 
 GOLF_API size_t golf_lpc_ss_bwd_workspace_bytes(int B, int L, int M, int hop, int chunk) {
@@ -241,8 +175,8 @@ GOLF_API size_t golf_lpc_ss_bwd_workspace_bytes(int B, int L, int M, int hop, in
 
 GOLF_API int golf_lpc_ss_bwd(const float* gy, const float* y, const float* ex, int64_t ex_stride, const float* gain,
                              const float* a, const float* zi, float* d_ex, float* d_gain, float* d_a, float* d_zi,
-                             int B, int L, int F, int M, int hop, int chunk, void* workspace, size_t workspace_bytes,
-                             void* stream) {
+                             int B, int L, int F, int M, int hop, int chunk, int refine, void* workspace,
+                             size_t workspace_bytes, void* stream) {
   if (!gy || !y || !ex || !a || B <= 0 || L <= 0 || F <= 0 || M <= 0 || hop <= 0) return GOLF_ERR_INVALID;
   if (ex_stride < L || (int64_t)L > (int64_t)(F - 1) * hop + 1) return GOLF_ERR_INVALID;
   SsPlan pl;
@@ -253,13 +187,12 @@ GOLF_API int golf_lpc_ss_bwd(const float* gy, const float* y, const float* ex, i
   char* ws = reinterpret_cast<char*>(workspace);
   SsParams p{};
   p.in = gy, p.in_stride = L, p.gain = gain, p.a = a, p.zi = nullptr;
-  p.W = reinterpret_cast<float*>(ws);
-  p.S = reinterpret_cast<float*>(ws + align_up(pl.w_floats * 4, 256));
+  plan_pointers(pl, workspace, &p);
   float* u = reinterpret_cast<float*>(ws + plan_bytes(pl));
   p.out = u, p.out2 = d_ex;
   p.B = B, p.L = L, p.F = F, p.M = M, p.hop = hop, p.Lc = pl.Lc, p.C = pl.C, p.HB = pl.HB;
   p.scale = lerp_scale(F, hop);
-  int rc = launch_form<1>(p, pl.MP, pl.generic, 7, st);
+  int rc = launch_form<1>(p, pl.MP, pl.generic, refine ? 15 : 7, st);
   if (rc) return rc;
   if (d_gain || d_a) {
     const int warps = 4;

@@ -1,4 +1,4 @@
-// lpc_ss.cu -- GOLF-ss: time-varying all-pole (LPC) filter and its adjoint on sm_100a.
+// lpc_ss.cuh -- GOLF-ss: time-varying all-pole (LPC) filter and its adjoint on sm_100a.
 //
 // Replaces models/filters.py:99-113 (LTVMinimumPhaseFilterPrecise.forward: ex*gain,
 // a.reduce_hop_length(), torchlpc.sample_wise_lpc) and torchlpc's autograd, without
@@ -6,29 +6,38 @@
 //
 // The recurrence  y[t] = e[t] - sum_i a[t,i] y[t-1-i]  is serial in t; at B=32 a
 // one-sequence-per-warp mapping would leave 99% of a B200 idle.  It is linear though,
-// so time is cut into chunks of Lc samples and solved in three launches:
+// so time is cut into chunks of Lc samples and solved in three kinds of launch:
 //
-//   1. ss_response_kernel   one WARP per (sequence, chunk).  Lanes 0..M-1 run the
-//      homogeneous responses to the M unit initial states, lane M the zero-state
-//      response to the excitation; all lanes share the chunk's coefficients, which the
-//      warp interpolates tile by tile (ATen arithmetic) into shared memory and reads
-//      back as LDS.128 broadcasts.  Output: the chunk's M x M transition matrix Phi and
-//      its zero-state end state z   (workspace W, L2 resident).
+//   1. ss_response_kernel   per chunk, M+1 recurrences share the chunk's coefficients: the
+//      homogeneous responses to the M unit initial states and the zero-state response to
+//      the excitation.  A lane runs 4 of those columns (so every coefficient it reads from
+//      shared memory feeds 4 FMAs -- the smem-operand : FP32-pipe ratio of the SM), a
+//      warp hosts 32/ceil((M+1)/4) chunks; the warp interpolates the coefficient rows tile
+//      by tile (ATen arithmetic) into shared memory.  Output: each chunk's M x M
+//      transition matrix Phi and zero-state end state z (workspace W, L2 resident).
 //   2. ss_stitch_kernel     one warp per sequence walks the chunks: s <- z + Phi s.
 //      Phi/z blocks are prefetched by the TMA unit (cp.async.bulk + mbarrier ring).
 //   3. ss_solve_kernel      one LANE per (sequence, chunk): re-runs the recurrence from
-//      the now-known initial state with the reference's tap order and writes y.
+//      the now-known initial state and writes y; also records the state it ends in (E).
 //      Frame coefficient pairs live in registers; inputs/outputs are staged through
 //      shared memory so global accesses stay coalesced.
+//   4. (refinement, optional) the end state E_p a chunk really reached differs from the
+//      stitched S_{p+1} by the float32 error of Phi/z.  ss_stitch_kernel(refine) propagates
+//      that mismatch, delta_{p+1} = Phi_p delta_p + (E_p - S_{p+1}), corrects S, and the
+//      solve runs once more: the result is then a piecewise *sequential* float32
+//      recurrence with consistent states, i.e. as accurate as the reference's own loop
+//      even for high-gain / near-unstable filters where Phi is badly conditioned.
 //
-// The adjoint  u[t] = g[t] - sum_i a[t+1+i,i] u[t+1+i]  runs through the same three
-// kernels on reversed time in transposed form (FORM 1): every product pairs u[s] with
-// the coefficient row of its own time s, so coefficient staging is identical.
+// The adjoint  u[t] = g[t] - sum_i a[t+1+i,i] u[t+1+i]  runs through the same kernels on
+// reversed time in transposed form (FORM 1): every product pairs u[s] with the
+// coefficient row of its own time s, so coefficient staging is identical.
 //
 // Algorithmic HBM bytes per sample: 4 (ex) + 4 (y) + 4(M+1)/hop (controls) = 8.383 B at
-// M=22, hop=240; the work is ~M(M+1) FMA/sample in pass 1 -- FP32-issue bound, see
+// M=22, hop=240; the work is ~M(M+1) FMA/sample in pass 1 -- FP32-pipe bound, see
 // DESIGN.md.
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace golf {
@@ -42,6 +51,7 @@ struct SsParams {
   float* out2;         // FORM1: d_ex = u * up(gain) [B,L] or null
   float* W;            // [B][C-1][(MP+1)*MP]   chunk responses
   float* S;            // [B][C][MP]            state entering each chunk (processing order)
+  float* E;            // [B][C][MP]            state each chunk ended in (written by the solve)
   const float* zi;     // [B,M] or null (FORM0 only)
   int B, L, F, M, hop, Lc, C, HB;
   float scale;
@@ -53,162 +63,319 @@ __device__ __forceinline__ int time_of(const SsParams& p, int pi, int n) {
   return FORM == 0 ? pi * p.Lc + n : (p.C - pi) * p.Lc - 1 - n;
 }
 
+__device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y); }
+
 // ------------------------------------------------------------------ pass 1 --------
+// Chunk responses.  Operand bandwidth decides the mapping: shared memory hands a warp 32
+// lane-words per cycle, the FP32 pipe wants 128 lane-FMAs per cycle, so every coefficient a
+// lane reads must feed FOUR of its FMAs.  Each lane therefore owns 4 of the M+1 columns of
+// one chunk ([Phi | z]; LPC = ceil((M+1)/4) lanes per chunk) and a warp hosts
+// CPW = 32/LPC chunks side by side (M=22: 6 lanes x 4 columns, 5 chunks per warp, 30 lanes).
+// Per step a lane issues MP/4 LDS.128 for its chunk's coefficient row and 4*MP FFMA.
+constexpr int kNC = 4;          // columns per lane
+constexpr int kRespThreads = 160;  // 5 warps: 2 CTAs/SM at <= 204 registers -> 10 warps/SM, one wave at B=32
+
 template <int MP, int FORM>
-__global__ void __launch_bounds__(128) ss_response_kernel(SsParams p) {
-  constexpr int SLOTS = (MP + 1 + 31) / 32;  // columns per lane (M+1 columns in all)
-  constexpr int TAPS = (MP + 31) / 32;       // taps per lane while staging coefficients
+__global__ void __launch_bounds__(kRespThreads, (MP <= 24 ? 2 : 1)) ss_response_kernel(SsParams p, int LPC, int CPW) {
+  constexpr int TSTR = MP * MP + 4;  // per-chunk tile stride: +4 floats puts the groups in different bank quads
   extern __shared__ __align__(128) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nresp = p.C - 1;
+  const int wps = (nresp + CPW - 1) / CPW;  // warps per sequence
   const int wg = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (wg >= p.B * nresp) return;
-  const int b = wg / nresp, pi = wg % nresp;
-  float* ctile = smem + warp * (MP * MP + MP);  // [MP rows][MP taps], negated coefficients
-  float* etile = ctile + MP * MP;               // [MP] chunk input
+  if (wg >= p.B * wps) return;
+  const int b = wg / wps, w0 = (wg % wps) * CPW;
+  const int gi = min(lane / LPC, CPW - 1), li = lane % LPC;
+  const bool lane_on = lane < LPC * CPW;
+  const int pi = w0 + gi;
+  const bool chunk_on = lane_on && pi < nresp;
 
-  // state registers: FORM0 h[k] holds the output of tile position k (newest = MP-1);
-  // FORM1 r[k] holds the (negated) pending sum that is consumed at tile position k.
-  float st[SLOTS][MP];
-  bool zsr[SLOTS];
+  float* ctile = smem + (size_t)warp * (CPW * TSTR + CPW * MP * 5);  // [CPW][MP rows][MP taps] negated coefficients
+  float* etile = ctile + CPW * TSTR;                                 // [CPW][MP] chunk inputs
+  float4* lw = reinterpret_cast<float4*>(etile + CPW * MP);          // [CPW][MP] (l0, l1, i0, i1) per row
+  const float* __restrict__ ab = p.a + (size_t)b * p.F * p.M;
+  const float* __restrict__ gb = p.gain ? p.gain + (size_t)b * p.F : nullptr;
+  const float* __restrict__ inb = p.in + (size_t)b * p.in_stride;
+
+  // state: FORM0 st[c][k] = output of tile position k; FORM1 st[c][k] = (negated) pending sum
+  // consumed at tile position k.  Column `col` starts from the unit state `col`; column M
+  // (zero-state response) starts from rest and is driven by the input.
+  float st[kNC][MP];
+  bool zsr[kNC];
 #pragma unroll
-  for (int sl = 0; sl < SLOTS; ++sl) {
-    const int col = lane + 32 * sl;
-    zsr[sl] = (col == p.M);
+  for (int c = 0; c < kNC; ++c) {
+    const int col = kNC * li + c;
+    zsr[c] = (col == p.M);
 #pragma unroll
     for (int k = 0; k < MP; ++k) {
       const int comp = FORM == 0 ? MP - 1 - k : k;  // state component stored in slot k
-      st[sl][k] = (col < p.M && comp == col) ? 1.f : 0.f;
+      st[c][k] = (col < p.M && comp == col) ? 1.f : 0.f;
     }
   }
-
-  const float* ab = p.a + (size_t)b * p.F * p.M;
-  const float* gb = p.gain ? p.gain + (size_t)b * p.F : nullptr;
-  const float* inb = p.in + (size_t)b * p.in_stride;
+  const float* myc = ctile + gi * TSTR;
+  const float* mye = etile + gi * MP;
+  float qa0[4], qa1[4];  // stage-B frame pair of this lane's (chunk, tap quad)
+  int qf0 = -1, qf1 = -1;
+  // interpolation weights (l0, l1, i0, i1) + input of the (chunk, row) pairs this lane stages,
+  // fetched one tile ahead so the global-load latency hides behind the recurrence
+  constexpr int NA = 4;  // CPW * MP <= 128 rows for every (M, MP) bucket (checked on the host)
+  float pre_x[NA], pre_g0[NA], pre_g1[NA];
+  float4 pre_w[NA];
+  auto prefetch = [&](int tile) {  // raw loads only: nothing here waits on them
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+      const int r = lane + 32 * j;
+      const int k = r / MP, sr = r - k * MP;
+      const int ppi = w0 + k;
+      const int t = time_of<FORM>(p, ppi, tile * MP + sr);
+      const bool ok = r < CPW * MP && ppi < nresp && t >= 0 && t < p.L;
+      const Lerp w = lerp_at(ok ? t : 0, p.scale, p.F);
+      pre_x[j] = ok ? __ldg(inb + t) : 0.f;
+      pre_g0[j] = (FORM == 0 && gb) ? __ldg(gb + w.i0) : 1.f;
+      pre_g1[j] = (FORM == 0 && gb) ? __ldg(gb + w.i1) : 1.f;
+      pre_w[j] = make_float4(ok ? w.l0 : 0.f, ok ? w.l1 : 0.f, __int_as_float(w.i0), __int_as_float(w.i1));
+    }
+  };
+  prefetch(0);
 
 #pragma unroll 1
   for (int tile = 0; tile < p.Lc / MP; ++tile) {
     __syncwarp();
-    // ---- stage MP coefficient rows + inputs (lanes = rows for the weights, = taps for the values)
-    Lerp wrow[TAPS];
-    bool vrow[TAPS];
+    // ---- stage A: publish the weights + inputs prefetched for this tile
 #pragma unroll
-    for (int q = 0; q < TAPS; ++q) {
-      const int s = lane + 32 * q;
-      const int t = time_of<FORM>(p, pi, tile * MP + s);
-      vrow[q] = (s < MP) && (t < p.L) && (t >= 0);
-      wrow[q] = lerp_at(vrow[q] ? t : 0, p.scale, p.F);
-      if (s < MP) {
-        float e = 0.f;
-        if (vrow[q]) {
-          e = inb[t];
-          if (FORM == 0 && gb) e = __fmul_rn(e, lerp_apply(wrow[q], gb[wrow[q].i0], gb[wrow[q].i1]));
-        }
-        etile[s] = e;
-      }
-    }
-    int cur0 = -1;
-    float a0v[TAPS], a1v[TAPS];
-#pragma unroll
-    for (int s = 0; s < MP; ++s) {
-      const int q = s / 32, src = s % 32;
-      const int i0 = __shfl_sync(0xffffffffu, wrow[q].i0, src);
-      const int i1 = __shfl_sync(0xffffffffu, wrow[q].i1, src);
-      const float l0 = __shfl_sync(0xffffffffu, wrow[q].l0, src);
-      const float l1 = __shfl_sync(0xffffffffu, wrow[q].l1, src);
-      const bool ok = __shfl_sync(0xffffffffu, (int)vrow[q], src) != 0;
-      if (i0 != cur0) {  // warp-uniform: new frame pair
-        cur0 = i0;
-#pragma unroll
-        for (int q2 = 0; q2 < TAPS; ++q2) {
-          const int i = lane + 32 * q2;
-          a0v[q2] = i < p.M ? ab[(size_t)i0 * p.M + i] : 0.f;
-          a1v[q2] = i < p.M ? ab[(size_t)i1 * p.M + i] : 0.f;
-        }
-      }
-#pragma unroll
-      for (int q2 = 0; q2 < TAPS; ++q2) {
-        const int i = lane + 32 * q2;
-        if (i < MP) {
-          const float v = __fmaf_rn(l0, a0v[q2], __fmul_rn(l1, a1v[q2]));
-          ctile[s * MP + i] = ok ? -v : 0.f;
-        }
+    for (int j = 0; j < NA; ++j) {
+      const int r = lane + 32 * j;
+      if (r < CPW * MP) {
+        float e = pre_x[j];
+        if (FORM == 0 && gb) e = __fmul_rn(e, __fmaf_rn(pre_w[j].x, pre_g0[j], __fmul_rn(pre_w[j].y, pre_g1[j])));
+        etile[r] = e;
+        lw[r] = pre_w[j];
       }
     }
     __syncwarp();
+    // ---- stage B: coefficient rows (ATen arithmetic, negated).  Lane = (chunk, tap quad);
+    // its frame pair sits in registers and is re-fetched only when a row's frame differs
+    // (frame change, or ATen's floor() landing one frame low at t % hop == 0).
+    if (lane < CPW * (MP / 4)) {
+      const int k = lane / (MP / 4), tq = lane - k * (MP / 4);
+#pragma unroll 4
+      for (int sr = 0; sr < MP; ++sr) {
+        const float4 wv = lw[k * MP + sr];
+        const int i0 = __float_as_int(wv.z), i1 = __float_as_int(wv.w);
+        if (i0 != qf0 || i1 != qf1) {
+          qf0 = i0, qf1 = i1;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool in = 4 * tq + i < p.M;
+            qa0[i] = in ? __ldg(ab + (size_t)i0 * p.M + 4 * tq + i) : 0.f;
+            qa1[i] = in ? __ldg(ab + (size_t)i1 * p.M + 4 * tq + i) : 0.f;
+          }
+        }
+        float4 v;
+        v.x = -__fmaf_rn(wv.x, qa0[0], __fmul_rn(wv.y, qa1[0]));
+        v.y = -__fmaf_rn(wv.x, qa0[1], __fmul_rn(wv.y, qa1[1]));
+        v.z = -__fmaf_rn(wv.x, qa0[2], __fmul_rn(wv.y, qa1[2]));
+        v.w = -__fmaf_rn(wv.x, qa0[3], __fmul_rn(wv.y, qa1[3]));
+        *reinterpret_cast<float4*>(ctile + k * TSTR + sr * MP + 4 * tq) = v;
+      }
+    }
+    __syncwarp();
+    if (tile + 1 < p.Lc / MP) prefetch(tile + 1);
     // ---- MP recurrence steps, fully unrolled so the state rotates through registers
 #pragma unroll
     for (int s = 0; s < MP; ++s) {
-      const float e = etile[s];
+      const float e = mye[s];
       float c[MP];
 #pragma unroll
       for (int i4 = 0; i4 < MP / 4; ++i4) {
-        const float4 v = *reinterpret_cast<const float4*>(ctile + s * MP + 4 * i4);
+        const float4 v = *reinterpret_cast<const float4*>(myc + s * MP + 4 * i4);
         c[4 * i4] = v.x, c[4 * i4 + 1] = v.y, c[4 * i4 + 2] = v.z, c[4 * i4 + 3] = v.w;
       }
+      if (FORM == 0) {
+        // oldest tap first (lag L = MP - j pairs with coefficient c[L-1]); the four columns'
+        // chains are interleaved tap by tap so the FMA pipe always has 4 independent ops
+        float acc[kNC];
 #pragma unroll
-      for (int sl = 0; sl < SLOTS; ++sl) {
-        if (FORM == 0) {
-          float acc = zsr[sl] ? e : 0.f;
+        for (int cc = 0; cc < kNC; ++cc) acc[cc] = zsr[cc] ? e : 0.f;
 #pragma unroll
-          for (int i = 0; i < MP; ++i) acc = __fmaf_rn(c[i], st[sl][(s - 1 - i + 2 * MP) % MP], acc);
-          st[sl][s] = acc;
-        } else {
-          const float u = (zsr[sl] ? e : 0.f) + st[sl][s];
+        for (int j = 0; j < MP; ++j)
 #pragma unroll
-          for (int k = 0; k < MP - 1; ++k) st[sl][(s + 1 + k) % MP] = __fmaf_rn(c[k], u, st[sl][(s + 1 + k) % MP]);
-          st[sl][s] = __fmul_rn(c[MP - 1], u);
-        }
+          for (int cc = 0; cc < kNC; ++cc) acc[cc] = __fmaf_rn(c[MP - 1 - j], st[cc][(s + j) % MP], acc[cc]);
+#pragma unroll
+        for (int cc = 0; cc < kNC; ++cc) st[cc][s] = acc[cc];
+      } else {
+        float u[kNC];
+#pragma unroll
+        for (int cc = 0; cc < kNC; ++cc) u[cc] = (zsr[cc] ? e : 0.f) + st[cc][s];
+#pragma unroll
+        for (int k = 0; k < MP - 1; ++k)
+#pragma unroll
+          for (int cc = 0; cc < kNC; ++cc) st[cc][(s + 1 + k) % MP] = __fmaf_rn(c[k], u[cc], st[cc][(s + 1 + k) % MP]);
+#pragma unroll
+        for (int cc = 0; cc < kNC; ++cc) st[cc][s] = __fmul_rn(c[MP - 1], u[cc]);
       }
     }
   }
-  // ---- emit column `col` of [Phi | z]: W[col][k] = end-state component k
-  float* wb = p.W + ((size_t)b * nresp + pi) * ((MP + 1) * MP);
+  // ---- emit this lane's columns of [Phi | z]: W[col][k] = end-state component k
+  if (chunk_on) {
+    float* wb = p.W + ((size_t)b * nresp + pi) * ((MP + 1) * MP);
 #pragma unroll
-  for (int sl = 0; sl < SLOTS; ++sl) {
-    const int col = lane + 32 * sl;
-    if (col <= p.M) {
+    for (int cc = 0; cc < kNC; ++cc) {
+      const int col = kNC * li + cc;
+      if (col <= p.M) {
 #pragma unroll
-      for (int k4 = 0; k4 < MP / 4; ++k4) {
-        float4 v;
-        if (FORM == 0) {
-          v = make_float4(st[sl][MP - 1 - 4 * k4], st[sl][MP - 2 - 4 * k4], st[sl][MP - 3 - 4 * k4], st[sl][MP - 4 - 4 * k4]);
-        } else {
-          v = make_float4(st[sl][4 * k4], st[sl][4 * k4 + 1], st[sl][4 * k4 + 2], st[sl][4 * k4 + 3]);
+        for (int k4 = 0; k4 < MP / 4; ++k4) {
+          float4 v;
+          if (FORM == 0) {
+            v = make_float4(st[cc][MP - 1 - 4 * k4], st[cc][MP - 2 - 4 * k4], st[cc][MP - 3 - 4 * k4], st[cc][MP - 4 - 4 * k4]);
+          } else {
+            v = make_float4(st[cc][4 * k4], st[cc][4 * k4 + 1], st[cc][4 * k4 + 2], st[cc][4 * k4 + 3]);
+          }
+          *reinterpret_cast<float4*>(wb + col * MP + 4 * k4) = v;
         }
-        *reinterpret_cast<float4*>(wb + col * MP + 4 * k4) = v;
       }
     }
   }
 }
 
-constexpr int kStitchStages = 8;
-__global__ void ss_stitch_kernel(SsParams p, int MP);
+// ------------------------------------------------------------------ pass 2 --------
+// One warp per sequence.  s_{p+1} = z_p + Phi_p s_p for p = 0..C-2; S[b][p] = s_p.
+// refine: delta_{p+1} = Phi_p delta_p + (E_p - S_{p+1}); S_{p+1} += delta_{p+1}.
+// Each chunk's block ([Phi | z], and in refine mode the E_p and S_{p+1} rows) streams
+// through a ring of shared-memory stages filled by the TMA unit (1-D cp.async.bulk,
+// completion counted on an mbarrier per stage).
+constexpr int kStitchStages = 3;  // ring depth
+constexpr int kStitchGroup = 4;   // chunk blocks per stage (one mbarrier wait per group)
+
+template <int MP>
+__global__ void __launch_bounds__(32) ss_stitch_kernel(SsParams p, int refine) {
+  constexpr int Q = (MP + 31) / 32;
+  constexpr int SLOT = (MP + 1) * MP;           // floats per chunk block
+  constexpr int GW = kStitchGroup * SLOT;        // W floats per stage
+  constexpr int STAGE = GW + 2 * kStitchGroup * MP;  // + E rows + S rows
+  extern __shared__ __align__(128) float smem[];
+  const int lane = threadIdx.x, b = blockIdx.x;
+  float* ring = smem;                               // [stages][STAGE]
+  float* svec = ring + kStitchStages * STAGE;       // [2][MP] state, double buffered
+  uint64_t* bars = reinterpret_cast<uint64_t*>(svec + 2 * MP);
+  const int nresp = p.C - 1;
+  const int ngroups = (nresp + kStitchGroup - 1) / kStitchGroup;
+  const float* wb = p.W + (size_t)b * nresp * SLOT;
+  float* sb = p.S + (size_t)b * p.C * MP;
+  const float* eb = p.E + (size_t)b * p.C * MP;
+
+  // one elected lane programs the TMA unit: group g -> stage g % kStitchStages
+  auto issue = [&](int g) {
+    const int stg = g % kStitchStages;
+    const int first = g * kStitchGroup;
+    const int n = min(kStitchGroup, nresp - first);
+    float* dst = ring + stg * STAGE;
+    const uint32_t wbytes = (uint32_t)(((n - 1) * SLOT + (p.M + 1) * MP) * sizeof(float));
+    const uint32_t rbytes = (uint32_t)(n * MP * sizeof(float));
+    mbar_expect_tx(&bars[stg], wbytes + (refine ? 2 * rbytes : 0));
+    bulk_g2s(dst, wb + (size_t)first * SLOT, wbytes, &bars[stg]);
+    if (refine) {
+      bulk_g2s(dst + GW, eb + (size_t)first * MP, rbytes, &bars[stg]);
+      bulk_g2s(dst + GW + kStitchGroup * MP, sb + (size_t)(first + 1) * MP, rbytes, &bars[stg]);
+    }
+  };
+
+  if (lane == 0) {
+    for (int s = 0; s < kStitchStages; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int k = lane + 32 * q;
+    if (k < MP) {
+      const float v = (!refine && p.zi && k < p.M) ? p.zi[(size_t)b * p.M + k] : 0.f;
+      svec[k] = v;
+      if (!refine) sb[k] = v;
+    }
+  }
+  __syncwarp();
+  if (lane == 0)
+    for (int g = 0; g < kStitchStages && g < ngroups; ++g) issue(g);
+
+  int buf = 0;
+#pragma unroll 1
+  for (int g = 0; g < ngroups; ++g) {
+    const int stg = g % kStitchStages;
+    mbar_wait(&bars[stg], (uint32_t)((g / kStitchStages) & 1));
+    const float* grp = ring + stg * STAGE;
+    const int n = min(kStitchGroup, nresp - g * kStitchGroup);
+#pragma unroll 1
+    for (int c = 0; c < n; ++c) {
+      const int pi = g * kStitchGroup + c;
+      const float* blk = grp + c * SLOT;
+      // everything that does not depend on the running state first ...
+      float phi[Q][MP], base[Q], old[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const int k = min(lane + 32 * q, MP - 1);
+#pragma unroll
+        for (int j = 0; j < MP; ++j) phi[q][j] = j < p.M ? blk[j * MP + k] : 0.f;
+        if (refine) {
+          old[q] = grp[GW + kStitchGroup * MP + c * MP + k];
+          base[q] = grp[GW + c * MP + k] - old[q];
+        } else {
+          old[q] = 0.f;
+          base[q] = blk[p.M * MP + k];
+        }
+      }
+      // ... then the dependent part: broadcast-read the state, 4 FMA chains per component
+      float sv[MP];
+#pragma unroll
+      for (int j4 = 0; j4 < MP / 4; ++j4) {
+        const float4 v = *reinterpret_cast<const float4*>(svec + buf * MP + 4 * j4);
+        sv[4 * j4] = v.x, sv[4 * j4 + 1] = v.y, sv[4 * j4 + 2] = v.z, sv[4 * j4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const int k = lane + 32 * q;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < MP; ++j) acc[j & 3] = __fmaf_rn(phi[q][j], sv[j], acc[j & 3]);
+        const float nxt = base[q] + ((acc[0] + acc[1]) + (acc[2] + acc[3]));
+        if (k < MP) {
+          svec[(buf ^ 1) * MP + k] = nxt;
+          sb[(size_t)(pi + 1) * MP + k] = old[q] + nxt;
+        }
+      }
+      buf ^= 1;
+      __syncwarp();
+    }
+    // the whole warp has consumed this stage: refill it with the group kStitchStages ahead
+    if (lane == 0 && g + kStitchStages < ngroups) issue(g + kStitchStages);
+  }
+}
 
 // ------------------------------------------------------------------ pass 3 --------
-// One lane per chunk.  GENERIC: coefficients fetched from global every step (any hop /
-// chunk relation).  !GENERIC: requires HB % MP == 0 with HB = min(hop, Lc) dividing
-// max(hop, Lc): the frame pair sits in registers and is reloaded at tile starts only.
+// One lane per chunk, one warp per CTA (the grid is small; spread it over every SM).
+// GENERIC: coefficients fetched from global every step (any hop / chunk relation).
+// !GENERIC: requires HB % MP == 0 with HB = min(hop, Lc) dividing max(hop, Lc): the frame
+// pair sits in registers and is reloaded at tile starts only.
+// Taps are summed oldest-first in three interleaved chains with the newest tap last, so
+// consecutive steps overlap in the FMA pipe (the serial dependency is one FMA per step).
 template <int MP, int FORM, bool GENERIC>
-__global__ void __launch_bounds__(128) ss_solve_kernel(SsParams p) {
+__global__ void __launch_bounds__(32) ss_solve_kernel(SsParams p) {
   constexpr int TST = MP + 1;  // tile row stride (odd -> conflict-free per-lane rows)
+  constexpr int NLD = MP;      // staged elements per lane per tile (32 rows x MP / 32 lanes)
   extern __shared__ __align__(128) float smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x;
   const int G = (p.C + 31) / 32;
-  const int wg = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (wg >= p.B * G) return;
-  const int b = wg / G, g = wg % G;
+  const int b = blockIdx.x / G, g = blockIdx.x % G;
   const int pi = g * 32 + lane;
   const bool active = pi < p.C;
   const int pic = active ? pi : p.C - 1;
-  float* tile = smem + warp * (FORM == 0 ? 1 : 2) * 32 * TST;
+  float* tile = smem;
   float* tile2 = tile + 32 * TST;  // FORM1 only: d_ex
 
-  const float* ab = p.a + (size_t)b * p.F * p.M;
-  const float* gb = p.gain ? p.gain + (size_t)b * p.F : nullptr;
-  const float* inb = p.in + (size_t)b * p.in_stride;
-  float* outb = p.out + (size_t)b * p.L;
-  float* out2b = (FORM == 1 && p.out2) ? p.out2 + (size_t)b * p.L : nullptr;
+  const float* __restrict__ ab = p.a + (size_t)b * p.F * p.M;
+  const float* __restrict__ gb = p.gain ? p.gain + (size_t)b * p.F : nullptr;
+  const float* __restrict__ inb = p.in + (size_t)b * p.in_stride;
+  float* __restrict__ outb = p.out + (size_t)b * p.L;
+  float* __restrict__ out2b = (FORM == 1 && p.out2) ? p.out2 + (size_t)b * p.L : nullptr;
 
   float st[MP];
   {
@@ -229,13 +396,20 @@ __global__ void __launch_bounds__(128) ss_solve_kernel(SsParams p) {
   for (int tl = 0; tl < p.Lc / MP; ++tl) {
     const int n0 = tl * MP;
     __syncwarp();
-    // ---- stage this tile's input rows (row r = chunk 32g+r), coalesced along time
-    for (int r = 0; r < 32; ++r) {
-      const int pr = g * 32 + r;
-      if (pr >= p.C) break;
-      for (int s = lane; s < MP; s += 32) {
-        const int t = time_of<FORM>(p, pr, n0 + s);
-        tile[r * TST + s] = (t >= 0 && t < p.L) ? inb[t] : 0.f;
+    // ---- stage this tile's input rows (row r = chunk 32g+r): all loads first, then stores
+    {
+      float v[NLD];
+#pragma unroll
+      for (int j = 0; j < NLD; ++j) {
+        const int idx = lane + 32 * j, r = idx / MP, s = idx - r * MP;
+        const int prr = g * 32 + r;
+        const int t = time_of<FORM>(p, prr, n0 + s);
+        v[j] = (prr < p.C && t >= 0 && t < p.L) ? __ldg(inb + t) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < NLD; ++j) {
+        const int idx = lane + 32 * j, r = idx / MP, s = idx - r * MP;
+        tile[r * TST + s] = v[j];
       }
     }
     __syncwarp();
@@ -256,11 +430,10 @@ __global__ void __launch_bounds__(128) ss_solve_kernel(SsParams p) {
           const int k1 = min(kreg + 1, p.F - 1);
 #pragma unroll
           for (int i = 0; i < MP; ++i) {
-            na0[i] = i < p.M ? -ab[(size_t)kreg * p.M + i] : 0.f;
-            na1[i] = i < p.M ? -ab[(size_t)k1 * p.M + i] : 0.f;
+            na0[i] = i < p.M ? -__ldg(ab + (size_t)kreg * p.M + i) : 0.f;
+            na1[i] = i < p.M ? -__ldg(ab + (size_t)k1 * p.M + i) : 0.f;
           }
-          if (FORM == 0 && gb) g0 = gb[kreg], g1 = gb[k1];
-          if (FORM == 1 && gb) g0 = gb[kreg], g1 = gb[k1];
+          if (gb) g0 = __ldg(gb + kreg), g1 = __ldg(gb + k1);
         }
         const float src = __fmul_rn(p.scale, (float)tc);
         if (s == (FORM == 0 ? 0 : MP - 1)) {
@@ -272,8 +445,12 @@ __global__ void __launch_bounds__(128) ss_solve_kernel(SsParams p) {
           float l1 = __fsub_rn(src, kregf);
           l1 = fminf(fmaxf(l1, 0.f), 1.f);
           const float l0 = __fsub_rn(1.f, l1);
+          const float2 l0p = f2(l0, l0), l1p = f2(l1, l1);
 #pragma unroll
-          for (int i = 0; i < MP; ++i) nc[i] = __fmaf_rn(l0, na0[i], __fmul_rn(l1, na1[i]));
+          for (int i = 0; i < MP; i += 2) {  // two taps per packed FMUL2/FFMA2
+            const float2 c2 = __ffma2_rn(l0p, f2(na0[i], na0[i + 1]), __fmul2_rn(l1p, f2(na1[i], na1[i + 1])));
+            nc[i] = c2.x, nc[i + 1] = c2.y;
+          }
           if (gb) gv = __fmaf_rn(l0, g0, __fmul_rn(l1, g1));
         }
       }
@@ -282,21 +459,25 @@ __global__ void __launch_bounds__(128) ss_solve_kernel(SsParams p) {
         const float* r0 = ab + (size_t)w.i0 * p.M;
         const float* r1 = ab + (size_t)w.i1 * p.M;
 #pragma unroll
-        for (int i = 0; i < MP; ++i) nc[i] = i < p.M ? -lerp_apply(w, r0[i], r1[i]) : 0.f;
-        if (gb) gv = lerp_apply(w, gb[w.i0], gb[w.i1]);
+        for (int i = 0; i < MP; ++i) nc[i] = i < p.M ? -lerp_apply(w, __ldg(r0 + i), __ldg(r1 + i)) : 0.f;
+        if (gb) gv = lerp_apply(w, __ldg(gb + w.i0), __ldg(gb + w.i1));
       }
-      if (!valid) {
-#pragma unroll
-        for (int i = 0; i < MP; ++i) nc[i] = 0.f;
-      }
+      // (steps outside [0, L) keep their coefficients: their input is zero, their output is
+      //  never stored and no later chunk reads their end state)
       const float x = tile[lane * TST + s];
       if (FORM == 0) {
-        float acc = valid ? __fmul_rn(x, gv) : 0.f;
-        if (!gb) acc = valid ? x : 0.f;
+        // lag L pairs nc[L-1] with st[(s - L) mod MP]; chains over lags MP..2, newest (L=1) last
+        float acc0 = valid ? (gb ? __fmul_rn(x, gv) : x) : 0.f, acc1 = 0.f, acc2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < MP; ++i) acc = __fmaf_rn(nc[i], st[(s - 1 - i + 2 * MP) % MP], acc);
-        st[s] = acc;
-        tile[lane * TST + s] = acc;
+        for (int L = MP; L >= 2; --L) {
+          const float h = st[(s - L + 2 * MP) % MP];
+          if ((MP - L) % 3 == 0) acc0 = __fmaf_rn(nc[L - 1], h, acc0);
+          if ((MP - L) % 3 == 1) acc1 = __fmaf_rn(nc[L - 1], h, acc1);
+          if ((MP - L) % 3 == 2) acc2 = __fmaf_rn(nc[L - 1], h, acc2);
+        }
+        const float y = __fmaf_rn(nc[0], st[(s - 1 + MP) % MP], (acc0 + acc1) + acc2);
+        st[s] = y;
+        tile[lane * TST + s] = y;
       } else {
         const float u = (valid ? x : 0.f) + st[s];
 #pragma unroll
@@ -308,52 +489,69 @@ __global__ void __launch_bounds__(128) ss_solve_kernel(SsParams p) {
     }
     __syncwarp();
     // ---- write the tile back, coalesced
-    for (int r = 0; r < 32; ++r) {
-      const int pr = g * 32 + r;
-      if (pr >= p.C) break;
-      for (int s = lane; s < MP; s += 32) {
-        const int t = time_of<FORM>(p, pr, n0 + s);
-        if (t >= 0 && t < p.L) {
-          outb[t] = tile[r * TST + s];
-          if (FORM == 1 && out2b) out2b[t] = tile2[r * TST + s];
-        }
+#pragma unroll
+    for (int j = 0; j < NLD; ++j) {
+      const int idx = lane + 32 * j, r = idx / MP, s = idx - r * MP;
+      const int prr = g * 32 + r;
+      const int t = time_of<FORM>(p, prr, n0 + s);
+      if (prr < p.C && t >= 0 && t < p.L) {
+        outb[t] = tile[r * TST + s];
+        if (FORM == 1 && out2b) out2b[t] = tile2[r * TST + s];
       }
     }
   }
-  // FORM1 with zi: nothing more here; d_zi is produced by ss_grad_kernel.
+  // ---- the state this chunk really ended in (input of the refinement stitch)
+  if (active && p.E) {
+    float* e0 = p.E + ((size_t)b * p.C + pi) * MP;
+#pragma unroll
+    for (int k = 0; k < MP; ++k) e0[k] = st[FORM == 0 ? MP - 1 - k : k];
+  }
 }
 
+// passes: bit0 responses, bit1 stitch, bit2 solve, bit3 refinement (stitch + solve again)
 template <int MP, int FORM>
 int launch_mp(const SsParams& p, bool generic, int passes, cudaStream_t st) {
   const int nresp = p.C - 1;
   if (nresp > 0 && (passes & 1)) {
-    const int warps = 4;
-    const size_t sm = warps * (MP * MP + MP) * sizeof(float);
-    ss_response_kernel<MP, FORM><<<ceil_div(p.B * nresp, warps), warps * 32, sm, st>>>(p);
-    GOLF_CHECK_LAUNCH();
-  }
-  if (passes & 2) {
-    const size_t sm = (size_t)kStitchStages * (MP + 1) * MP * 4 + (((MP + 3) / 4) * 4 + 4) * 4 + kStitchStages * 8 + 128;
-    static bool attr_done = false;
-    if (!attr_done) {
-      GOLF_CUDA(cudaFuncSetAttribute(ss_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      attr_done = true;
+    const int warps = kRespThreads / 32;
+    const int LPC = ceil_div(p.M + 1, kNC);
+    const int CPW = std::min(32 / LPC, 128 / MP);  // rows staged per tile: CPW * MP <= 128
+    const int wps = ceil_div(nresp, CPW);
+    if (CPW * MP > 128 || CPW * (MP / 4) > 32) return GOLF_ERR_UNSUPPORTED;
+    const size_t sm = (size_t)warps * (CPW * (MP * MP + 4) + CPW * MP * 5) * sizeof(float);
+    static size_t sm_allowed = 48 * 1024;
+    if (sm > sm_allowed) {
+      GOLF_CUDA(cudaFuncSetAttribute(ss_response_kernel<MP, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      sm_allowed = sm;
     }
-    ss_stitch_kernel<<<p.B, 32, sm, st>>>(p, MP);
+    ss_response_kernel<MP, FORM><<<ceil_div(p.B * wps, warps), warps * 32, sm, st>>>(p, LPC, CPW);
     GOLF_CHECK_LAUNCH();
   }
-  if (passes & 4) {
-    const int warps = 4;
-    const int G = ceil_div(p.C, 32);
-    const size_t sm = warps * (FORM == 0 ? 1 : 2) * 32 * (MP + 1) * sizeof(float);
-    if (generic)
-      ss_solve_kernel<MP, FORM, true><<<ceil_div(p.B * G, warps), warps * 32, sm, st>>>(p);
-    else
-      ss_solve_kernel<MP, FORM, false><<<ceil_div(p.B * G, warps), warps * 32, sm, st>>>(p);
-    GOLF_CHECK_LAUNCH();
+  const size_t sm_stitch =
+      ((size_t)kStitchStages * kStitchGroup * ((MP + 1) * MP + 2 * MP) + 2 * MP) * sizeof(float) + kStitchStages * 8 + 128;
+  static bool attr2 = false;
+  if (!attr2) {
+    GOLF_CUDA(cudaFuncSetAttribute(ss_stitch_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stitch));
+    attr2 = true;
+  }
+  const int G = ceil_div(p.C, 32);
+  const size_t sm_solve = (FORM == 0 ? 1 : 2) * 32 * (MP + 1) * sizeof(float);
+  for (int round = 0; round < 2; ++round) {
+    const bool refine = round == 1;
+    if (refine && !((passes & 8) && nresp > 0)) break;
+    if (refine || (passes & 2)) {
+      ss_stitch_kernel<MP><<<p.B, 32, sm_stitch, st>>>(p, refine ? 1 : 0);
+      GOLF_CHECK_LAUNCH();
+    }
+    if (refine || (passes & 4)) {
+      if (generic)
+        ss_solve_kernel<MP, FORM, true><<<p.B * G, 32, sm_solve, st>>>(p);
+      else
+        ss_solve_kernel<MP, FORM, false><<<p.B * G, 32, sm_solve, st>>>(p);
+      GOLF_CHECK_LAUNCH();
+    }
   }
   return GOLF_OK;
 }
-
 
 }  // namespace golf

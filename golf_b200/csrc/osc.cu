@@ -8,10 +8,11 @@
 //
 // Here:
 //   osc_tables_kernel       tables[b,f,:] = table[lo]*(1-p) + table[lo+1]*p   (L2 resident)
-//   osc_knot_prefix_kernel  the phase increments are piecewise linear between the Np
+//   osc_knot_prefix_*       the phase increments are piecewise linear between the Np
 //                           control knots, so the running sum has a closed form inside a
-//                           knot interval; only the per-knot prefix needs a scan.  Done in
-//                           float64, one CTA per utterance (frac part kept).
+//                           knot interval; only the per-knot prefix needs a scan.  Default:
+//                           exact 64-bit fixed point (Q0.64 cycles, wraps at one period,
+//                           integer adds -> order-independent, no FP64 unit needed).
 //                           accumulate=1 ("aten_cpu") keeps the unwrapped sum and rounds it
 //                           to float32 before `% 1`, which is what ATen's CPU cumsum does
 //                           (double accumulator, float32 output) -- used for parity checks.
@@ -46,16 +47,19 @@ __global__ void __launch_bounds__(256) osc_knot_prefix_kernel(const float* __res
                                                               int Np, int hp, int os, int wrap) {
   __shared__ double part[256];
   const int b = blockIdx.x, tid = threadIdx.x;
-  const float* ph = phase + (size_t)b * Np;
+  const float* __restrict__ ph = phase + (size_t)b * Np;
   double* pb = pref + (size_t)b * Np;
   const int per = (Np + 255) / 256;
   const int k0 = tid * per, k1 = min(Np, k0 + per);
-  const double inv_os = 1.0 / (double)os;
+  const double inv_os = 1.0 / (double)os, dh = (double)hp, half = 0.5 * (double)(hp - 1);
+  // interval k contributes hp*x_k + (x_{k+1}-x_k)(hp-1)/2; the loads are independent of the
+  // running sum, so unrolling lets them overlap
   double s = 0.0;
+#pragma unroll 8
   for (int k = k0; k < k1; ++k) {
-    const double xk = (double)ph[k] * inv_os;
-    const double xn = (double)ph[min(k + 1, Np - 1)] * inv_os;
-    s += (double)hp * xk + (xn - xk) * 0.5 * (double)(hp - 1);
+    const double xk = (double)__ldg(ph + k) * inv_os;
+    const double xn = (double)__ldg(ph + min(k + 1, Np - 1)) * inv_os;
+    s += dh * xk + (xn - xk) * half;
   }
   part[tid] = s;
   __syncthreads();
@@ -70,12 +74,75 @@ __global__ void __launch_bounds__(256) osc_knot_prefix_kernel(const float* __res
   }
   __syncthreads();
   double run = part[tid];
+#pragma unroll 8
   for (int k = k0; k < k1; ++k) {
     pb[k] = run;
-    const double xk = (double)ph[k] * inv_os;
-    const double xn = (double)ph[min(k + 1, Np - 1)] * inv_os;
-    run += (double)hp * xk + (xn - xk) * 0.5 * (double)(hp - 1);
+    const double xk = (double)__ldg(ph + k) * inv_os;
+    const double xn = (double)__ldg(ph + min(k + 1, Np - 1)) * inv_os;
+    run += dh * xk + (xn - xk) * half;
     if (wrap) run -= floor(run);
+  }
+}
+
+// ---- exact phase in 64-bit fixed point ------------------------------------------------
+// Default accumulation.  A phase in cycles only matters mod 1, so it is kept as an unsigned
+// Q0.64 fraction: adding increments is exact integer arithmetic that wraps exactly at one
+// cycle, is associative (any scan order gives the same bits) and needs no FP64 unit.
+__device__ __forceinline__ uint64_t q64_from_float(float x) {  // x in [0, 1): x * 2^64 (exact for x >= 2^-40)
+  const uint32_t u = __float_as_uint(x);
+  const int e = (int)((u >> 23) & 0xff);
+  const uint64_t m = (uint64_t)((u & 0x7fffffu) | (e ? 0x800000u : 0u));
+  const int sh = (e ? e : 1) - 86;  // value = m * 2^(e-150); times 2^64
+  return sh >= 0 ? (sh < 64 ? m << sh : 0ull) : (sh > -64 ? m >> (-sh) : 0ull);
+}
+// increment sum of knot interval k: hp*X_k + (X_{k+1}-X_k)(hp-1)/2   (mod 2^64)
+__device__ __forceinline__ uint64_t q64_interval(uint64_t xk, uint64_t xn, int hp) {
+  const int64_t half = ((int64_t)(xn - xk)) >> 1;
+  return xk * (uint64_t)hp + (uint64_t)(half * (int64_t)(hp - 1));
+}
+
+__global__ void __launch_bounds__(1024) osc_knot_prefix_q64_kernel(const float* __restrict__ phase,
+                                                                   unsigned long long* __restrict__ pref, int Np, int hp,
+                                                                   float os_f) {
+  __shared__ unsigned long long wsum[32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* __restrict__ ph = phase + (size_t)b * Np;
+  unsigned long long* pb = pref + (size_t)b * Np;
+  const int per = (Np + 1023) / 1024;
+  const int k0 = min(tid * per, Np), k1 = min(Np, k0 + per);
+  unsigned long long s = 0;
+#pragma unroll 4
+  for (int k = k0; k < k1; ++k) {
+    const uint64_t xk = q64_from_float(__fdiv_rn(__ldg(ph + k), os_f));
+    const uint64_t xn = q64_from_float(__fdiv_rn(__ldg(ph + min(k + 1, Np - 1)), os_f));
+    s += q64_interval(xk, xn, hp);
+  }
+  // exclusive block scan of the per-thread sums (integer adds: order does not matter)
+  unsigned long long inc = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += v;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = wsum[lane], winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long v = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += v;
+    }
+    wsum[lane] = winc - w;
+  }
+  __syncthreads();
+  unsigned long long run = wsum[warp] + (inc - s);
+#pragma unroll 4
+  for (int k = k0; k < k1; ++k) {
+    pb[k] = run;
+    const uint64_t xk = q64_from_float(__fdiv_rn(__ldg(ph + k), os_f));
+    const uint64_t xn = q64_from_float(__fdiv_rn(__ldg(ph + min(k + 1, Np - 1)), os_f));
+    run += q64_interval(xk, xn, hp);
   }
 }
 
@@ -90,8 +157,8 @@ __device__ __forceinline__ float osc_read(const float* __restrict__ tb, int R, i
                                           float ydenom, int blocks) {
   const float gx = __fsub_rn(__fmul_rn(wrapped, 2.f), 1.f);
   const float gy = __fsub_rn(__fmul_rn(__fdiv_rn((float)t, ydenom), 2.f), 1.f);
-  const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)P);
-  const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), (float)blocks);
+  const float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), (float)P);  // (x+1)/2: *0.5 is the same float
+  const float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)blocks);
   const float x0f = floorf(ix), y0f = floorf(iy);
   const float fx = __fsub_rn(ix, x0f), fy = __fsub_rn(iy, y0f);
   const int x0 = (int)x0f, y0 = (int)y0f;
@@ -153,34 +220,54 @@ __global__ void __launch_bounds__(128) osc_flow_decimate_kernel(OscParams p) {
     const int n = q * p.os + phs;
     hp_[i] = (n <= 2 * Z * p.os) ? (p.dec ? p.dec[n] : 1.f) : 0.f;
   }
-  // oversampled samples u in [(m0-Z)*os, (m0-Z)*os + os*plen): vp[phs][j] = v[(m0-Z+j)*os + phs]
-  const int total = p.os * p.plen;
-  for (int i = tid; i < total; i += blockDim.x) {
-    const int j = i / p.os, phs = i % p.os;  // consecutive threads -> consecutive oversampled times
-    const int t = (m0 - Z + j) * p.os + phs;
-    float v = 0.f;
-    if (t >= 0 && t < p.N) {
-      const float inc = osc_inc(ph, t, p.scale, p.Np, os_f);
-      float wr;
-      {
-        const int k = min(t / p.hp, p.Np - 1), r = t - k * p.hp;
-        const double xk = (double)ph[k] / (double)p.os;
-        const double xn = (double)ph[min(k + 1, p.Np - 1)] / (double)p.os;
-        double phi = p.pref[(size_t)b * p.Np + k] + (double)(r + 1) * xk +
-                     (xn - xk) * ((double)r * (double)(r + 1)) / (2.0 * (double)p.hp);
+  // strip index j <-> output-rate index mj = m0 - Z + j; its `os` oversampled samples
+  // t = mj*os + phs share one knot interval (knot spacing hp = phase_hop*os), so the float64
+  // prefix / slope are fetched once per j:  vp[phs][j] = v[mj*os + phs]
+  const int phase_hop = p.hp / p.os;
+  const double inv_os = 1.0 / (double)p.os, inv_2hp = 1.0 / (2.0 * (double)p.hp);
+  for (int j = tid; j < p.plen; j += blockDim.x) {
+    const int mj = m0 - Z + j;
+    const bool in = mj >= 0 && (int64_t)mj * p.os < p.N;
+    int k = 0, r0 = 0;
+    double xk = 0.0, dk = 0.0, pk = 0.0;        // aten_cpu: float64 running sum
+    uint64_t qx = 0, qp = 0;                     // default: Q0.64 fixed point
+    int64_t qq = 0;
+    if (in) {
+      k = phase_hop == 1 ? mj : mj / phase_hop;
+      k = min(k, p.Np - 1);
+      r0 = (mj - k * phase_hop) * p.os;
+      const float fk = __ldg(ph + k), fn = __ldg(ph + min(k + 1, p.Np - 1));
+      if (p.aten_cpu) {
+        xk = (double)fk * inv_os;
+        dk = (double)fn * inv_os - xk;
+        pk = __ldg(p.pref + (size_t)b * p.Np + k);
+      } else {
+        qx = q64_from_float(__fdiv_rn(fk, os_f));
+        const uint64_t qn = q64_from_float(__fdiv_rn(fn, os_f));
+        qq = (int64_t)(qn - qx) / (int64_t)(2 * p.hp);  // slope term per r(r+1)
+        qp = reinterpret_cast<const unsigned long long*>(p.pref)[(size_t)b * p.Np + k];
+      }
+    }
+    for (int phs = 0; phs < p.os; ++phs) {
+      const int t = mj * p.os + phs;
+      float v = 0.f;
+      if (in && t < p.N) {
+        const int r = r0 + phs;
+        float wr;
         if (p.aten_cpu) {  // cumsum output is float32, then `% 1` in float32
+          const double phi = pk + (double)(r + 1) * xk + dk * ((double)r * (double)(r + 1)) * inv_2hp;
           const float f = (float)phi;
           wr = __fsub_rn(f, floorf(f));
         } else {
-          phi -= floor(phi);
-          wr = (float)phi;
+          const uint64_t phi = qp + (uint64_t)(r + 1) * qx + (uint64_t)(qq * (int64_t)(r * (r + 1)));
+          wr = __fmul_rn(__ull2float_rn(phi), 5.42101086242752217e-20f);  // * 2^-64
           if (wr >= 1.f) wr = 0.f;
         }
+        v = osc_read(tb, p.Fw, p.P, wr, t, p.ydenom, p.blocks);
+        if (p.equal_energy) v = __fmul_rn(v, __fdiv_rn(1.f, __fsqrt_rn(osc_inc(ph, t, p.scale, p.Np, os_f))));
       }
-      v = osc_read(tb, p.Fw, p.P, wr, t, p.ydenom, p.blocks);
-      if (p.equal_energy) v = __fmul_rn(v, __fdiv_rn(1.f, __fsqrt_rn(inc)));
+      vp[phs * p.plen + j] = v;
     }
-    vp[phs * p.plen + j] = v;
   }
   __syncthreads();
   const int r0 = tid * kR;  // outputs m0 + r0 .. m0 + r0 + 7
@@ -237,7 +324,10 @@ GOLF_API int golf_glottal_osc_fwd(const float* phase, const float* w, const floa
   osc_tables_kernel<<<ceil_div(B * Fw * P, 256), 256, 0, st>>>(w, table, tables, B * Fw, n_tab, P);
   GOLF_CHECK_LAUNCH();
   if (accumulate != 0 && accumulate != 1) return GOLF_ERR_INVALID;
-  osc_knot_prefix_kernel<<<B, 256, 0, st>>>(phase, pref, Np, L.hp, os, accumulate == 0 ? 1 : 0);
+  if (accumulate == 0)
+    osc_knot_prefix_q64_kernel<<<B, 1024, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), Np, L.hp, (float)os);
+  else
+    osc_knot_prefix_kernel<<<B, 256, 0, st>>>(phase, pref, Np, L.hp, os, 0);
   GOLF_CHECK_LAUNCH();
   OscParams p{};
   p.phase = phase, p.tables = tables, p.pref = pref, p.aten_cpu = accumulate;

@@ -78,12 +78,12 @@ class LTVMinimumPhaseFilterPrecise(LTVFilterInterface):
             )
 
     def forward(self, ex, gain, a):
-        assert ex.ndim == 2 and gain.ndim == 2 and a.ndim == 3
-        assert a.shape[1] == gain.shape[1]
+        x, g, c = plain(ex), plain(gain), plain(a)
+        assert x.ndim == 2 and g.ndim == 2 and c.ndim == 3
+        assert c.shape[1] == g.shape[1]
         hop, ex_hop = hop_of(gain), hop_of(ex)
         assert hop % ex_hop == 0 and hop_of(a, hop) == hop, (ex_hop, hop, hop_of(a))
-        y = G.lpc_ss(plain(ex), plain(gain), plain(a), hop // ex_hop)
-        return like(ex, y, ex_hop)
+        return like(ex, G.lpc_ss(x, g, c, hop // ex_hop), ex_hop)
 
     def reverse(self, ex, y, gain, a) -> Tuple[AudioTensor, AudioTensor]:
         """inverse-filter the target (models/filters.py:186-195): returns (ex*gain, A(z) y)"""
@@ -107,19 +107,19 @@ class LTVMinimumPhaseFilter(LTVMinimumPhaseFilterPrecise):
         self.centred = centred
 
     def forward(self, ex, gain, a):
-        assert a.shape[1] == gain.shape[1]
+        x, g, c = plain(ex), plain(gain), plain(a)
+        assert c.shape[1] == g.shape[1]
         hop = hop_of(gain) // hop_of(ex)
         W = self._window.shape[0]
         assert W >= hop * 2, f"{W} < {hop * 2}"
-        x = plain(ex)
         if not self.centred:
             x = x[..., hop // 2 :]
-        if torch.is_grad_enabled() and any(t.requires_grad for t in (ex, gain, a)):
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (x, g, c)):
             raise GolfError(
                 "LTVMinimumPhaseFilter: the frame-wise CUDA path is forward-only in this build; "
                 "train with LTVMinimumPhaseFilterPrecise (differentiable) or wrap the call in torch.no_grad()"
             )
-        y = G.lpc_ff(x, plain(gain), plain(a), self._window, hop)
+        y = G.lpc_ff(x, g, c, self._window, hop)
         if not self.centred:
             y = F.pad(y[:, None], (hop // 2, 0), "reflect")[:, 0]
         return like(ex, y, hop_of(ex))
@@ -146,12 +146,24 @@ class LTVZeroPhaseFIRFilter(LTVFilterInterface):
     def windowing(self, kernel: torch.Tensor) -> torch.Tensor:
         return kernel * self.window_fn(kernel.shape[-1], device=kernel.device, dtype=kernel.dtype)
 
+    def _window(self, K: int, like_t: torch.Tensor) -> torch.Tensor:
+        key = (K, like_t.device)
+        if getattr(self, "_win_key", None) != key:
+            self._win_cache = self.window_fn(K, device=like_t.device, dtype=torch.float32)
+            self._win_key = key
+        return self._win_cache
+
     def forward(self, ex, log_mag, add=None):
         hop = hop_of(log_mag) // hop_of(ex)
-        kernel = self.windowing(self.get_zero_phase_fir(plain(log_mag)))
-        if torch.is_grad_enabled() and (kernel.requires_grad or ex.requires_grad):
-            raise GolfError("LTVZeroPhaseFIRFilter: forward-only in this build (wrap in torch.no_grad())")
-        y = G.ltv_fir_blocks(plain(ex), kernel, hop, None if add is None else plain(add))
+        lm, x = plain(log_mag), plain(ex)
+        add = None if add is None else plain(add)
+        need_grad = torch.is_grad_enabled() and (lm.requires_grad or x.requires_grad or (add is not None and add.requires_grad))
+        if need_grad:  # differentiable path: final taps built by torch (frame rate), FIR + adjoint in CUDA
+            kernel = self.windowing(self.get_zero_phase_fir(lm))
+            y = G.ltv_fir_blocks(x, kernel, hop, add)
+        else:  # inference: cuFFT gives the raw impulse responses, shift + window ride along in the FIR kernel
+            raw = torch.fft.irfft(torch.exp(lm).to(torch.complex64), dim=-1)
+            y = G.ltv_fir_blocks(x, raw, hop, add, window=self._window(raw.shape[-1], raw))
         return like(ex, y, hop_of(ex))
 
 
@@ -167,8 +179,6 @@ class LTIAcousticFilter(FilterInterface):
         self._padding = length - 1
 
     def forward(self, ex):
-        if torch.is_grad_enabled() and (self.kernel.requires_grad or ex.requires_grad):
-            raise GolfError("LTIAcousticFilter: forward-only in this build (wrap in torch.no_grad())")
         return like(ex, G.room_fir(plain(ex), self.kernel), hop_of(ex))
 
     @property

@@ -59,6 +59,24 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class _on:
+    """`with _on(device):` -- make `device` current for the launch; free when it already is"""
+
+    __slots__ = ("dev", "prev")
+
+    def __init__(self, device):
+        self.dev = device.index if device.index is not None else torch.cuda.current_device()
+
+    def __enter__(self):
+        self.prev = torch.cuda.current_device()
+        if self.prev != self.dev:
+            torch.cuda.set_device(self.dev)
+
+    def __exit__(self, *exc):
+        if self.prev != self.dev:
+            torch.cuda.set_device(self.prev)
+
+
 def _workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
@@ -68,7 +86,7 @@ def lpc_ss_length(t_ex: int, frames: int, hop: int) -> int:
     return min(int(t_ex), (int(frames) - 1) * int(hop) + 1)
 
 
-def _lpc_ss_fwd(ex, gain, a, zi, hop: int, chunk: int = 0, passes: int = 7):
+def _lpc_ss_fwd(ex, gain, a, zi, hop: int, chunk: int = 0, passes: int = 15):
     ex = _rows(ex, "ex")
     a = _cuda_f32(a, "a")
     gain = None if gain is None else _cuda_f32(gain, "gain")
@@ -84,14 +102,14 @@ def _lpc_ss_fwd(ex, gain, a, zi, hop: int, chunk: int = 0, passes: int = 7):
     if nbytes == 0:
         raise GolfError(f"lpc_ss: unsupported configuration B={B} L={L} M={M} hop={hop} chunk={chunk}")
     ws = _workspace(nbytes, ex.device)
-    with torch.cuda.device(ex.device):
+    with _on(ex.device):
         rc = lib.golf_lpc_ss_fwd_passes(_ptr(ex), ex.stride(0), _ptr(gain), _ptr(a), _ptr(zi), _ptr(y), B, L, Fr, M, hop, chunk,
                                         _ptr(ws), ws.numel(), passes, _stream())
     check(rc, "golf_lpc_ss_fwd")
     return y
 
 
-def _lpc_ss_bwd(gy, y, ex, gain, a, zi, hop: int, need, chunk: int = 0):
+def _lpc_ss_bwd(gy, y, ex, gain, a, zi, hop: int, need, chunk: int = 0, refine: bool = True):
     """need = (ex, gain, a, zi) booleans -> gradients (None where not needed)."""
     gy = _cuda_f32(gy, "gy")
     y = _cuda_f32(y, "y")
@@ -108,42 +126,44 @@ def _lpc_ss_bwd(gy, y, ex, gain, a, zi, hop: int, need, chunk: int = 0):
     d_zi = torch.empty(B, M, dtype=torch.float32, device=dev) if (need[3] and zi is not None) else None
     lib = _lib.lib()
     ws = _workspace(lib.golf_lpc_ss_bwd_workspace_bytes(B, L, M, hop, chunk), dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         rc = lib.golf_lpc_ss_bwd(_ptr(gy), _ptr(y), _ptr(ex), ex.stride(0), _ptr(gain), _ptr(a), _ptr(zi), _ptr(d_ex),
-                                 _ptr(d_gain), _ptr(d_a), _ptr(d_zi), B, L, Fr, M, hop, chunk, _ptr(ws), ws.numel(), _stream())
+                                 _ptr(d_gain), _ptr(d_a), _ptr(d_zi), B, L, Fr, M, hop, chunk, 1 if refine else 0, _ptr(ws), ws.numel(), _stream())
     check(rc, "golf_lpc_ss_bwd")
     return d_ex, d_gain, d_a, d_zi
 
 
 class _LpcSS(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ex, gain, a, zi, hop, chunk):
-        y = _lpc_ss_fwd(ex, gain, a, zi, hop, chunk)
+    def forward(ctx, ex, gain, a, zi, hop, chunk, refine):
+        y = _lpc_ss_fwd(ex, gain, a, zi, hop, chunk, 15 if refine else 7)
         ctx.save_for_backward(ex, gain, a, zi, y)
-        ctx.hop, ctx.chunk = hop, chunk
+        ctx.hop, ctx.chunk, ctx.refine = hop, chunk, refine
         return y
 
     @staticmethod
     def backward(ctx, gy):
         ex, gain, a, zi, y = ctx.saved_tensors
         need = ctx.needs_input_grad[:4]
-        d_ex, d_gain, d_a, d_zi = _lpc_ss_bwd(gy, y, ex, gain, a, zi, ctx.hop, need, ctx.chunk)
+        d_ex, d_gain, d_a, d_zi = _lpc_ss_bwd(gy, y, ex, gain, a, zi, ctx.hop, need, ctx.chunk, ctx.refine)
         if d_ex is not None and d_ex.shape[1] < ex.shape[1]:  # ex was longer than the filtered span
             d_ex = torch.nn.functional.pad(d_ex, (0, ex.shape[1] - d_ex.shape[1]))
-        return d_ex, d_gain, d_a, d_zi, None, None
+        return d_ex, d_gain, d_a, d_zi, None, None, None
 
 
-def lpc_ss(ex, gain, a, hop: int, zi=None, chunk: int = 0) -> torch.Tensor:
+def lpc_ss(ex, gain, a, hop: int, zi=None, chunk: int = 0, refine: bool = True) -> torch.Tensor:
     """y[t] = ex[t]*up(gain)[t] - sum_i up(a)[t,i] y[t-1-i]; ex [B,T], gain [B,F], a [B,F,M] at
-    `hop`; returns [B, min(T,(F-1)*hop+1)].  Differentiable in ex, gain, a, zi."""
-    return _LpcSS.apply(ex, gain, a, zi, int(hop), int(chunk))
+    `hop`; returns [B, min(T,(F-1)*hop+1)].  Differentiable in ex, gain, a, zi.
+    refine=False skips the chunk-boundary refinement round (faster; up to ~10x less accurate
+    on high-gain filters)."""
+    return _LpcSS.apply(ex, gain, a, zi, int(hop), int(chunk), bool(refine))
 
 
 def sample_wise_lpc(x, a, zi=None) -> torch.Tensor:
     """torchlpc.sample_wise_lpc: x [B,T], a [B,T,M] sample-rate coefficients, zi [B,M]."""
     if x.ndim != 2 or a.ndim != 3 or a.shape[:2] != x.shape:
         raise GolfError(f"sample_wise_lpc: x{tuple(x.shape)} a{tuple(a.shape)}")
-    return _LpcSS.apply(x, None, a, zi, 1, 0)
+    return _LpcSS.apply(x, None, a, zi, 1, 0, True)
 
 
 # ------------------------------------------------------------------------- GOLF-ff
@@ -160,7 +180,7 @@ def lpc_ff(ex, gain, a, window, hop: int) -> torch.Tensor:
         raise AssertionError(f"{n_frames} frames but only {Fr} control frames")  # filters.py:157
     out_len = (n_frames - 1) * hop + win - 2 * (win // 2)
     y = torch.empty(B, out_len, dtype=torch.float32, device=ex.device)
-    with torch.cuda.device(ex.device):
+    with _on(ex.device):
         rc = _lib.lib().golf_lpc_ff_fwd(_ptr(ex), ex.stride(0), _ptr(gain), _ptr(a), _ptr(window), _ptr(y), B, Tex, Fr, M,
                                         hop, win, _stream())
     check(rc, "golf_lpc_ff_fwd")
@@ -178,7 +198,7 @@ def biquad_ff(ex, gain, biquads, window, hop: int) -> torch.Tensor:
     if n_frames > Fr:
         raise AssertionError(f"{n_frames} frames but only {Fr} control frames")  # lpc.py:102-104
     y = torch.empty(B, (n_frames - 1) * hop + win - 2 * pad, dtype=torch.float32, device=ex.device)
-    with torch.cuda.device(ex.device):
+    with _on(ex.device):
         rc = _lib.lib().golf_biquad_ff_fwd(_ptr(ex), ex.stride(0), _ptr(gain), _ptr(biquads), _ptr(window), _ptr(y), B, Tex,
                                            Fr, K, hop, win, _stream())
     check(rc, "golf_biquad_ff_fwd")
@@ -192,46 +212,108 @@ def lpc_inverse(y, a, hop: int) -> torch.Tensor:
     Fr, M = a.shape[1], a.shape[2]
     L = lpc_ss_length(T, Fr, hop)
     r = torch.empty(B, L, dtype=torch.float32, device=y.device)
-    with torch.cuda.device(y.device):
+    with _on(y.device):
         rc = _lib.lib().golf_lpc_inverse_fwd(_ptr(y), y.stride(0), _ptr(a), _ptr(r), B, L, Fr, M, hop, _stream())
     check(rc, "golf_lpc_inverse_fwd")
     return r
 
 
 # ---------------------------------------------------------------------- FIR stages
-def ltv_fir_blocks(ex, kernel, hop: int, add=None) -> torch.Tensor:
-    """Block FIR with per-frame kernels [B,F,K]; optional fused `add + result`."""
+def _fir_blocks_count(T: int, Fr: int, K: int, hop: int) -> int:
+    p = (K - 1) // 2
+    return min((T + 2 * p - (K + hop - 1)) // hop + 1, Fr)
+
+
+def _ltv_fir_fwd(ex, kernel, hop, add=None, window=None):
     ex = _rows(ex, "ex")
     kernel = _cuda_f32(kernel, "kernel")
+    window = None if window is None else _cuda_f32(window, "window")
     B, T = ex.shape
     Fr, K = kernel.shape[1], kernel.shape[2]
-    p = (K - 1) // 2
-    n_blocks = min((T + 2 * p - (K + hop - 1)) // hop + 1, Fr)
+    n_blocks = _fir_blocks_count(T, Fr, K, hop)
     if add is not None:
         add = _rows(add, "add")
         if add.shape[1] < n_blocks * hop:
             raise GolfError("ltv_fir_blocks: `add` shorter than the output")
     y = torch.empty(B, n_blocks * hop, dtype=torch.float32, device=ex.device)
-    with torch.cuda.device(ex.device):
-        rc = _lib.lib().golf_noise_fir_fwd(_ptr(ex), ex.stride(0), _ptr(kernel), _ptr(add), 0 if add is None else add.stride(0),
-                                           _ptr(y), B, T, Fr, K, hop, _stream())
+    with _on(ex.device):
+        rc = _lib.lib().golf_noise_fir_fwd(_ptr(ex), ex.stride(0), _ptr(kernel), _ptr(window), _ptr(add),
+                                           0 if add is None else add.stride(0), _ptr(y), B, T, Fr, K, hop, _stream())
     check(rc, "golf_noise_fir_fwd")
     return y
 
 
+class _LtvFir(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ex, kernel, add, hop):
+        y = _ltv_fir_fwd(ex, kernel, hop, add)
+        ctx.save_for_backward(ex, kernel)
+        ctx.hop, ctx.has_add = hop, add is not None
+        ctx.add_len = 0 if add is None else add.shape[1]
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        ex, kernel = ctx.saved_tensors
+        gy = _cuda_f32(gy, "gy")
+        exr = _rows(ex, "ex")
+        kern = _cuda_f32(kernel, "kernel")
+        B, T = exr.shape
+        Fr, K = kern.shape[1], kern.shape[2]
+        d_ex = torch.empty(B, T, dtype=torch.float32, device=gy.device) if ctx.needs_input_grad[0] else None
+        d_k = torch.empty_like(kern) if ctx.needs_input_grad[1] else None
+        with _on(gy.device):
+            rc = _lib.lib().golf_noise_fir_bwd(_ptr(gy), _ptr(exr), exr.stride(0), _ptr(kern), _ptr(d_ex), _ptr(d_k), B, T, Fr, K,
+                                               ctx.hop, _stream())
+        check(rc, "golf_noise_fir_bwd")
+        d_add = None
+        if ctx.has_add and ctx.needs_input_grad[2]:
+            d_add = torch.nn.functional.pad(gy, (0, ctx.add_len - gy.shape[1])) if ctx.add_len > gy.shape[1] else gy
+        return d_ex, d_k, d_add, None
+
+
+def ltv_fir_blocks(ex, kernel, hop: int, add=None, window=None) -> torch.Tensor:
+    """Block FIR with per-frame kernels [B,F,K]; optional fused `add + result`.  With `window`
+    ([K]) the kernel argument is the raw irfft output and fftshift + windowing are fused into the
+    tap staging (inference path, no autograd)."""
+    if window is not None:
+        return _ltv_fir_fwd(ex, kernel, int(hop), add, window)
+    return _LtvFir.apply(ex, kernel, add, int(hop))
+
+
+class _RoomFir(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k):
+        xc, kc = _cuda_f32(x, "x"), _cuda_f32(k, "k")
+        B, T = xc.shape
+        out = torch.empty_like(xc)
+        with _on(xc.device):
+            rc = _lib.lib().golf_room_fir_fwd(_ptr(xc), _ptr(kc), _ptr(out), B, T, kc.numel(), _stream())
+        check(rc, "golf_room_fir_fwd")
+        ctx.save_for_backward(xc, kc)
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        xc, kc = ctx.saved_tensors
+        gy = _cuda_f32(gy, "gy")
+        B, T = xc.shape
+        d_x = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        d_k = torch.empty_like(kc) if ctx.needs_input_grad[1] else None
+        with _on(gy.device):
+            rc = _lib.lib().golf_room_fir_bwd(_ptr(gy), _ptr(xc), _ptr(kc), _ptr(d_x), _ptr(d_k), B, T, kc.numel(), _stream())
+        check(rc, "golf_room_fir_bwd")
+        return d_x, d_k
+
+
 def room_fir(x, k) -> torch.Tensor:
-    x, k = _cuda_f32(x, "x"), _cuda_f32(k, "k")
-    B, T = x.shape
-    out = torch.empty_like(x)
-    with torch.cuda.device(x.device):
-        rc = _lib.lib().golf_room_fir_fwd(_ptr(x), _ptr(k), _ptr(out), B, T, k.numel(), _stream())
-    check(rc, "golf_room_fir_fwd")
-    return out
+    """out[t] = x[t] + sum_j k[j] x[t-len(k)+j]; differentiable in x and k."""
+    return _RoomFir.apply(x, k)
 
 
 # ---------------------------------------------------------------------- oscillator
 def glottal_osc(phase, phase_hop: int, w, w_hop: int, table, dec_kernel=None, oversampling: int = 1,
-                equal_energy: bool = False, accumulate: str = "fp64") -> torch.Tensor:
+                equal_energy: bool = False, accumulate: str = "exact") -> torch.Tensor:
     phase, w, table = _cuda_f32(phase, "phase"), _cuda_f32(w, "w"), _cuda_f32(table, "table")
     dec_kernel = None if dec_kernel is None else _cuda_f32(dec_kernel, "dec_kernel")
     B, Np = phase.shape
@@ -243,8 +325,8 @@ def glottal_osc(phase, phase_hop: int, w, w_hop: int, table, dec_kernel=None, ov
     out = torch.empty(B, (N - 1) // os_ + 1, dtype=torch.float32, device=phase.device)
     lib = _lib.lib()
     ws = _workspace(lib.golf_glottal_osc_workspace_bytes(B, Np, phase_hop, Fw, P, os_), phase.device)
-    mode = {"fp64": 0, "aten_cpu": 1}[accumulate]
-    with torch.cuda.device(phase.device):
+    mode = {"exact": 0, "fp64": 0, "aten_cpu": 1}[accumulate]
+    with _on(phase.device):
         rc = lib.golf_glottal_osc_fwd(_ptr(phase), _ptr(w), _ptr(table), _ptr(dec_kernel), _ptr(out), B, Np, phase_hop, Fw,
                                       w_hop, n_tab, P, os_, zeros, mode, 1 if equal_energy else 0, _ptr(ws), ws.numel(), _stream())
     check(rc, "golf_glottal_osc_fwd")
@@ -256,7 +338,7 @@ def wavetable_read(wrapped, tables, hop_tab: int) -> torch.Tensor:
     B, N = wrapped.shape
     R, P = tables.shape[1], tables.shape[2]
     out = torch.empty_like(wrapped)
-    with torch.cuda.device(wrapped.device):
+    with _on(wrapped.device):
         rc = _lib.lib().golf_wavetable_read_fwd(_ptr(wrapped), _ptr(tables), _ptr(out), B, N, R, P, hop_tab, _stream())
     check(rc, "golf_wavetable_read_fwd")
     return out
@@ -269,7 +351,7 @@ def linear_upsample(x, hop: int) -> torch.Tensor:
     n = x.shape[-1]
     rows = x.numel() // n
     out = torch.empty(x.shape[:-1] + ((n - 1) * hop + 1,), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         rc = _lib.lib().golf_linear_upsample(_ptr(x), _ptr(out), rows, n, hop, _stream())
     check(rc, "golf_linear_upsample")
     return out
@@ -280,7 +362,7 @@ def rc2lpc(logits, max_abs: float = 1.0) -> torch.Tensor:
     logits = _cuda_f32(logits, "logits")
     M = logits.shape[-1]
     a = torch.empty_like(logits)
-    with torch.cuda.device(logits.device):
+    with _on(logits.device):
         rc = _lib.lib().golf_rc2lpc_fwd(_ptr(logits), _ptr(a), logits.numel() // M, M, float(max_abs), _stream())
     check(rc, "golf_rc2lpc_fwd")
     return a

@@ -32,15 +32,14 @@ CHECK_INPUTS = "sync"
 
 
 def _check_phase(m, args):
-    phase = args[0]
-    assert phase.ndim == 2, phase.shape
+    p = plain(args[0])
+    assert p.ndim == 2, p.shape
     if CHECK_INPUTS == "sync":
-        p = plain(phase)
         assert bool(((p >= 0) & (p <= 0.5)).all()), "phase (cycles/sample) must lie in [0, 0.5]"
 
 
 def _check_out(m, args, out):
-    assert out.ndim == 2, out.shape
+    assert plain(out).ndim == 2
     assert hop_of(out, -1) == 1
 
 
@@ -107,9 +106,9 @@ class GlottalFlowTable(OscillatorInterface):
 
 
 class IndexedGlottalFlowTable(GlottalFlowTable):
-    # "fp64": exact running phase (default); "aten_cpu": the reference's CPU arithmetic
+    # "exact": running phase in 64-bit fixed point (default); "aten_cpu": the reference CPU arithmetic
     # (float64 accumulate, float32 round, then mod 1) for parity checks
-    phase_accumulation = "fp64"
+    phase_accumulation = "exact"
 
     def __init__(self, *args, oversampling: int = 1, equal_energy: bool = False, **kwargs):
         super().__init__(*args, **kwargs)
@@ -121,10 +120,10 @@ class IndexedGlottalFlowTable(GlottalFlowTable):
             self.decimater.register_buffer("kernel", self.decimater.kernel, persistent=False)
 
     def forward(self, phase, table_select_weight, phase_offset=None):
-        assert table_select_weight.dim() == 2
+        w = plain(table_select_weight)
+        assert w.dim() == 2
         if phase_offset is not None:
             raise NotImplementedError("phase_offset is not used by the GOLF configs and is not fused")
-        w = plain(table_select_weight)
         if CHECK_INPUTS == "sync":
             assert bool(((w >= 0) & (w <= 1)).all()), "table_select_weight must lie in [0, 1]"
         dk = self.decimater.kernel if self.oversampling > 1 else None

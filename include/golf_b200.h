@@ -65,7 +65,9 @@ int golf_lpc_ss_fwd(const float *ex, int64_t ex_stride, const float *gain, const
                     const float *zi, float *y, int B, int L, int F, int M, int hop,
                     int chunk, void *workspace, size_t workspace_bytes, void *stream);
 /* Same, running only the selected passes (bit 0: chunk responses, bit 1: stitch, bit 2:
- * solve) -- for per-kernel timing in bench.py; passes == 7 is golf_lpc_ss_fwd. */
+ * solve, bit 3: one refinement round = mismatch stitch + solve again).  golf_lpc_ss_fwd is
+ * passes == 15; 7 skips the refinement (faster, less accurate on high-gain filters);
+ * single bits are for per-kernel timing in bench.py. */
 int golf_lpc_ss_fwd_passes(const float *ex, int64_t ex_stride, const float *gain,
                            const float *a, const float *zi, float *y, int B, int L, int F,
                            int M, int hop, int chunk, void *workspace, size_t workspace_bytes,
@@ -76,7 +78,7 @@ size_t golf_lpc_ss_bwd_workspace_bytes(int B, int L, int M, int hop, int chunk);
 int golf_lpc_ss_bwd(const float *gy, const float *y, const float *ex, int64_t ex_stride,
                     const float *gain, const float *a, const float *zi, float *d_ex,
                     float *d_gain, float *d_a, float *d_zi, int B, int L, int F, int M,
-                    int hop, int chunk, void *workspace, size_t workspace_bytes,
+                    int hop, int chunk, int refine, void *workspace, size_t workspace_bytes,
                     void *stream);
 
 /* ------------------------------------------------------------------ GOLF-ff ---- */
@@ -104,21 +106,32 @@ int golf_lpc_inverse_fwd(const float *y, int64_t y_stride, const float *a, float
  * cross-correlation of ex zero-padded by (K-1)/2 with kernel[b,k,:];
  * n_blocks = min((T + 2*((K-1)/2) - (K+hop-1))/hop + 1, F); y [B, n_blocks*hop].
  * If add != NULL ([B, >= n_blocks*hop], row stride add_stride) it is added to the
- * result (fuses `harm + noise_filter(noise)`, models/sf.py:53-56). */
+ * result (fuses `harm + noise_filter(noise)`, models/sf.py:53-56).
+ * If window != NULL ([K], K even), `kernel` is the RAW irfft(exp(log_mag)) output and the
+ * fftshift + windowing of models/filters.py:294-306 happen while the taps are staged. */
 int golf_noise_fir_fwd(const float *ex, int64_t ex_stride, const float *kernel,
-                       const float *add, int64_t add_stride, float *y, int B, int T, int F,
+                       const float *window, const float *add, int64_t add_stride, float *y,
+                       int B, int T, int F, int K, int hop, void *stream);
+/* Adjoint w.r.t. the input (d_ex [B,T]) and the final taps (d_kernel [B,F,K]); either may be
+ * NULL.  gy [B, n_blocks*hop]. */
+int golf_noise_fir_bwd(const float *gy, const float *ex, int64_t ex_stride,
+                       const float *kernel, float *d_ex, float *d_kernel, int B, int T, int F,
                        int K, int hop, void *stream);
 /* out[t] = x[t] + sum_{j<n} k[j] x[t-n+j]   (n = length-1 learned taps) */
 int golf_room_fir_fwd(const float *x, const float *k, float *out, int B, int T, int n,
                       void *stream);
+/* Adjoint: d_x [B,T] and d_k [n] (either may be NULL).  d_k is accumulated with float
+ * atomics: its last bit is not reproducible run to run. */
+int golf_room_fir_bwd(const float *gy, const float *x, const float *k, float *d_x, float *d_k,
+                      int B, int T, int n, void *stream);
 
 /* -------------------------------------------------------------- oscillator ---- */
 /* Glottal-flow wavetable oscillator at `os`x oversampling.
  * phase [B,Np] cycles/sample at hop phase_hop; w [B,Fw] in [0,1] at hop w_hop;
  * table [n_tab, P]; dec_kernel [2*zeros*os+1] (os > 1).  N_os = (Np-1)*phase_hop*os+1
  * oversampled samples, out [B, (N_os-1)/os+1].
- * accumulate: 0 = float64 running phase, wrapped in float64 (default; closer to exact
- * than the reference), 1 = "aten_cpu": float64 running sum rounded to float32
+ * accumulate: 0 = exact running phase in 64-bit fixed point (Q0.64 cycles; default,
+ * closer to exact than the reference), 1 = "aten_cpu": float64 running sum rounded to float32
  * before `% 1`, the arithmetic of ATen's CPU cumsum (parity checks).
  * flags bit0: equal_energy (multiply by rsqrt(upsampled phase)). */
 size_t golf_glottal_osc_workspace_bytes(int B, int Np, int phase_hop, int Fw, int P, int os);

@@ -271,19 +271,20 @@ def zero_phase_fir(log_mag: torch.Tensor, window: str = "hanning") -> torch.Tens
 def ltv_fir_blocks(ex: torch.Tensor, kernel: torch.Tensor, hop: int) -> torch.Tensor:
     """models/filters.py:360-384: block k (hop samples) is the valid cross-correlation
     of padded ex[k*hop : k*hop+K+hop-1] with kernel k."""
-    ex, kernel = _f32(ex), _f32(kernel)
+    if not (ex.requires_grad or kernel.requires_grad):
+        ex, kernel = _f32(ex), _f32(kernel)
     B, T = ex.shape
     K = kernel.shape[-1]
     p = (K - 1) // 2
     padded = F.pad(ex, (p, p))
     n_blocks = (padded.shape[1] - (K + hop - 1)) // hop + 1
     n_blocks = min(n_blocks, kernel.shape[1])
-    out = torch.empty(B, n_blocks, hop)
-    for k in range(n_blocks):
-        seg = padded[:, k * hop : k * hop + K + hop - 1]
-        win = seg.unfold(1, K, 1)  # [B, hop, K]
-        out[:, k] = torch.einsum("brj,bj->br", win, kernel[:, k])
-    return out.reshape(B, -1)
+    # one group per (utterance, block): the reference's own formulation (grouped conv1d over the
+    # unfolded input), which is also what makes this leg a fair CPU baseline
+    segs = padded.unfold(1, K + hop - 1, hop)[:, :n_blocks]
+    out = F.conv1d(segs.reshape(1, B * n_blocks, K + hop - 1), kernel[:, :n_blocks].reshape(B * n_blocks, 1, K),
+                   groups=B * n_blocks)
+    return out.view(B, -1)
 
 
 def noise_fir(ex, log_mag, hop: int, window: str = "hanning") -> torch.Tensor:
@@ -295,7 +296,8 @@ def noise_fir(ex, log_mag, hop: int, window: str = "hanning") -> torch.Tensor:
 def room_fir(x: torch.Tensor, k: torch.Tensor) -> torch.Tensor:
     """LTIAcousticFilter.forward, models/filters.py:443-450:
     out[t] = x[t] + sum_{j<len(k)} k[j] x[t-len(k)+j]."""
-    x, k = _f32(x), _f32(k)
+    if not (x.requires_grad or k.requires_grad):
+        x, k = _f32(x), _f32(k)
     n = k.numel()
     xp = F.pad(x[:, None, :-1], (n, 0))
     return x + F.conv1d(xp, k[None, None, :])[:, 0]
