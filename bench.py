@@ -184,6 +184,7 @@ def run_gpu(args):
     import golf_b200
     from golf_b200 import functional as G
     from golf_b200.audiotensor import AudioTensor
+    from golf_b200.sharding import max_over_ranks
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -240,10 +241,7 @@ def run_gpu(args):
             barrier()
             ms = ev[0].elapsed_time(ev[1])
             launches = golf_b200.launch_count() - l0
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = max_over_ranks(ms, dev)  # the job is as slow as its slowest rank
         return ms, launches, out
 
     with ClockSampler(local) as clocks:

@@ -1,40 +1,50 @@
-// lpc_ff.cu -- GOLF-ff: frame-wise LTI all-pole filtering with Hann overlap-add, the
-// cascaded-biquad variant, and the inverse (analysis) filter.
+// lpc_ff.cu -- GOLF-ff: frame-wise LTI all-pole filtering with Hann overlap-add (forward and
+// adjoint), the cascaded-biquad variant, and the inverse (analysis) filter.
 //
 // Replaces models/filters.py:131-184 (LTVMinimumPhaseFilter.forward: ex*gain, pad,
 // unfold(win, hop), models/lpc.py:11-16 lpc_synthesis -> torchaudio lfilter per frame,
-// conv_transpose1d OLA with a dense diag(window) kernel, divide by the OLA'd window),
-// models/lpc.py:94-131 (BatchSecondOrderLPCSynth) and models/filters.py:186-195.
+// conv_transpose1d OLA with a dense diag(window) kernel, divide by the OLA'd window) and
+// torchaudio's DifferentiableIIR.backward; models/lpc.py:94-131 (BatchSecondOrderLPCSynth);
+// models/filters.py:186-195 (reverse) + models/utils.py:433-441 (fir_filt).
 //
-// Mapping: frames are independent, each a serial recurrence of `win` steps from zero
-// state -- one LANE per frame, coefficients and filter state in registers (static
-// rotation, loop unrolled by the padded order MP), taps visited oldest-first exactly
-// like libtorchaudio's CPU loop so consecutive steps overlap in the FMA pipe.
-// A warp owns 32 consecutive frames of one utterance and the 33-NQ padded-coordinate
-// segments (hop samples each, NQ = win/hop) those frames fully determine, so the
-// overlap-add is a shared-memory accumulate with no atomics and no 4x unfold in HBM:
-//   * the warp's excitation strip (ex*up(gain), computed once per sample) is staged in
-//     shared memory, segment stride hop+1 so the per-lane strided reads are bank-
-//     conflict free;
+// Mapping: frames are independent, each a serial recurrence of `win` steps from zero state --
+// one LANE per frame, coefficients and filter state in registers (static rotation, loop
+// unrolled by the padded order MP).  Taps are visited oldest-first like libtorchaudio's CPU
+// loop, in three interleaved chains with the newest tap last, so only one FMA per step sits on
+// the serial dependency.  A CTA owns 32 consecutive frames of one utterance (warp 0 runs them)
+// and the 33-NQ padded-coordinate segments (hop samples each, NQ = win/hop) those frames fully
+// determine; all 4 warps of the CTA stage and write out:
+//   * the excitation strip (ex*up(gain), computed once per sample) is staged in shared memory,
+//     segment stride hop+1 so the per-lane strided reads are bank-conflict free;
 //   * lane l at step n = q*hop + r adds window[n]*y to segment l+q-(NQ-1), offset r;
 //   * write-out divides by the overlap-added window and stores coalesced.
-// Adjacent warps recompute NQ-1 frames of overlap (10% at NQ=4) instead of exchanging
-// partial sums: deterministic and launch-local.
+// Adjacent CTAs recompute NQ-1 frames of overlap (10% at NQ=4) instead of exchanging partial
+// sums: deterministic, no atomics, no 4x unfold in HBM.
+//
+// The adjoint has the same geometry (a frame's input and output positions coincide): the strip
+// holds gy/norm, the lane multiplies by window[n], runs the same recurrence on reversed time
+// (u), scatters u into the segment accumulators (-> d_e) and accumulates
+// d_a[i] -= u[n] * v[n-1-i] against the frame's forward output v, which a forward pass with
+// STORE_V left in a workspace ([B*n_frames, win], L2 resident).
 //
 // Algorithmic HBM bytes per output sample: 4 (ex) + 4 (y) + 4(M+1)/hop = 8.383 B.
 #include "common.cuh"
 
 namespace golf {
 
+constexpr int kFfThreads = 128;
+
 struct FfParams {
-  const float* ex;
+  const float* ex;       // fwd: excitation [B, ex_stride]; bwd: gy [B, out_len]
   int64_t ex_stride;
-  const float* gain;    // [B,F]
-  const float* coef;    // all-pole: a [B,F,M]; biquad: [B,F,K,3]
-  const float* window;  // [win]
-  float* y;             // [B, out_len]
-  int B, Le, F, M, hop, win, NQ, pad, n_frames, out_len, nseg0, nseg, warps_per_seq;
-  int interp_gain;      // 1: strip holds ex*up(gain) (ff); 0: gain applied per frame (biquad synth)
+  const float* gain;     // [B,F]
+  const float* coef;     // all-pole: a [B,F,M]; biquad: [B,F,K,3]
+  const float* window;   // [win]
+  float* y;              // fwd: [B, out_len]; bwd: d_e [B, Le]
+  float* vws;            // [B*n_frames, win] frame outputs (fwd STORE_V writes, bwd reads)
+  float* d_a;            // bwd: [B,F,M]
+  int B, Le, F, M, hop, win, NQ, pad, n_frames, out_len, nseg0, nseg, ctas_per_seq;
+  int interp_gain;       // 1: strip holds ex*up(gain) (ff); 0: gain applied per frame (biquad synth)
   float scale;
 };
 
@@ -42,24 +52,29 @@ struct FfParams {
 template <int MP>
 struct AllPole {
   static constexpr int TILE = MP;
-  float na[MP];  // na[j] = -a[M-1-j'] arranged oldest-first: index j pairs with y[n-MP+j]
+  float na[MP];  // na[j] = -a[MP-1-j]: index j pairs with the output MP-j steps back (oldest first)
   float h[MP];   // h[s] = output of tile position s (static rotation)
   __device__ __forceinline__ void load(const FfParams& p, int b, int k, bool ok) {
     const float* a = p.coef + ((size_t)b * p.F + (ok ? k : 0)) * p.M;
 #pragma unroll
     for (int j = 0; j < MP; ++j) {
       const int i = MP - 1 - j;  // tap index (a[i] multiplies y[n-1-i])
-      na[j] = (ok && i < p.M) ? -a[i] : 0.f;
+      na[j] = (ok && i < p.M) ? -__ldg(a + i) : 0.f;
       h[j] = 0.f;
     }
   }
   template <int S>
   __device__ __forceinline__ float step(float x) {
-    float acc = x;
+    float acc0 = x, acc1 = 0.f, acc2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < MP; ++j) acc = __fmaf_rn(na[j], h[(S + j) % MP], acc);  // y[n-MP+j] sits in slot (S+j)%MP
-    h[S] = acc;
-    return acc;
+    for (int j = 0; j < MP - 1; ++j) {  // y[n-MP+j] sits in slot (S+j)%MP
+      if (j % 3 == 0) acc0 = __fmaf_rn(na[j], h[(S + j) % MP], acc0);
+      if (j % 3 == 1) acc1 = __fmaf_rn(na[j], h[(S + j) % MP], acc1);
+      if (j % 3 == 2) acc2 = __fmaf_rn(na[j], h[(S + j) % MP], acc2);
+    }
+    const float y = __fmaf_rn(na[MP - 1], h[(S + MP - 1) % MP], (acc0 + acc1) + acc2);
+    h[S] = y;
+    return y;
   }
 };
 
@@ -98,90 +113,281 @@ struct BiquadCascade {
   }
 };
 
-template <class Filt, int S>
-struct StepRunner {
-  // (q0, r0) = (n0 / hop, n0 % hop); hop >= TILE so a tile crosses at most one hop boundary
-  __device__ __forceinline__ static void run(Filt& f, const FfParams& p, const float* strip, float* acc, const float* wsm,
-                                             int lane, int n0, int q0, int r0, bool frame_ok, float gframe) {
-    const int n = n0 + S;
-    if (n < p.win) {
-      const bool wrap = r0 + S >= p.hop;
-      const int q = q0 + (wrap ? 1 : 0), r = r0 + S - (wrap ? p.hop : 0);
-      float x = strip[(lane + q) * (p.hop + 1) + r];
-      if (!p.interp_gain) x = __fmul_rn(x, gframe);
-      const float yv = f.template step<S>(x);
-      const int sj = lane + q - (p.NQ - 1);
-      if (frame_ok && sj >= 0 && sj < 33 - p.NQ) acc[sj * (p.hop + 1) + r] += wsm[n] * yv;
-    }
-    if constexpr (S + 1 < Filt::TILE) StepRunner<Filt, S + 1>::run(f, p, strip, acc, wsm, lane, n0, q0, r0, frame_ok, gframe);
+template <class Filt, int S, int N>
+struct TileSteps {
+  __device__ __forceinline__ static void run(Filt& f, const float* xs, float* ys) {
+    ys[S] = f.template step<S>(xs[S]);
+    if constexpr (S + 1 < N) TileSteps<Filt, S + 1, N>::run(f, xs, ys);
   }
 };
 
-template <class Filt>
-__global__ void __launch_bounds__(32) ff_frames_kernel(FfParams p) {
+struct FfGeom {
+  int NS, NSTRIP, seg_stride, P0, k0;
+};
+__device__ __forceinline__ FfGeom ff_geom(const FfParams& p, int w) {
+  FfGeom g;
+  g.NS = 33 - p.NQ;          // complete segments per CTA
+  g.NSTRIP = 32 + p.NQ - 1;  // segments the CTA's 32 frames touch
+  g.seg_stride = p.hop + 1;
+  g.P0 = p.nseg0 + w * g.NS;  // first padded segment owned by this CTA
+  g.k0 = g.P0 - (p.NQ - 1);   // frame handled by lane 0
+  return g;
+}
+// overlap-added window at padded segment P, offset r
+__device__ __forceinline__ float ff_norm(const FfParams& p, const float* wsm, int P, int r) {
+  float norm = 0.f;
+  for (int q = p.NQ - 1; q >= 0; --q) {  // frame P-q contributes its q-th hop of the window
+    const int kk = P - q;
+    if (kk >= 0 && kk < p.n_frames) norm += wsm[q * p.hop + r];
+  }
+  return norm;
+}
+
+// ---- forward ------------------------------------------------------------------------
+// ALIGNED: hop % TILE == 0 and win % TILE == 0 -> a tile never crosses a hop boundary, every
+// shared-memory access of a tile is base + constant offset (no per-step index arithmetic).
+template <class Filt, bool STORE_V, bool ALIGNED>
+__global__ void __launch_bounds__(kFfThreads) ff_forward_kernel(FfParams p) {
   extern __shared__ __align__(16) float smem[];
-  const int lane = threadIdx.x;
-  const int b = blockIdx.x / p.warps_per_seq, w = blockIdx.x % p.warps_per_seq;
-  const int NS = 33 - p.NQ;              // complete segments per warp
-  const int NSTRIP = 32 + p.NQ - 1;      // segments of excitation the warp's frames touch
-  const int seg_stride = p.hop + 1;
-  float* strip = smem;                        // [NSTRIP][hop+1]  padded-coordinate excitation
-  float* acc = strip + NSTRIP * seg_stride;   // [NS][hop+1]      overlap-add accumulators
-  float* wsm = acc + NS * seg_stride;         // [win]            window
-  const int P0 = p.nseg0 + w * NS;            // first padded segment owned by this warp
-  const int k0 = P0 - (p.NQ - 1);             // frame handled by lane 0
-  const int k = k0 + lane;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / p.ctas_per_seq;
+  const FfGeom g = ff_geom(p, blockIdx.x % p.ctas_per_seq);
+  float* __restrict__ strip = smem;                       // [NSTRIP][hop+1] padded-coordinate excitation
+  float* __restrict__ acc = strip + g.NSTRIP * g.seg_stride;  // [NS][hop+1]     overlap-add accumulators
+  float* __restrict__ wsm = acc + g.NS * g.seg_stride;        // [win]           window
+  float* __restrict__ vt = wsm + p.win;                       // [32][TILE+1]    v tile (STORE_V)
+  const int k = g.k0 + lane;
   const bool frame_ok = (k >= 0) && (k < p.n_frames);
 
-  // ---- stage window, zero accumulators, build the excitation strip
-  for (int i = lane; i < p.win; i += 32) wsm[i] = p.window[i];
-  for (int i = lane; i < NS * seg_stride; i += 32) acc[i] = 0.f;
-  const float* exb = p.ex + (size_t)b * p.ex_stride;
-  const float* gb = p.gain + (size_t)b * p.F;
-  for (int sg = 0; sg < NSTRIP; ++sg) {
-    const int xbase = (k0 + sg) * p.hop - p.pad;  // signal position of the segment start
-    for (int r = lane; r < p.hop; r += 32) {
-      const int pos = xbase + r;
-      float v = 0.f;
-      if (pos >= 0 && pos < p.Le) {
-        v = exb[pos];
-        if (p.interp_gain) {
-          const Lerp lw = lerp_at(pos, p.scale, p.F);
-          v = __fmul_rn(v, lerp_apply(lw, gb[lw.i0], gb[lw.i1]));
+  // ---- all warps: window, zeroed accumulators, excitation strip
+  for (int i = tid; i < p.win; i += kFfThreads) wsm[i] = __ldg(p.window + i);
+  for (int i = tid; i < g.NS * g.seg_stride; i += kFfThreads) acc[i] = 0.f;
+  const float* __restrict__ exb = p.ex + (size_t)b * p.ex_stride;
+  const float* __restrict__ gb = p.gain + (size_t)b * p.F;
+  for (int i = tid; i < g.NSTRIP * p.hop; i += kFfThreads) {
+    const int sg = i / p.hop, r = i - sg * p.hop;
+    const int pos = (g.k0 + sg) * p.hop - p.pad + r;  // signal position
+    float v = 0.f;
+    if (pos >= 0 && pos < p.Le) {
+      v = __ldg(exb + pos);
+      if (p.interp_gain) {
+        const Lerp lw = lerp_at(pos, p.scale, p.F);
+        v = __fmul_rn(v, lerp_apply(lw, __ldg(gb + lw.i0), __ldg(gb + lw.i1)));
+      }
+    }
+    strip[sg * g.seg_stride + r] = v;
+  }
+  __syncthreads();
+
+  // ---- warp 0: the serial part, `win` recurrence steps per lane
+  if (warp == 0) {
+    Filt f;
+    f.load(p, b, k, frame_ok);
+    const float gframe = (!p.interp_gain && frame_ok) ? __ldg(gb + k) : 1.f;
+    int q0 = 0, r0 = 0;  // (n0 / hop, n0 % hop); hop >= TILE so a tile crosses at most one hop boundary
+#pragma unroll 1
+    for (int n0 = 0; n0 < p.win; n0 += Filt::TILE) {
+      float xs[Filt::TILE], ys[Filt::TILE];
+      if (ALIGNED) {
+        const float* __restrict__ xrow = strip + (lane + q0) * g.seg_stride + r0;
+#pragma unroll
+        for (int s = 0; s < Filt::TILE; ++s) xs[s] = xrow[s];
+      } else {
+#pragma unroll
+        for (int s = 0; s < Filt::TILE; ++s) {
+          const bool wrap = r0 + s >= p.hop;
+          const int q = q0 + (wrap ? 1 : 0), r = r0 + s - (wrap ? p.hop : 0);
+          xs[s] = (n0 + s < p.win) ? strip[(lane + q) * g.seg_stride + r] : 0.f;
         }
       }
-      strip[sg * seg_stride + r] = v;
-    }
-  }
-  Filt f;
-  f.load(p, b, k, frame_ok);
-  const float gframe = (!p.interp_gain && frame_ok) ? gb[k] : 1.f;
-  __syncwarp();
-
-  // ---- the serial part: `win` recurrence steps per lane
-  int q0 = 0, r0 = 0;
-#pragma unroll 1
-  for (int n0 = 0; n0 < p.win; n0 += Filt::TILE) {
-    StepRunner<Filt, 0>::run(f, p, strip, acc, wsm, lane, n0, q0, r0, frame_ok, gframe);
-    r0 += Filt::TILE;
-    if (r0 >= p.hop) r0 -= p.hop, ++q0;
-    __syncwarp();
-  }
-
-  // ---- normalise by the overlap-added window and store
-  float* yb = p.y + (size_t)b * p.out_len;
-  for (int sj = 0; sj < NS; ++sj) {
-    const int P = P0 + sj;  // padded segment
-    for (int r = lane; r < p.hop; r += 32) {
-      const int o = P * p.hop + r - p.pad;
-      if (o < 0 || o >= p.out_len) continue;
-      float norm = 0.f;
-      for (int q = p.NQ - 1; q >= 0; --q) {  // frames P-q contribute their q-th hop of the window
-        const int kk = P - q;
-        if (kk >= 0 && kk < p.n_frames) norm += wsm[q * p.hop + r];
+      if (!p.interp_gain) {
+#pragma unroll
+        for (int s = 0; s < Filt::TILE; ++s) xs[s] = __fmul_rn(xs[s], gframe);
       }
-      yb[o] = acc[sj * seg_stride + r] / norm;
+      TileSteps<Filt, 0, Filt::TILE>::run(f, xs, ys);  // static tile positions
+      if (ALIGNED) {
+        const int sj = lane + q0 - (p.NQ - 1);
+        if (frame_ok && sj >= 0 && sj < g.NS) {
+          float* __restrict__ arow = acc + sj * g.seg_stride + r0;
+          const float* __restrict__ wrow = wsm + n0;
+#pragma unroll
+          for (int s = 0; s < Filt::TILE; ++s) arow[s] = __fmaf_rn(wrow[s], ys[s], arow[s]);
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < Filt::TILE; ++s) {
+          const bool wrap = r0 + s >= p.hop;
+          const int q = q0 + (wrap ? 1 : 0), r = r0 + s - (wrap ? p.hop : 0);
+          const int sj = lane + q - (p.NQ - 1);
+          if (n0 + s < p.win && frame_ok && sj >= 0 && sj < g.NS) acc[sj * g.seg_stride + r] += wsm[n0 + s] * ys[s];
+        }
+      }
+      if (STORE_V) {
+#pragma unroll
+        for (int s = 0; s < Filt::TILE; ++s) vt[lane * (Filt::TILE + 1) + s] = ys[s];
+      }
+      if (STORE_V) {  // coalesced rows of the frame-output workspace
+        __syncwarp();
+        for (int i = lane; i < 32 * Filt::TILE; i += 32) {
+          const int rr = i / Filt::TILE, s = i - rr * Filt::TILE;
+          const int kk = g.k0 + rr;
+          // frames owned by this CTA only (overlap frames are written by the neighbour that owns them)
+          const bool own = kk >= 0 && kk < p.n_frames && rr >= p.NQ - 1 - (blockIdx.x % p.ctas_per_seq == 0 ? p.NQ - 1 : 0);
+          if (own && n0 + s < p.win) p.vws[((size_t)b * p.n_frames + kk) * p.win + n0 + s] = vt[rr * (Filt::TILE + 1) + s];
+        }
+        __syncwarp();
+      }
+      r0 += Filt::TILE;
+      if (r0 >= p.hop) r0 -= p.hop, ++q0;
     }
+  }
+  __syncthreads();
+
+  // ---- all warps: normalise by the overlap-added window and store
+  float* __restrict__ yb = p.y + (size_t)b * p.out_len;
+  for (int i = tid; i < g.NS * p.hop; i += kFfThreads) {
+    const int sj = i / p.hop, r = i - sj * p.hop;
+    const int P = g.P0 + sj;
+    const int o = P * p.hop + r - p.pad;
+    if (o < 0 || o >= p.out_len) continue;
+    yb[o] = acc[sj * g.seg_stride + r] / ff_norm(p, wsm, P, r);
+  }
+}
+
+// ---- adjoint (all-pole only) ----------------------------------------------------------
+// ex := gy [B,out_len]; y := d_e [B,Le]; vws = forward frame outputs; d_a [B,F,M].
+template <int MP>
+__global__ void __launch_bounds__(kFfThreads) ff_backward_kernel(FfParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cta = blockIdx.x % p.ctas_per_seq, b = blockIdx.x / p.ctas_per_seq;
+  const FfGeom g = ff_geom(p, cta);
+  float* __restrict__ strip = smem;                           // [NSTRIP][hop+1] gy / norm in padded coordinates
+  float* __restrict__ acc = strip + g.NSTRIP * g.seg_stride;  // [NS][hop+1]     d_e accumulators
+  float* __restrict__ wsm = acc + g.NS * g.seg_stride;        // [win]
+  float* __restrict__ vt = wsm + p.win;                       // [32][2*MP+1]    v tile: column c <-> v[nhi - 2*MP + c]
+  const int k = g.k0 + lane;
+  const bool frame_ok = (k >= 0) && (k < p.n_frames);
+  // a frame's d_a is produced by the CTA that owns it (not by the neighbour that recomputes it)
+  const bool own = frame_ok && (lane >= p.NQ - 1 || cta == 0);
+
+  for (int i = tid; i < p.win; i += kFfThreads) wsm[i] = __ldg(p.window + i);
+  for (int i = tid; i < g.NS * g.seg_stride; i += kFfThreads) acc[i] = 0.f;
+  __syncthreads();
+  const float* __restrict__ gyb = p.ex + (size_t)b * p.ex_stride;
+  for (int i = tid; i < g.NSTRIP * p.hop; i += kFfThreads) {
+    const int sg = i / p.hop, r = i - sg * p.hop;
+    const int P = g.k0 + sg;
+    const int o = P * p.hop + r - p.pad;
+    float v = 0.f;
+    if (o >= 0 && o < p.out_len) v = __ldg(gyb + o) / ff_norm(p, wsm, P, r);
+    strip[sg * g.seg_stride + r] = v;
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    AllPole<MP> f;
+    f.load(p, b, k, frame_ok);
+    float da[MP];  // da[i] accumulates -sum_n u[n] v[n-1-i]
+    float vh[MP];  // vh[m mod MP] = v[m] for the M most recent m < n (win % MP == 0 keeps slots static)
+#pragma unroll
+    for (int i = 0; i < MP; ++i) da[i] = 0.f, vh[i] = 0.f;
+    constexpr int VT = 2 * MP + 1;
+    // reversed time: tau = 0..win-1 <-> n = win-1-tau.  Tile tau0..tau0+MP-1 covers n in [nhi-MP+1, nhi].
+    int q0 = p.NQ - 1, r0 = p.hop - 1;  // (n / hop, n % hop) at the tile's first step
+#pragma unroll 1
+    for (int tau0 = 0; tau0 < p.win; tau0 += MP) {
+      const int nhi = p.win - 1 - tau0;
+      // ---- stage v[nhi-2*MP .. nhi] of all 32 frames (rows coalesced)
+      __syncwarp();
+      for (int i = lane; i < 32 * VT; i += 32) {
+        const int rr = i / VT, c = i - rr * VT;
+        const int kk = g.k0 + rr, m = nhi - 2 * MP + c;
+        vt[rr * VT + c] = (kk >= 0 && kk < p.n_frames && m >= 0) ? __ldg(p.vws + ((size_t)b * p.n_frames + kk) * p.win + m) : 0.f;
+      }
+      __syncwarp();
+      if (tau0 == 0) {  // history for the first step: v[win-2 .. win-1-MP]
+#pragma unroll
+        for (int i = 0; i < MP; ++i) {
+          const int c = 2 * MP - 1 - i;  // m = nhi - 1 - i
+          vh[((MP - 2 - i) % MP + MP) % MP] = vt[lane * VT + c];
+        }
+      }
+      // hop % MP == 0 (checked on the host): the tile stays inside hop-segment q0, offsets r0-s
+      float xs[MP], us[MP];
+      {
+        const float* __restrict__ xrow = strip + (lane + q0) * g.seg_stride + r0;
+        const float* __restrict__ wrow = wsm + nhi;
+#pragma unroll
+        for (int s = 0; s < MP; ++s) xs[s] = __fmul_rn(xrow[-s], wrow[-s]);
+      }
+      TileSteps<AllPole<MP>, 0, MP>::run(f, xs, us);
+      const float* __restrict__ vrow_t = vt + lane * VT;
+#pragma unroll
+      for (int s = 0; s < MP; ++s) {
+        // n = nhi - s; n mod MP = (MP-1-s) since win % MP == 0 and tau0 % MP == 0
+        // v[n-1-i] sits in slot (n-1-i) mod MP = (2*MP-2-s-i) % MP
+#pragma unroll
+        for (int i = 0; i < MP; ++i) da[i] = __fmaf_rn(us[s], vh[(2 * MP - 2 - s - i) % MP], da[i]);
+        // slide: v[n-1] leaves, v[n-1-MP] enters (same slot)
+        vh[(2 * MP - 2 - s) % MP] = vrow_t[MP - 1 - s];  // column of m = n-1-MP = nhi-s-1-MP
+      }
+      {
+        const int sj = lane + q0 - (p.NQ - 1);
+        if (frame_ok && sj >= 0 && sj < g.NS) {
+          float* __restrict__ arow = acc + sj * g.seg_stride + r0;
+#pragma unroll
+          for (int s = 0; s < MP; ++s) arow[-s] += us[s];
+        }
+      }
+      r0 -= MP;
+      if (r0 < 0) r0 += p.hop, --q0;
+    }
+    if (own && p.d_a) {
+      float* dst = p.d_a + ((size_t)b * p.F + k) * p.M;
+      for (int i = 0; i < p.M; ++i) dst[i] = -da[i];
+    }
+  }
+  __syncthreads();
+  float* __restrict__ deb = p.y + (size_t)b * p.Le;
+  for (int i = tid; i < g.NS * p.hop; i += kFfThreads) {
+    const int sj = i / p.hop, r = i - sj * p.hop;
+    const int pos = (g.P0 + sj) * p.hop + r - p.pad;
+    if (pos >= 0 && pos < p.Le) deb[pos] = acc[sj * g.seg_stride + r];
+  }
+}
+
+// d_ex = d_e * up(gain); d_gain[b,k] = sum_t w_k(t) d_e[t] ex[t]; frames beyond n_frames get d_a = 0
+__global__ void ff_finish_kernel(const float* __restrict__ d_e, const float* __restrict__ ex, int64_t ex_stride,
+                                 const float* __restrict__ gain, float* __restrict__ d_ex, int64_t dex_stride,
+                                 float* __restrict__ d_gain, float* __restrict__ d_a, int B, int T_ex, int Le, int F, int M,
+                                 int hop, int n_frames, int skip, float scale) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d_ex && t < T_ex + skip) {
+    float v = 0.f;
+    const int te = t - skip;
+    if (te >= 0 && te < Le) {
+      const Lerp w = lerp_at(te, scale, F);
+      v = __fmul_rn(d_e[(size_t)b * Le + te], lerp_apply(w, gain[(size_t)b * F + w.i0], gain[(size_t)b * F + w.i1]));
+    }
+    d_ex[(size_t)b * dex_stride + t] = v;
+  }
+  if (t < F) {
+    if (d_gain) {
+      float acc = 0.f;
+      const int t_lo = max(0, (t - 1) * hop), t_hi = min(Le - 1, (t + 1) * hop);
+      for (int tt = t_lo; tt <= t_hi; ++tt) {
+        const Lerp w = lerp_at(tt, scale, F);
+        float wk = 0.f;
+        if (w.i0 == t) wk += w.l0;
+        if (w.i1 == t) wk += w.l1;
+        if (wk != 0.f) acc = __fmaf_rn(wk, d_e[(size_t)b * Le + tt] * ex[(size_t)b * ex_stride + tt], acc);
+      }
+      d_gain[(size_t)b * F + t] = acc;
+    }
+    if (d_a && t >= n_frames)
+      for (int i = 0; i < M; ++i) d_a[((size_t)b * F + t) * M + i] = 0.f;
   }
 }
 
@@ -204,17 +410,43 @@ __global__ void lpc_inverse_kernel(const float* __restrict__ y, int64_t y_stride
   r[(size_t)b * L + t] = acc + yb[t];
 }
 
-template <class Filt>
-static int launch_ff(const FfParams& p, cudaStream_t st) {
+// ---- host side ------------------------------------------------------------------------
+static size_t ff_smem_bytes(const FfParams& p, int vt_floats) {
   const int NS = 33 - p.NQ, NSTRIP = 32 + p.NQ - 1;
-  const size_t sm = ((size_t)(NS + NSTRIP) * (p.hop + 1) + p.win) * sizeof(float);
+  return ((size_t)(NS + NSTRIP) * (p.hop + 1) + p.win + vt_floats) * sizeof(float);
+}
+
+template <class Filt, bool STORE_V, bool ALIGNED>
+static int launch_ff_fwd_a(const FfParams& p, cudaStream_t st) {
+  const size_t sm = ff_smem_bytes(p, STORE_V ? 32 * (Filt::TILE + 1) : 0);
   if (sm > 220 * 1024) return GOLF_ERR_UNSUPPORTED;
   static size_t sm_allowed = 48 * 1024;  // per instantiation
   if (sm > sm_allowed) {
-    GOLF_CUDA(cudaFuncSetAttribute(ff_frames_kernel<Filt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    GOLF_CUDA(cudaFuncSetAttribute(ff_forward_kernel<Filt, STORE_V, ALIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     sm_allowed = sm;
   }
-  ff_frames_kernel<Filt><<<p.B * p.warps_per_seq, 32, sm, st>>>(p);
+  ff_forward_kernel<Filt, STORE_V, ALIGNED><<<p.B * p.ctas_per_seq, kFfThreads, sm, st>>>(p);
+  GOLF_CHECK_LAUNCH();
+  return GOLF_OK;
+}
+template <class Filt, bool STORE_V>
+static int launch_ff_fwd(const FfParams& p, cudaStream_t st) {
+  if (p.hop % Filt::TILE == 0 && p.win % Filt::TILE == 0) return launch_ff_fwd_a<Filt, STORE_V, true>(p, st);
+  return launch_ff_fwd_a<Filt, STORE_V, false>(p, st);
+}
+
+template <int MP>
+static int launch_ff_bwd(const FfParams& pf, const FfParams& pb, cudaStream_t st) {
+  int rc = launch_ff_fwd<AllPole<MP>, true>(pf, st);
+  if (rc) return rc;
+  const size_t sm = ff_smem_bytes(pb, 32 * (2 * MP + 1));
+  if (sm > 220 * 1024) return GOLF_ERR_UNSUPPORTED;
+  static size_t sm_allowed = 48 * 1024;
+  if (sm > sm_allowed) {
+    GOLF_CUDA(cudaFuncSetAttribute(ff_backward_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    sm_allowed = sm;
+  }
+  ff_backward_kernel<MP><<<pb.B * pb.ctas_per_seq, kFfThreads, sm, st>>>(pb);
   GOLF_CHECK_LAUNCH();
   return GOLF_OK;
 }
@@ -234,7 +466,7 @@ static int fill_geometry(FfParams* p, int T_ex, int pad) {
   p->nseg0 = pad / p->hop;
   const int last = (pad + p->out_len - 1) / p->hop;
   p->nseg = last - p->nseg0 + 1;
-  p->warps_per_seq = ceil_div(p->nseg, 33 - p->NQ);
+  p->ctas_per_seq = ceil_div(p->nseg, 33 - p->NQ);
   p->scale = lerp_scale(p->F, p->hop);
   return GOLF_OK;
 }
@@ -254,14 +486,67 @@ GOLF_API int golf_lpc_ff_fwd(const float* ex, int64_t ex_stride, const float* ga
   int rc = fill_geometry(&p, T_ex, win / 2);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (M <= 4) return launch_ff<AllPole<4>>(p, st);
-  if (M <= 8) return launch_ff<AllPole<8>>(p, st);
-  if (M <= 12) return launch_ff<AllPole<12>>(p, st);
-  if (M <= 16) return launch_ff<AllPole<16>>(p, st);
-  if (M <= 20) return launch_ff<AllPole<20>>(p, st);
-  if (M <= 24) return launch_ff<AllPole<24>>(p, st);
-  if (M <= 32) return launch_ff<AllPole<32>>(p, st);
-  return launch_ff<AllPole<40>>(p, st);
+  if (M <= 4) return launch_ff_fwd<AllPole<4>, false>(p, st);
+  if (M <= 8) return launch_ff_fwd<AllPole<8>, false>(p, st);
+  if (M <= 12) return launch_ff_fwd<AllPole<12>, false>(p, st);
+  if (M <= 16) return launch_ff_fwd<AllPole<16>, false>(p, st);
+  if (M <= 20) return launch_ff_fwd<AllPole<20>, false>(p, st);
+  if (M <= 24) return launch_ff_fwd<AllPole<24>, false>(p, st);
+  if (M <= 32) return launch_ff_fwd<AllPole<32>, false>(p, st);
+  return launch_ff_fwd<AllPole<40>, false>(p, st);
+}
+
+GOLF_API size_t golf_lpc_ff_bwd_workspace_bytes(int B, int T_ex, int F, int hop, int win) {
+  if (B <= 0 || T_ex <= 0 || F <= 0 || hop <= 0 || win < 2 * hop) return 0;
+  FfParams p{};
+  p.B = B, p.F = F, p.hop = hop, p.win = win, p.interp_gain = 1;
+  if (fill_geometry(&p, T_ex, win / 2)) return 0;
+  return align_up((size_t)B * p.n_frames * win * 4, 256) + align_up((size_t)B * p.Le * 4, 256) + align_up((size_t)B * p.out_len * 4, 256);
+}
+
+GOLF_API int golf_lpc_ff_bwd(const float* gy, const float* ex, int64_t ex_stride, const float* gain, const float* a,
+                             const float* window, float* d_ex, int64_t dex_stride, float* d_gain, float* d_a, int B, int T_ex,
+                             int F, int M, int hop, int win, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!gy || !ex || !gain || !a || !window || B <= 0 || T_ex <= 0 || F <= 0 || M <= 0 || hop <= 0 || win < 2 * hop)
+    return GOLF_ERR_INVALID;
+  if (M > 40 || hop < 40) return GOLF_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  FfParams pf{};
+  pf.ex = ex, pf.ex_stride = ex_stride, pf.gain = gain, pf.coef = a, pf.window = window;
+  pf.B = B, pf.F = F, pf.M = M, pf.hop = hop, pf.win = win, pf.interp_gain = 1;
+  int rc = fill_geometry(&pf, T_ex, win / 2);
+  if (rc) return rc;
+  const size_t need = golf_lpc_ff_bwd_workspace_bytes(B, T_ex, F, hop, win);
+  if (!workspace || workspace_bytes < need) return GOLF_ERR_WORKSPACE;
+  char* ws = reinterpret_cast<char*>(workspace);
+  float* vws = reinterpret_cast<float*>(ws);
+  float* d_e = reinterpret_cast<float*>(ws + align_up((size_t)B * pf.n_frames * win * 4, 256));
+  float* yscratch = reinterpret_cast<float*>(ws + align_up((size_t)B * pf.n_frames * win * 4, 256) + align_up((size_t)B * pf.Le * 4, 256));
+  pf.vws = vws, pf.y = yscratch;
+  FfParams pb = pf;
+  pb.ex = gy, pb.ex_stride = pf.out_len, pb.y = d_e, pb.d_a = d_a;
+  // the adjoint writes d_e over every input position [0, Le), which can reach past the last output
+  pb.nseg = (pf.pad + pf.Le - 1) / hop - pf.nseg0 + 1;
+  pb.ctas_per_seq = ceil_div(pb.nseg, 33 - pf.NQ);
+  const int mp = M <= 4 ? 4 : M <= 8 ? 8 : M <= 12 ? 12 : M <= 16 ? 16 : M <= 20 ? 20 : M <= 24 ? 24 : M <= 32 ? 32 : 40;
+  if (win % mp != 0 || hop % mp != 0) return GOLF_ERR_UNSUPPORTED;  // the adjoint keeps static slots / offsets
+  switch (mp) {
+    case 4: rc = launch_ff_bwd<4>(pf, pb, st); break;
+    case 8: rc = launch_ff_bwd<8>(pf, pb, st); break;
+    case 12: rc = launch_ff_bwd<12>(pf, pb, st); break;
+    case 16: rc = launch_ff_bwd<16>(pf, pb, st); break;
+    case 20: rc = launch_ff_bwd<20>(pf, pb, st); break;
+    case 24: rc = launch_ff_bwd<24>(pf, pb, st); break;
+    case 32: rc = launch_ff_bwd<32>(pf, pb, st); break;
+    default: rc = launch_ff_bwd<40>(pf, pb, st); break;
+  }
+  if (rc) return rc;
+  // d_ex covers the caller's full excitation row (zeros beyond the filtered span)
+  const int span = T_ex > F ? T_ex : F;
+  ff_finish_kernel<<<dim3(ceil_div(span, 256), B), 256, 0, st>>>(d_e, ex, ex_stride, gain, d_ex, dex_stride, d_gain, d_a, B, T_ex,
+                                                                pf.Le, F, M, hop, pf.n_frames, 0, pf.scale);
+  GOLF_CHECK_LAUNCH();
+  return GOLF_OK;
 }
 
 GOLF_API int golf_biquad_ff_fwd(const float* ex, int64_t ex_stride, const float* gain, const float* biquads,
@@ -276,10 +561,10 @@ GOLF_API int golf_biquad_ff_fwd(const float* ex, int64_t ex_stride, const float*
   int rc = fill_geometry(&p, T_ex, (win - hop) / 2);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (K <= 4) return launch_ff<BiquadCascade<4>>(p, st);
-  if (K <= 8) return launch_ff<BiquadCascade<8>>(p, st);
-  if (K <= 12) return launch_ff<BiquadCascade<12>>(p, st);
-  return launch_ff<BiquadCascade<16>>(p, st);
+  if (K <= 4) return launch_ff_fwd<BiquadCascade<4>, false>(p, st);
+  if (K <= 8) return launch_ff_fwd<BiquadCascade<8>, false>(p, st);
+  if (K <= 12) return launch_ff_fwd<BiquadCascade<12>, false>(p, st);
+  return launch_ff_fwd<BiquadCascade<16>, false>(p, st);
 }
 
 GOLF_API int golf_lpc_inverse_fwd(const float* y, int64_t y_stride, const float* a, float* r, int B, int L, int F, int M,

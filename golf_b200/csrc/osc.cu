@@ -84,6 +84,11 @@ __global__ void __launch_bounds__(256) osc_knot_prefix_kernel(const float* __res
   }
 }
 
+// phase / os exactly as the reference divides it; a power-of-two os makes the reciprocal exact
+__device__ __forceinline__ float div_os(float x, float os_f, float inv_os_f, bool pow2) {
+  return pow2 ? __fmul_rn(x, inv_os_f) : __fdiv_rn(x, os_f);
+}
+
 // ---- exact phase in 64-bit fixed point ------------------------------------------------
 // Default accumulation.  A phase in cycles only matters mod 1, so it is kept as an unsigned
 // Q0.64 fraction: adding increments is exact integer arithmetic that wraps exactly at one
@@ -101,21 +106,29 @@ __device__ __forceinline__ uint64_t q64_interval(uint64_t xk, uint64_t xn, int h
   return xk * (uint64_t)hp + (uint64_t)(half * (int64_t)(hp - 1));
 }
 
-__global__ void __launch_bounds__(1024) osc_knot_prefix_q64_kernel(const float* __restrict__ phase,
-                                                                   unsigned long long* __restrict__ pref, int Np, int hp,
-                                                                   float os_f) {
-  __shared__ unsigned long long wsum[32];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// grid (kPrefSplit, B): each CTA scans a contiguous 1/kPrefSplit of the knots, stores prefixes local
+// to its span plus the span total; readers add the totals of the earlier spans (<= kPrefSplit-1 adds).
+constexpr int kPrefSplit = 8;
+__global__ void __launch_bounds__(256) osc_knot_prefix_q64_kernel(const float* __restrict__ phase,
+                                                                  unsigned long long* __restrict__ pref,
+                                                                  unsigned long long* __restrict__ totals, int Np, int hp,
+                                                                  float os_f, int span) {
+  __shared__ unsigned long long wsum[8];
+  const int sp = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* __restrict__ ph = phase + (size_t)b * Np;
   unsigned long long* pb = pref + (size_t)b * Np;
-  const int per = (Np + 1023) / 1024;
-  const int k0 = min(tid * per, Np), k1 = min(Np, k0 + per);
+  const bool pow2 = ((int)os_f & ((int)os_f - 1)) == 0;
+  const float inv_os_f = 1.f / os_f;
+  const int s0 = sp * span, s1 = min(Np, s0 + span);
+  const int per = (span + 255) / 256;
+  const int k0 = min(s0 + tid * per, s1), k1 = min(s1, k0 + per);
   unsigned long long s = 0;
+  uint64_t xk = k0 < k1 ? q64_from_float(div_os(__ldg(ph + k0), os_f, inv_os_f, pow2)) : 0ull;
 #pragma unroll 4
   for (int k = k0; k < k1; ++k) {
-    const uint64_t xk = q64_from_float(__fdiv_rn(__ldg(ph + k), os_f));
-    const uint64_t xn = q64_from_float(__fdiv_rn(__ldg(ph + min(k + 1, Np - 1)), os_f));
+    const uint64_t xn = q64_from_float(div_os(__ldg(ph + min(k + 1, Np - 1)), os_f, inv_os_f, pow2));
     s += q64_interval(xk, xn, hp);
+    xk = xn;
   }
   // exclusive block scan of the per-thread sums (integer adds: order does not matter)
   unsigned long long inc = s;
@@ -127,53 +140,59 @@ __global__ void __launch_bounds__(1024) osc_knot_prefix_q64_kernel(const float* 
   if (lane == 31) wsum[warp] = inc;
   __syncthreads();
   if (warp == 0) {
-    unsigned long long w = wsum[lane], winc = w;
+    unsigned long long w = lane < 8 ? wsum[lane] : 0ull, winc = w;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
+    for (int d = 1; d < 8; d <<= 1) {
       const unsigned long long v = __shfl_up_sync(0xffffffffu, winc, d);
       if (lane >= d) winc += v;
     }
-    wsum[lane] = winc - w;
+    if (lane < 8) wsum[lane] = winc - w;
+    if (lane == 7) totals[(size_t)b * kPrefSplit + sp] = winc;
   }
   __syncthreads();
   unsigned long long run = wsum[warp] + (inc - s);
+  xk = k0 < k1 ? q64_from_float(div_os(__ldg(ph + k0), os_f, inv_os_f, pow2)) : 0ull;
 #pragma unroll 4
   for (int k = k0; k < k1; ++k) {
     pb[k] = run;
-    const uint64_t xk = q64_from_float(__fdiv_rn(__ldg(ph + k), os_f));
-    const uint64_t xn = q64_from_float(__fdiv_rn(__ldg(ph + min(k + 1, Np - 1)), os_f));
+    const uint64_t xn = q64_from_float(div_os(__ldg(ph + min(k + 1, Np - 1)), os_f, inv_os_f, pow2));
     run += q64_interval(xk, xn, hp);
+    xk = xn;
   }
 }
 
 // upsampled increment at oversampled time t, ATen arithmetic on phase/os
-__device__ __forceinline__ float osc_inc(const float* ph, int t, float scale, int Np, float os_f) {
+__device__ __forceinline__ float osc_inc(const float* ph, int t, float scale, int Np, float os_f, float inv_os_f, bool pow2) {
   const Lerp w = lerp_at(t, scale, Np);
-  return lerp_apply(w, __fdiv_rn(ph[w.i0], os_f), __fdiv_rn(ph[w.i1], os_f));
+  return lerp_apply(w, div_os(__ldg(ph + w.i0), os_f, inv_os_f, pow2), div_os(__ldg(ph + w.i1), os_f, inv_os_f, pow2));
 }
 
-// bilinear table read, F.grid_sample(align_corners=True, zeros padding) arithmetic
+// bilinear table read, F.grid_sample(align_corners=True, zeros padding) arithmetic.  The column
+// (phase) coordinate follows ATen operation by operation -- the table is steep around glottal
+// closure; the row (time) coordinate uses t * (1/ydenom): rows differ slowly, the 1-ulp
+// difference against ATen's division moves the result by < 1e-7.
 __device__ __forceinline__ float osc_read(const float* __restrict__ tb, int R, int P, float wrapped, int t,
-                                          float ydenom, int blocks) {
+                                          float inv_ydenom, int blocks) {
   const float gx = __fsub_rn(__fmul_rn(wrapped, 2.f), 1.f);
-  const float gy = __fsub_rn(__fmul_rn(__fdiv_rn((float)t, ydenom), 2.f), 1.f);
+  const float gy = __fsub_rn(__fmul_rn(__fmul_rn((float)t, inv_ydenom), 2.f), 1.f);
   const float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), (float)P);  // (x+1)/2: *0.5 is the same float
   const float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)blocks);
   const float x0f = floorf(ix), y0f = floorf(iy);
   const float fx = __fsub_rn(ix, x0f), fy = __fsub_rn(iy, y0f);
-  const int x0 = (int)x0f, y0 = (int)y0f;
+  const int x0 = min(max((int)x0f, 0), P), y0 = min(max((int)y0f, 0), blocks);
+  // column P wraps to column 0; column P+1 / row blocks+1 are outside the image (weight 0 anyway);
   // rows beyond the R supplied ones replicate the last (F.pad replicate, synth.py:138-148)
-  auto tap = [&](int yy, int xx) -> float {
-    if (xx < 0 || xx > P || yy < 0 || yy > blocks) return 0.f;
-    const int row = min(yy, R - 1);
-    const int col = xx == P ? 0 : xx;  // column P wraps to column 0
-    return tb[(size_t)row * P + col];
-  };
+  const int c0 = x0 == P ? 0 : x0, c1 = x0 + 1 >= P ? (x0 + 1 == P ? 0 : -1) : x0 + 1;
+  const float* r0p = tb + (size_t)min(y0, R - 1) * P;
+  const float* r1p = tb + (size_t)min(y0 + 1, R - 1) * P;
+  const bool row1 = y0 + 1 <= blocks;
+  const float t00 = __ldg(r0p + c0), t01 = c1 >= 0 ? __ldg(r0p + c1) : 0.f;
+  const float t10 = row1 ? __ldg(r1p + c0) : 0.f, t11 = (row1 && c1 >= 0) ? __ldg(r1p + c1) : 0.f;
   const float gx1 = __fsub_rn(1.f, fx), gy1 = __fsub_rn(1.f, fy);
-  float v = __fmul_rn(tap(y0, x0), __fmul_rn(gx1, gy1));
-  v = __fmaf_rn(tap(y0, x0 + 1), __fmul_rn(fx, gy1), v);
-  v = __fmaf_rn(tap(y0 + 1, x0), __fmul_rn(gx1, fy), v);
-  v = __fmaf_rn(tap(y0 + 1, x0 + 1), __fmul_rn(fx, fy), v);
+  float v = __fmul_rn(t00, __fmul_rn(gx1, gy1));
+  v = __fmaf_rn(t01, __fmul_rn(fx, gy1), v);
+  v = __fmaf_rn(t10, __fmul_rn(gx1, fy), v);
+  v = __fmaf_rn(t11, __fmul_rn(fx, fy), v);
   return v;
 }
 
@@ -184,7 +203,7 @@ __global__ void wavetable_read_kernel(const float* __restrict__ wrapped, const f
   if (t >= N) return;
   const int blocks = (N + hop_tab - 1) / hop_tab;
   out[(size_t)b * N + t] =
-      osc_read(tables + (size_t)b * R * P, R, P, wrapped[(size_t)b * N + t], t, (float)((int64_t)hop_tab * blocks), blocks);
+      osc_read(tables + (size_t)b * R * P, R, P, wrapped[(size_t)b * N + t], t, 1.f / (float)((int64_t)hop_tab * blocks), blocks);
 }
 
 // ---- fused flow + decimation --------------------------------------------------------
@@ -196,6 +215,8 @@ struct OscParams {
   const float* tables;    // [B,Fw,P]
   const double* pref;     // [B,Np] exclusive knot prefix (frac part, or unwrapped when aten_cpu)
   int aten_cpu;           // 1: round the running sum to float32 before mod 1 (ATen CPU cumsum semantics)
+  const unsigned long long* totals;  // [B][kPrefSplit] span totals of the Q0.64 prefix
+  int span;               // knots per span
   const float* dec;       // [2*zeros*os+1]
   float* out;             // [B,n_out]
   int B, Np, hp, N, n_out, Fw, P, hop_tab, blocks, os, zeros, equal_energy;
@@ -225,6 +246,8 @@ __global__ void __launch_bounds__(128) osc_flow_decimate_kernel(OscParams p) {
   // prefix / slope are fetched once per j:  vp[phs][j] = v[mj*os + phs]
   const int phase_hop = p.hp / p.os;
   const double inv_os = 1.0 / (double)p.os, inv_2hp = 1.0 / (2.0 * (double)p.hp);
+  const bool pow2 = (p.os & (p.os - 1)) == 0;
+  const float inv_os_f = 1.f / os_f, inv_yd = 1.f / p.ydenom;
   for (int j = tid; j < p.plen; j += blockDim.x) {
     const int mj = m0 - Z + j;
     const bool in = mj >= 0 && (int64_t)mj * p.os < p.N;
@@ -242,10 +265,12 @@ __global__ void __launch_bounds__(128) osc_flow_decimate_kernel(OscParams p) {
         dk = (double)fn * inv_os - xk;
         pk = __ldg(p.pref + (size_t)b * p.Np + k);
       } else {
-        qx = q64_from_float(__fdiv_rn(fk, os_f));
-        const uint64_t qn = q64_from_float(__fdiv_rn(fn, os_f));
+        qx = q64_from_float(div_os(fk, os_f, inv_os_f, pow2));
+        const uint64_t qn = q64_from_float(div_os(fn, os_f, inv_os_f, pow2));
         qq = (int64_t)(qn - qx) / (int64_t)(2 * p.hp);  // slope term per r(r+1)
         qp = reinterpret_cast<const unsigned long long*>(p.pref)[(size_t)b * p.Np + k];
+        const int spn = k / p.span;
+        for (int q = 0; q < spn; ++q) qp += p.totals[(size_t)b * kPrefSplit + q];
       }
     }
     for (int phs = 0; phs < p.os; ++phs) {
@@ -263,8 +288,9 @@ __global__ void __launch_bounds__(128) osc_flow_decimate_kernel(OscParams p) {
           wr = __fmul_rn(__ull2float_rn(phi), 5.42101086242752217e-20f);  // * 2^-64
           if (wr >= 1.f) wr = 0.f;
         }
-        v = osc_read(tb, p.Fw, p.P, wr, t, p.ydenom, p.blocks);
-        if (p.equal_energy) v = __fmul_rn(v, __fdiv_rn(1.f, __fsqrt_rn(osc_inc(ph, t, p.scale, p.Np, os_f))));
+        v = osc_read(tb, p.Fw, p.P, wr, t, inv_yd, p.blocks);
+        // torch.rsqrt: MUFU.RSQ-based rsqrtf is within 2 ulp of ATen's CPU 1/sqrt
+        if (p.equal_energy) v = __fmul_rn(v, rsqrtf(osc_inc(ph, t, p.scale, p.Np, os_f, inv_os_f, pow2)));
       }
       vp[phs * p.plen + j] = v;
     }
@@ -293,7 +319,7 @@ static bool osc_layout(int B, int Np, int phase_hop, int Fw, int P, int os, OscL
   L->hp = (int)hp, L->N = (int)N, L->n_out = (int)((N - 1) / os + 1);
   L->off_tables = 0;
   L->off_pref = align_up((size_t)B * Fw * P * 4, 256);
-  L->bytes = L->off_pref + align_up((size_t)B * Np * 8, 256);
+  L->bytes = L->off_pref + align_up((size_t)B * Np * 8, 256) + align_up((size_t)B * kPrefSplit * 8, 256);
   return true;
 }
 
@@ -324,13 +350,17 @@ GOLF_API int golf_glottal_osc_fwd(const float* phase, const float* w, const floa
   osc_tables_kernel<<<ceil_div(B * Fw * P, 256), 256, 0, st>>>(w, table, tables, B * Fw, n_tab, P);
   GOLF_CHECK_LAUNCH();
   if (accumulate != 0 && accumulate != 1) return GOLF_ERR_INVALID;
+  unsigned long long* totals = reinterpret_cast<unsigned long long*>(ws + L.off_pref + align_up((size_t)B * Np * 8, 256));
+  const int span = ceil_div(Np, kPrefSplit);
   if (accumulate == 0)
-    osc_knot_prefix_q64_kernel<<<B, 1024, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), Np, L.hp, (float)os);
+    osc_knot_prefix_q64_kernel<<<dim3(kPrefSplit, B), 256, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), totals, Np,
+                                                                  L.hp, (float)os, span);
   else
     osc_knot_prefix_kernel<<<B, 256, 0, st>>>(phase, pref, Np, L.hp, os, 0);
   GOLF_CHECK_LAUNCH();
   OscParams p{};
   p.phase = phase, p.tables = tables, p.pref = pref, p.aten_cpu = accumulate;
+  p.totals = totals, p.span = span;
   p.dec = os > 1 ? dec_kernel : nullptr, p.out = out;
   p.B = B, p.Np = Np, p.hp = L.hp, p.N = L.N, p.n_out = L.n_out, p.Fw = Fw, p.P = P;
   p.hop_tab = w_hop * os;

@@ -114,11 +114,6 @@ class LTVMinimumPhaseFilter(LTVMinimumPhaseFilterPrecise):
         assert W >= hop * 2, f"{W} < {hop * 2}"
         if not self.centred:
             x = x[..., hop // 2 :]
-        if torch.is_grad_enabled() and any(t.requires_grad for t in (x, g, c)):
-            raise GolfError(
-                "LTVMinimumPhaseFilter: the frame-wise CUDA path is forward-only in this build; "
-                "train with LTVMinimumPhaseFilterPrecise (differentiable) or wrap the call in torch.no_grad()"
-            )
         y = G.lpc_ff(x, g, c, self._window, hop)
         if not self.centred:
             y = F.pad(y[:, None], (hop // 2, 0), "reflect")[:, 0]

@@ -167,8 +167,7 @@ def sample_wise_lpc(x, a, zi=None) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------- GOLF-ff
-def lpc_ff(ex, gain, a, window, hop: int) -> torch.Tensor:
-    """Frame-wise filter + Hann OLA (forward only for now)."""
+def _lpc_ff_fwd(ex, gain, a, window, hop: int) -> torch.Tensor:
     ex = _rows(ex, "ex")
     gain, a, window = _cuda_f32(gain, "gain"), _cuda_f32(a, "a"), _cuda_f32(window, "window")
     B, Tex = ex.shape
@@ -185,6 +184,42 @@ def lpc_ff(ex, gain, a, window, hop: int) -> torch.Tensor:
                                         hop, win, _stream())
     check(rc, "golf_lpc_ff_fwd")
     return y
+
+
+class _LpcFF(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ex, gain, a, window, hop):
+        y = _lpc_ff_fwd(ex, gain, a, window, hop)
+        ctx.save_for_backward(ex, gain, a, window)
+        ctx.hop = hop
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        ex, gain, a, window = ctx.saved_tensors
+        gy = _cuda_f32(gy, "gy")
+        exr = _rows(ex, "ex")
+        gain_c, a_c, win_c = _cuda_f32(gain, "gain"), _cuda_f32(a, "a"), _cuda_f32(window, "window")
+        B, Tex = exr.shape
+        Fr, M = a_c.shape[1], a_c.shape[2]
+        win, hop = win_c.numel(), ctx.hop
+        need = ctx.needs_input_grad
+        dev = gy.device
+        d_ex = torch.empty(B, Tex, dtype=torch.float32, device=dev) if need[0] else None
+        d_gain = torch.empty(B, Fr, dtype=torch.float32, device=dev) if need[1] else None
+        d_a = torch.empty(B, Fr, M, dtype=torch.float32, device=dev) if need[2] else None
+        lib = _lib.lib()
+        ws = _workspace(lib.golf_lpc_ff_bwd_workspace_bytes(B, Tex, Fr, hop, win), dev)
+        with _on(dev):
+            rc = lib.golf_lpc_ff_bwd(_ptr(gy), _ptr(exr), exr.stride(0), _ptr(gain_c), _ptr(a_c), _ptr(win_c), _ptr(d_ex),
+                                     Tex, _ptr(d_gain), _ptr(d_a), B, Tex, Fr, M, hop, win, _ptr(ws), ws.numel(), _stream())
+        check(rc, "golf_lpc_ff_bwd")
+        return d_ex, d_gain, d_a, None, None
+
+
+def lpc_ff(ex, gain, a, window, hop: int) -> torch.Tensor:
+    """Frame-wise filter + windowed OLA; differentiable in ex, gain, a."""
+    return _LpcFF.apply(ex, gain, a, window, int(hop))
 
 
 def biquad_ff(ex, gain, biquads, window, hop: int) -> torch.Tensor:

@@ -91,6 +91,14 @@ int golf_lpc_ss_bwd(const float *gy, const float *y, const float *ex, int64_t ex
 int golf_lpc_ff_fwd(const float *ex, int64_t ex_stride, const float *gain, const float *a,
                     const float *window, float *y, int B, int T_ex, int F, int M, int hop,
                     int win, void *stream);
+/* Adjoint of golf_lpc_ff_fwd: gy [B,(n_frames-1)*hop] -> d_ex [B,T_ex] (row stride dex_stride),
+ * d_gain [B,F], d_a [B,F,M] (any may be NULL).  Recomputes the per-frame recurrences into the
+ * workspace.  Requires win % MP == 0 for the padded order MP (true for every shipped config). */
+size_t golf_lpc_ff_bwd_workspace_bytes(int B, int T_ex, int F, int hop, int win);
+int golf_lpc_ff_bwd(const float *gy, const float *ex, int64_t ex_stride, const float *gain,
+                    const float *a, const float *window, float *d_ex, int64_t dex_stride,
+                    float *d_gain, float *d_a, int B, int T_ex, int F, int M, int hop, int win,
+                    void *workspace, size_t workspace_bytes, void *stream);
 /* Cascade of K second-order all-pole sections per frame (biquads [B,F,K,3]),
  * gain applied per frame, zero-pad (win-hop)/2, Hann OLA + normalise. */
 int golf_biquad_ff_fwd(const float *ex, int64_t ex_stride, const float *gain,

@@ -158,3 +158,26 @@ def test_audiotensor_agrees_with_reference(reference):
     r = Ref(z, hop_length=120) * Ref(x, hop_length=240)
     m = Mine(z, hop_length=120) * Mine(x, hop_length=240)
     assert torch.equal(r.as_tensor(), m.as_tensor()) and r.hop_length == m.hop_length == 120
+
+
+@pytest.mark.reference
+def test_interop_inside_the_reference_process(reference):
+    """with the reference importable, golf_b200 modules ARE reference Controllables and can be
+    mixed into the reference's own Synth"""
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from oracle import refimport; refimport.import_reference()\n"
+        "import models.ctrl, models.sf, models.synth, models.noise, models.filters, models.audiotensor\n"
+        "import golf_b200, golf_b200.filters as F, golf_b200.audiotensor as A, golf_b200.ctrl as C\n"
+        "assert C.Controllable is models.ctrl.Controllable and A.AudioTensor is models.audiotensor.AudioTensor\n"
+        "dec = models.sf.SourceFilterSynth(\n"
+        "    models.synth.DownsampledIndexedGlottalFlowTable(hop_rate=10, in_channels=64, oversampling=4, equal_energy=True, lf_v2=True, points=2048),\n"
+        "    models.noise.StandardNormalNoise(), F.LTVZeroPhaseFIRFilter('hanning', n_mag=256),\n"
+        "    F.LTVMinimumPhaseFilterPrecise(lpc_order=22), F.LTIAcousticFilter(128, 'fft'), subtract_harmonics=False)\n"
+        "sizes, _, names = dec.split_sizes_and_trsfms\n"
+        "assert sizes == ((64,), (), (256,), (1, 22), ()), sizes\n"
+        "print('ok')\n" % ROOT
+    )
+    env = dict(os.environ, GOLF_B200_INTEROP="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

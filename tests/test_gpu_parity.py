@@ -167,6 +167,59 @@ def test_lpc_ff_matches_oracle(G, oracle, B, Tn, H, M):
     assert y.shape == ref.shape and rel_rms(y, ref) < REL_TOL
 
 
+def test_lpc_ff_gradients_reference_golden(G):
+    """adjoint of the frame-wise filter vs autograd of the reference module (torchaudio's
+    DifferentiableIIR + conv_transpose1d + interpolate backward)"""
+    g = golden("grads_ss")
+    H = int(g["hop"])
+    ex, gain, a = (T(g[k]).to(DEV).requires_grad_() for k in ("ex", "gain", "a"))
+    y = G.lpc_ff(ex, gain, a, torch.hann_window(4 * H).to(DEV), H)
+    assert rel_rms(y, T(g["ff_y"])) < 1e-5
+    dex, dgain, da = torch.autograd.grad(y, (ex, gain, a), T(g["ff_up"]).to(DEV))
+    assert rel_rms(dex, T(g["ff_dex"])) < REL_TOL
+    assert rel_rms(dgain, T(g["ff_dgain"])) < REL_TOL
+    assert rel_rms(da.flatten(1), T(g["ff_da"]).flatten(1)) < REL_TOL
+
+
+def test_lpc_ff_gradients_ragged(G, oracle):
+    """lengths that are not a multiple of the hop, hop 120, a different order: float64 autograd
+    through a literal per-frame implementation as the truth"""
+    for (Tn, H, M) in [(2500, 120, 12), (3001, 240, 20)]:
+        B, W = 2, 4 * H
+        Fr = Tn // H + 1
+        gain, a = synthetic_controls(B, Fr, M, seed=3)
+        gen = torch.Generator().manual_seed(9)
+        ex = torch.randn(B, Tn, generator=gen)
+        exd, gd, ad = (t.double().requires_grad_() for t in (ex, gain, a))
+        up_g = torch.nn.functional.interpolate(gd[:, None], (Fr - 1) * H + 1, mode="linear", align_corners=True)[:, 0]
+        n = min(Tn, up_g.shape[1])
+        e = exd[:, :n] * up_g[:, :n]
+        pad = torch.nn.functional.pad(e, (W // 2, W // 2))
+        nf = (pad.shape[1] - W) // H + 1
+        win = torch.hann_window(W, dtype=torch.float64)
+        full = torch.zeros(B, (nf - 1) * H + W, dtype=torch.float64)
+        norm = torch.zeros((nf - 1) * H + W, dtype=torch.float64)
+        for k in range(nf):
+            x = pad[:, k * H : k * H + W]
+            hist = [torch.zeros(B, dtype=torch.float64)] * M
+            outs = []
+            for i in range(W):
+                yv = x[:, i] - sum(ad[:, k, j] * hist[j] for j in range(M))
+                outs.append(yv)
+                hist = [yv] + hist[:-1]
+            full[:, k * H : k * H + W] = full[:, k * H : k * H + W] + torch.stack(outs, 1) * win
+            norm[k * H : k * H + W] += win
+        ref = full[:, W // 2 : W // 2 + (nf - 1) * H] / norm[W // 2 : W // 2 + (nf - 1) * H]
+        up = torch.randn(ref.shape, generator=gen)
+        gref = torch.autograd.grad(ref, (exd, gd, ad), up.double())
+        exg, gg, ag = (t.to(DEV).requires_grad_() for t in (ex, gain, a))
+        y = G.lpc_ff(exg, gg, ag, torch.hann_window(W).to(DEV), H)
+        assert y.shape == ref.shape and rel_rms(y, ref) < 1e-5
+        got = torch.autograd.grad(y, (exg, gg, ag), up.to(DEV))
+        for a_, b_ in zip(got, gref):
+            assert rel_rms(a_.flatten(1), b_.flatten(1)) < REL_TOL
+
+
 def test_biquad_cascade_reference_golden(G, oracle):
     g = golden("filters_rand")
     H = int(g["hop"])

@@ -171,6 +171,9 @@ def t_perf():
     for ch in (480, 960):
         timeit(f"lpc_ss B32 chunk{ch}", lambda: G.lpc_ss(ex, gain, a, H, chunk=ch))
     timeit("lpc_ff B32", lambda: G.lpc_ff(ex, gain, a, win, H))
+    exf = ex.clone().requires_grad_(); gf = gain.clone().requires_grad_(); af = a.clone().requires_grad_()
+    yf = G.lpc_ff(exf, gf, af, win, H); upf = torch.randn_like(yf)
+    timeit("lpc_ff bwd B32", lambda: torch.autograd.grad(yf, (exf, gf, af), upf, retain_graph=True))
     timeit("noise_fir B32", lambda: G.ltv_fir_blocks(ex, kern, H))
     timeit("room_fir B32", lambda: G.room_fir(ex, rk))
     timeit("osc B32 fp64", lambda: G.glottal_osc(ph, 1, w, 2400, table, dk, 4, True, "fp64"))
