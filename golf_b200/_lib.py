@@ -20,6 +20,8 @@ _SIGS = {
     "golf_last_cuda_error": (c_int, []),
     "golf_launch_count": (c_uint64, []),
     "golf_lpc_ss_workspace_bytes": (c_size_t, [c_int] * 5),
+    "golf_lpc_ss_set_refine_tolerance": (None, [c_float]),
+    "golf_lpc_ss_get_refine_tolerance": (c_float, []),
     "golf_lpc_ss_fwd": (c_int, [P, c_int64, P, P, P, P] + [c_int] * 6 + [P, c_size_t, P]),
     "golf_lpc_ss_fwd_passes": (c_int, [P, c_int64, P, P, P, P] + [c_int] * 6 + [P, c_size_t, c_int, P]),
     "golf_lpc_ss_bwd_workspace_bytes": (c_size_t, [c_int] * 5),

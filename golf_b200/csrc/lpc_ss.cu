@@ -63,8 +63,13 @@ __global__ void ss_dzi_kernel(const float* __restrict__ u, const float* __restri
 }
 
 // ------------------------------------------------------------------ host side -----
+// Refinement trigger: a sequence is refined when max_p |E_p - S_{p+1}| > tol * max_p |S_p|.
+// 0 refines always; the default skips it where the stitched states already agree with the
+// solve to a few float32 ulps (well-conditioned filters) -- see DESIGN.md 3.1.
+static float g_refine_tol = 1e-4f;
+
 struct SsPlan {
-  int MP, Lc, C, HB;
+  int B, MP, Lc, C, HB;
   bool generic;
   size_t w_floats, s_floats;
 };
@@ -79,6 +84,7 @@ static bool make_plan(int B, int L, int M, int hop, int chunk, SsPlan* pl) {
     if (!mp_any) mp_any = c;
     if (hop % c == 0) { mp = c; break; }
   }
+  pl->B = B;
   pl->generic = (mp == 0);
   pl->MP = mp ? mp : mp_any;
   const int target = 240;
@@ -106,13 +112,17 @@ static bool make_plan(int B, int L, int M, int hop, int chunk, SsPlan* pl) {
   return true;
 }
 
-// workspace layout: W | S | E
-static size_t plan_bytes(const SsPlan& pl) { return align_up(pl.w_floats * 4, 256) + 2 * align_up(pl.s_floats * 4, 256); }
+// workspace layout: W | S | E | flags
+static size_t plan_bytes(const SsPlan& pl) {
+  return align_up(pl.w_floats * 4, 256) + 2 * align_up(pl.s_floats * 4, 256) + align_up((size_t)pl.B * 8, 256);
+}
 static void plan_pointers(const SsPlan& pl, void* workspace, SsParams* p) {
   char* ws = reinterpret_cast<char*>(workspace);
   p->W = reinterpret_cast<float*>(ws);
   p->S = reinterpret_cast<float*>(ws + align_up(pl.w_floats * 4, 256));
   p->E = reinterpret_cast<float*>(ws + align_up(pl.w_floats * 4, 256) + align_up(pl.s_floats * 4, 256));
+  p->flags = reinterpret_cast<unsigned int*>(ws + align_up(pl.w_floats * 4, 256) + 2 * align_up(pl.s_floats * 4, 256));
+  p->refine_tol = g_refine_tol;
 }
 
 
@@ -137,6 +147,9 @@ static int launch_form(const SsParams& p, int MP, bool generic, int passes, cuda
 }  // namespace golf
 
 using namespace golf;
+
+GOLF_API void golf_lpc_ss_set_refine_tolerance(float tol) { g_refine_tol = tol >= 0.f ? tol : 0.f; }
+GOLF_API float golf_lpc_ss_get_refine_tolerance(void) { return g_refine_tol; }
 
 GOLF_API size_t golf_lpc_ss_workspace_bytes(int B, int L, int M, int hop, int chunk) {
   SsPlan pl;

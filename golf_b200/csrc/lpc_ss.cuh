@@ -53,8 +53,10 @@ struct SsParams {
   float* S;            // [B][C][MP]            state entering each chunk (processing order)
   float* E;            // [B][C][MP]            state each chunk ended in (written by the solve)
   const float* zi;     // [B,M] or null (FORM0 only)
+  unsigned int* flags; // [B][2]: float bits of max |E_p - S_{p+1}| and max |S_p| (adaptive refinement)
   int B, L, F, M, hop, Lc, C, HB;
   float scale;
+  float refine_tol;    // refine sequence b only if mismatch > refine_tol * max|S| (0: always)
 };
 
 // processing index p, step n within chunk -> absolute time
@@ -280,6 +282,12 @@ __global__ void __launch_bounds__(32) ss_stitch_kernel(SsParams p, int refine) {
     }
   };
 
+  if (refine) {  // adaptive: skip sequences whose chunk-boundary mismatch is already negligible
+    const float mism = __uint_as_float(p.flags[2 * b]), smax = __uint_as_float(p.flags[2 * b + 1]);
+    if (!(mism > p.refine_tol * smax)) return;
+  } else if (lane == 0) {
+    p.flags[2 * b] = 0u, p.flags[2 * b + 1] = 0u;
+  }
   if (lane == 0) {
     for (int s = 0; s < kStitchStages; ++s) mbar_init(&bars[s], 1);
     mbar_fence_init();
@@ -358,13 +366,17 @@ __global__ void __launch_bounds__(32) ss_stitch_kernel(SsParams p, int refine) {
 // Taps are summed oldest-first in three interleaved chains with the newest tap last, so
 // consecutive steps overlap in the FMA pipe (the serial dependency is one FMA per step).
 template <int MP, int FORM, bool GENERIC>
-__global__ void __launch_bounds__(32) ss_solve_kernel(SsParams p) {
+__global__ void __launch_bounds__(32) ss_solve_kernel(SsParams p, int round) {
   constexpr int TST = MP + 1;  // tile row stride (odd -> conflict-free per-lane rows)
   constexpr int NLD = MP;      // staged elements per lane per tile (32 rows x MP / 32 lanes)
   extern __shared__ __align__(128) float smem[];
   const int lane = threadIdx.x;
   const int G = (p.C + 31) / 32;
   const int b = blockIdx.x / G, g = blockIdx.x % G;
+  if (round == 1) {  // refinement round: only for the sequences that need it
+    const float mism = __uint_as_float(p.flags[2 * b]), smax = __uint_as_float(p.flags[2 * b + 1]);
+    if (!(mism > p.refine_tol * smax)) return;
+  }
   const int pi = g * 32 + lane;
   const bool active = pi < p.C;
   const int pic = active ? pi : p.C - 1;
@@ -500,11 +512,34 @@ __global__ void __launch_bounds__(32) ss_solve_kernel(SsParams p) {
       }
     }
   }
-  // ---- the state this chunk really ended in (input of the refinement stitch)
-  if (active && p.E) {
-    float* e0 = p.E + ((size_t)b * p.C + pi) * MP;
+  // ---- the state this chunk really ended in (input of the refinement stitch), and how far
+  // it is from the stitched state of the next chunk (decides whether refinement is needed)
+  if (round == 0 && p.E) {
+    float mism = 0.f, smax = 0.f;
+    if (active) {
+      float* e0 = p.E + ((size_t)b * p.C + pi) * MP;
+      const float* s1 = p.S + ((size_t)b * p.C + min(pi + 1, p.C - 1)) * MP;
 #pragma unroll
-    for (int k = 0; k < MP; ++k) e0[k] = st[FORM == 0 ? MP - 1 - k : k];
+      for (int k = 0; k < MP; ++k) {
+        const float ev = st[FORM == 0 ? MP - 1 - k : k];
+        e0[k] = ev;
+        if (pi + 1 < p.C && k < p.M) {
+          const float sv = s1[k];
+          // NaN/inf states must force the comparison to "needs refinement"-agnostic: fmaxf drops NaN
+          mism = fmaxf(mism, fabsf(ev - sv));
+          smax = fmaxf(smax, fabsf(sv));
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      mism = fmaxf(mism, __shfl_xor_sync(0xffffffffu, mism, d));
+      smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, d));
+    }
+    if (lane == 0) {  // non-negative floats order like their bit patterns
+      atomicMax(p.flags + 2 * b, __float_as_uint(mism));
+      atomicMax(p.flags + 2 * b + 1, __float_as_uint(smax));
+    }
   }
 }
 
@@ -545,9 +580,9 @@ int launch_mp(const SsParams& p, bool generic, int passes, cudaStream_t st) {
     }
     if (refine || (passes & 4)) {
       if (generic)
-        ss_solve_kernel<MP, FORM, true><<<p.B * G, 32, sm_solve, st>>>(p);
+        ss_solve_kernel<MP, FORM, true><<<p.B * G, 32, sm_solve, st>>>(p, round);
       else
-        ss_solve_kernel<MP, FORM, false><<<p.B * G, 32, sm_solve, st>>>(p);
+        ss_solve_kernel<MP, FORM, false><<<p.B * G, 32, sm_solve, st>>>(p, round);
       GOLF_CHECK_LAUNCH();
     }
   }
