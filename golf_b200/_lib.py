@@ -37,6 +37,7 @@ _SIGS = {
     "golf_room_fir_bwd": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     "golf_glottal_osc_workspace_bytes": (c_size_t, [c_int] * 6),
     "golf_glottal_osc_fwd": (c_int, [P, P, P, P, P] + [c_int] * 11 + [P, c_size_t, P]),
+    "golf_glottal_osc_bwd_w": (c_int, [P, P, P, P, P, P] + [c_int] * 11 + [P, c_size_t, P]),
     "golf_wavetable_read_fwd": (c_int, [P, P, P] + [c_int] * 5 + [P]),
     "golf_linear_upsample": (c_int, [P, P, c_int, c_int, c_int, P]),
     "golf_rc2lpc_fwd": (c_int, [P, P, c_int, c_int, c_float, P]),

@@ -171,8 +171,12 @@ __device__ __forceinline__ float osc_inc(const float* ph, int t, float scale, in
 // (phase) coordinate follows ATen operation by operation -- the table is steep around glottal
 // closure; the row (time) coordinate uses t * (1/ydenom): rows differ slowly, the 1-ulp
 // difference against ATen's division moves the result by < 1e-7.
-__device__ __forceinline__ float osc_read(const float* __restrict__ tb, int R, int P, float wrapped, int t,
-                                          float inv_ydenom, int blocks) {
+struct OscTaps {
+  int row0, row1, c0, c1;      // table rows (already clamped to the R supplied ones) and columns; c1 < 0: outside
+  bool has_row1;
+  float w00, w01, w10, w11;    // bilinear weights of (row0,c0) (row0,c1) (row1,c0) (row1,c1)
+};
+__device__ __forceinline__ OscTaps osc_taps(int R, int P, float wrapped, int t, float inv_ydenom, int blocks) {
   const float gx = __fsub_rn(__fmul_rn(wrapped, 2.f), 1.f);
   const float gy = __fsub_rn(__fmul_rn(__fmul_rn((float)t, inv_ydenom), 2.f), 1.f);
   const float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), (float)P);  // (x+1)/2: *0.5 is the same float
@@ -180,19 +184,28 @@ __device__ __forceinline__ float osc_read(const float* __restrict__ tb, int R, i
   const float x0f = floorf(ix), y0f = floorf(iy);
   const float fx = __fsub_rn(ix, x0f), fy = __fsub_rn(iy, y0f);
   const int x0 = min(max((int)x0f, 0), P), y0 = min(max((int)y0f, 0), blocks);
+  OscTaps o;
   // column P wraps to column 0; column P+1 / row blocks+1 are outside the image (weight 0 anyway);
   // rows beyond the R supplied ones replicate the last (F.pad replicate, synth.py:138-148)
-  const int c0 = x0 == P ? 0 : x0, c1 = x0 + 1 >= P ? (x0 + 1 == P ? 0 : -1) : x0 + 1;
-  const float* r0p = tb + (size_t)min(y0, R - 1) * P;
-  const float* r1p = tb + (size_t)min(y0 + 1, R - 1) * P;
-  const bool row1 = y0 + 1 <= blocks;
-  const float t00 = __ldg(r0p + c0), t01 = c1 >= 0 ? __ldg(r0p + c1) : 0.f;
-  const float t10 = row1 ? __ldg(r1p + c0) : 0.f, t11 = (row1 && c1 >= 0) ? __ldg(r1p + c1) : 0.f;
+  o.c0 = x0 == P ? 0 : x0;
+  o.c1 = x0 + 1 >= P ? (x0 + 1 == P ? 0 : -1) : x0 + 1;
+  o.row0 = min(y0, R - 1), o.row1 = min(y0 + 1, R - 1);
+  o.has_row1 = y0 + 1 <= blocks;
   const float gx1 = __fsub_rn(1.f, fx), gy1 = __fsub_rn(1.f, fy);
-  float v = __fmul_rn(t00, __fmul_rn(gx1, gy1));
-  v = __fmaf_rn(t01, __fmul_rn(fx, gy1), v);
-  v = __fmaf_rn(t10, __fmul_rn(gx1, fy), v);
-  v = __fmaf_rn(t11, __fmul_rn(fx, fy), v);
+  o.w00 = __fmul_rn(gx1, gy1), o.w01 = __fmul_rn(fx, gy1), o.w10 = __fmul_rn(gx1, fy), o.w11 = __fmul_rn(fx, fy);
+  return o;
+}
+__device__ __forceinline__ float osc_read(const float* __restrict__ tb, int R, int P, float wrapped, int t,
+                                          float inv_ydenom, int blocks) {
+  const OscTaps o = osc_taps(R, P, wrapped, t, inv_ydenom, blocks);
+  const float* r0p = tb + (size_t)o.row0 * P;
+  const float* r1p = tb + (size_t)o.row1 * P;
+  const float t00 = __ldg(r0p + o.c0), t01 = o.c1 >= 0 ? __ldg(r0p + o.c1) : 0.f;
+  const float t10 = o.has_row1 ? __ldg(r1p + o.c0) : 0.f, t11 = (o.has_row1 && o.c1 >= 0) ? __ldg(r1p + o.c1) : 0.f;
+  float v = __fmul_rn(t00, o.w00);
+  v = __fmaf_rn(t01, o.w01, v);
+  v = __fmaf_rn(t10, o.w10, v);
+  v = __fmaf_rn(t11, o.w11, v);
   return v;
 }
 
@@ -225,6 +238,46 @@ struct OscParams {
   float scale, ydenom;
 };
 
+// running phase of the `os` oversampled samples of output-rate index mj (they share one knot interval)
+struct KnotPhase {
+  int r0;
+  double xk, dk, pk;   // aten_cpu: float64 running sum
+  uint64_t qx, qp;     // default: Q0.64 fixed point
+  int64_t qq;
+  __device__ __forceinline__ void init(const OscParams& p, const float* __restrict__ ph, int b, int mj, float os_f,
+                                       float inv_os_f, bool pow2) {
+    const int phase_hop = p.hp / p.os;
+    int k = phase_hop == 1 ? mj : mj / phase_hop;
+    k = min(k, p.Np - 1);
+    r0 = (mj - k * phase_hop) * p.os;
+    const float fk = __ldg(ph + k), fn = __ldg(ph + min(k + 1, p.Np - 1));
+    if (p.aten_cpu) {
+      const double inv_os = 1.0 / (double)p.os;
+      xk = (double)fk * inv_os;
+      dk = (double)fn * inv_os - xk;
+      pk = __ldg(p.pref + (size_t)b * p.Np + k);
+    } else {
+      qx = q64_from_float(div_os(fk, os_f, inv_os_f, pow2));
+      const uint64_t qn = q64_from_float(div_os(fn, os_f, inv_os_f, pow2));
+      qq = (int64_t)(qn - qx) / (int64_t)(2 * p.hp);  // slope term per r(r+1)
+      qp = reinterpret_cast<const unsigned long long*>(p.pref)[(size_t)b * p.Np + k];
+      const int spn = k / p.span;
+      for (int q = 0; q < spn; ++q) qp += p.totals[(size_t)b * kPrefSplit + q];
+    }
+  }
+  __device__ __forceinline__ float wrapped(const OscParams& p, int phs) const {
+    const int r = r0 + phs;
+    if (p.aten_cpu) {  // cumsum output is float32, then `% 1` in float32
+      const double phi = pk + (double)(r + 1) * xk + dk * ((double)r * (double)(r + 1)) / (2.0 * (double)p.hp);
+      const float f = (float)phi;
+      return __fsub_rn(f, floorf(f));
+    }
+    const uint64_t phi = qp + (uint64_t)(r + 1) * qx + (uint64_t)(qq * (int64_t)(r * (r + 1)));
+    const float wr = __fmul_rn(__ull2float_rn(phi), 5.42101086242752217e-20f);  // * 2^-64
+    return wr >= 1.f ? 0.f : wr;
+  }
+};
+
 __global__ void __launch_bounds__(128) osc_flow_decimate_kernel(OscParams p) {
   extern __shared__ __align__(16) float smem[];
   float* vp = smem;                      // [os][plen] polyphase oversampled flow
@@ -244,50 +297,18 @@ __global__ void __launch_bounds__(128) osc_flow_decimate_kernel(OscParams p) {
   // strip index j <-> output-rate index mj = m0 - Z + j; its `os` oversampled samples
   // t = mj*os + phs share one knot interval (knot spacing hp = phase_hop*os), so the float64
   // prefix / slope are fetched once per j:  vp[phs][j] = v[mj*os + phs]
-  const int phase_hop = p.hp / p.os;
-  const double inv_os = 1.0 / (double)p.os, inv_2hp = 1.0 / (2.0 * (double)p.hp);
   const bool pow2 = (p.os & (p.os - 1)) == 0;
   const float inv_os_f = 1.f / os_f, inv_yd = 1.f / p.ydenom;
   for (int j = tid; j < p.plen; j += blockDim.x) {
     const int mj = m0 - Z + j;
     const bool in = mj >= 0 && (int64_t)mj * p.os < p.N;
-    int k = 0, r0 = 0;
-    double xk = 0.0, dk = 0.0, pk = 0.0;        // aten_cpu: float64 running sum
-    uint64_t qx = 0, qp = 0;                     // default: Q0.64 fixed point
-    int64_t qq = 0;
-    if (in) {
-      k = phase_hop == 1 ? mj : mj / phase_hop;
-      k = min(k, p.Np - 1);
-      r0 = (mj - k * phase_hop) * p.os;
-      const float fk = __ldg(ph + k), fn = __ldg(ph + min(k + 1, p.Np - 1));
-      if (p.aten_cpu) {
-        xk = (double)fk * inv_os;
-        dk = (double)fn * inv_os - xk;
-        pk = __ldg(p.pref + (size_t)b * p.Np + k);
-      } else {
-        qx = q64_from_float(div_os(fk, os_f, inv_os_f, pow2));
-        const uint64_t qn = q64_from_float(div_os(fn, os_f, inv_os_f, pow2));
-        qq = (int64_t)(qn - qx) / (int64_t)(2 * p.hp);  // slope term per r(r+1)
-        qp = reinterpret_cast<const unsigned long long*>(p.pref)[(size_t)b * p.Np + k];
-        const int spn = k / p.span;
-        for (int q = 0; q < spn; ++q) qp += p.totals[(size_t)b * kPrefSplit + q];
-      }
-    }
+    KnotPhase kp;
+    if (in) kp.init(p, ph, b, mj, os_f, inv_os_f, pow2);
     for (int phs = 0; phs < p.os; ++phs) {
       const int t = mj * p.os + phs;
       float v = 0.f;
       if (in && t < p.N) {
-        const int r = r0 + phs;
-        float wr;
-        if (p.aten_cpu) {  // cumsum output is float32, then `% 1` in float32
-          const double phi = pk + (double)(r + 1) * xk + dk * ((double)r * (double)(r + 1)) * inv_2hp;
-          const float f = (float)phi;
-          wr = __fsub_rn(f, floorf(f));
-        } else {
-          const uint64_t phi = qp + (uint64_t)(r + 1) * qx + (uint64_t)(qq * (int64_t)(r * (r + 1)));
-          wr = __fmul_rn(__ull2float_rn(phi), 5.42101086242752217e-20f);  // * 2^-64
-          if (wr >= 1.f) wr = 0.f;
-        }
+        const float wr = kp.wrapped(p, phs);
         v = osc_read(tb, p.Fw, p.P, wr, t, inv_yd, p.blocks);
         // torch.rsqrt: MUFU.RSQ-based rsqrtf is within 2 ulp of ATen's CPU 1/sqrt
         if (p.equal_energy) v = __fmul_rn(v, rsqrtf(osc_inc(ph, t, p.scale, p.Np, os_f, inv_os_f, pow2)));
@@ -307,6 +328,99 @@ __global__ void __launch_bounds__(128) osc_flow_decimate_kernel(OscParams p) {
     if (m0 + r0 + i < p.n_out) ob[m0 + r0 + i] = acc[i];
 }
 
+
+// ---- adjoint w.r.t. the table-selection weight -----------------------------------------
+// d_w[b,f] = (n_tab-1) * sum_t gv[t] rs(t) * sum_{taps of t in row f} weight * (T[lo_f+1][col] - T[lo_f][col])
+// with gv = transposed decimation of the output gradient.  Same tiling as the forward: a CTA owns
+// 1024 output-rate indices; gv comes from the polyphase correlations with reversed taps, the table
+// geometry from the same phase code; per-row partial sums go through shared memory, one float
+// atomicAdd per (CTA, row) to global (order-dependent in the last bit).
+struct OscBwdParams {
+  OscParams f;          // forward geometry (out unused)
+  const float* gout;    // [B, n_out]
+  const float* w;       // [B, Fw]
+  const float* table;   // [n_tab, P]
+  float* d_w;           // [B, Fw], zero-initialised
+  int n_tab;
+};
+
+__global__ void __launch_bounds__(128) osc_dw_kernel(OscBwdParams q) {
+  const OscParams& p = q.f;
+  extern __shared__ __align__(16) float smem[];
+  float* gs = smem;                       // gout[m0 - Z + i]
+  float* hr = smem + p.plen;              // [os][kp12] reversed polyphase taps
+  float* dws = hr + p.os * p.kp12;        // [Fw] partial sums
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int m0 = blockIdx.x * kOscTile;
+  const float* ph = p.phase + (size_t)b * p.Np;
+  const float os_f = (float)p.os;
+  const int Z = p.zeros;
+  const bool pow2 = (p.os & (p.os - 1)) == 0;
+  const float inv_os_f = 1.f / os_f, inv_yd = 1.f / p.ydenom;
+  const float* gb = q.gout + (size_t)b * p.n_out;
+  for (int i = tid; i < p.plen; i += blockDim.x) {
+    const int m = m0 - Z + i;
+    gs[i] = (m >= 0 && m < p.n_out) ? __ldg(gb + m) : 0.f;
+  }
+  for (int i = tid; i < p.os * p.kp12; i += blockDim.x) {
+    const int phs = i / p.kp12, qr = i % p.kp12;
+    const int n = (2 * Z - qr) * p.os + phs;  // reversed: hr[phs][q'] = h[(2Z - q')*os + phs]
+    hr[i] = (qr <= 2 * Z && n >= 0 && n <= 2 * Z * p.os) ? (p.dec ? p.dec[n] : 1.f) : 0.f;
+  }
+  for (int i = tid; i < p.Fw; i += blockDim.x) dws[i] = 0.f;
+  __syncthreads();
+  const int r0 = tid * kR;
+  int cur = -1;          // row whose partial sums live in a0 (row cur) / a1 (row cur+1, clamped)
+  float a0 = 0.f, a1 = 0.f;
+  auto flush = [&]() {
+    if (cur >= 0) {
+      atomicAdd(dws + cur, a0);
+      atomicAdd(dws + min(cur + 1, p.Fw - 1), a1);
+    }
+    a0 = a1 = 0.f;
+  };
+  for (int phs = 0; phs < p.os; ++phs) {
+    float gv[kR];
+#pragma unroll
+    for (int i = 0; i < kR; ++i) gv[i] = 0.f;
+    fir_tile8(gs + r0, hr + phs * p.kp12, p.kp12, gv);  // gv[(m0+r0+i)*os + phs]
+#pragma unroll
+    for (int i = 0; i < kR; ++i) {
+      const int mj = m0 + r0 + i;
+      const int t = mj * p.os + phs;
+      if (mj >= p.n_out || t >= p.N) continue;
+      KnotPhase kp;
+      kp.init(p, ph, b, mj, os_f, inv_os_f, pow2);
+      const float wr = kp.wrapped(p, phs);
+      const OscTaps o = osc_taps(p.Fw, p.P, wr, t, inv_yd, p.blocks);
+      float g = gv[i];
+      if (p.equal_energy) g = __fmul_rn(g, rsqrtf(osc_inc(ph, t, p.scale, p.Np, os_f, inv_os_f, pow2)));
+      if (o.row0 != cur) {
+        flush();
+        cur = o.row0;
+      }
+      // slope of the row-interpolated table w.r.t. its selection weight: T[lo+1] - T[lo]
+      auto slope = [&](int row, int col) -> float {
+        const float raw = __fmul_rn(__ldg(q.w + (size_t)b * p.Fw + row), (float)(q.n_tab - 1));
+        const int lo = min(max((int)raw, 0), q.n_tab - 2);
+        return __ldg(q.table + (size_t)(lo + 1) * p.P + col) - __ldg(q.table + (size_t)lo * p.P + col);
+      };
+      float c0 = o.w00 * slope(o.row0, o.c0);
+      if (o.c1 >= 0) c0 = __fmaf_rn(o.w01, slope(o.row0, o.c1), c0);
+      a0 = __fmaf_rn(g, c0, a0);
+      if (o.has_row1) {
+        float c1 = o.w10 * slope(o.row1, o.c0);
+        if (o.c1 >= 0) c1 = __fmaf_rn(o.w11, slope(o.row1, o.c1), c1);
+        if (o.row1 == o.row0) a0 = __fmaf_rn(g, c1, a0); else a1 = __fmaf_rn(g, c1, a1);
+      }
+    }
+  }
+  flush();
+  __syncthreads();
+  for (int i = tid; i < p.Fw; i += blockDim.x)
+    if (dws[i] != 0.f) atomicAdd(q.d_w + (size_t)b * p.Fw + i, dws[i] * (float)(q.n_tab - 1));
+}
+
 struct OscLayout {
   int hp, N, n_out, hop_tab, blocks;
   size_t off_tables, off_pref, bytes;
@@ -321,6 +435,24 @@ static bool osc_layout(int B, int Np, int phase_hop, int Fw, int P, int os, OscL
   L->off_pref = align_up((size_t)B * Fw * P * 4, 256);
   L->bytes = L->off_pref + align_up((size_t)B * Np * 8, 256) + align_up((size_t)B * kPrefSplit * 8, 256);
   return true;
+}
+
+static OscParams osc_params(const float* phase, const float* tables, const double* pref, const unsigned long long* totals,
+                            int span, const float* dec_kernel, float* out, int B, int Np, int Fw, int w_hop, int P, int os,
+                            int zeros, int accumulate, int flags, const OscLayout& L) {
+  OscParams p{};
+  p.phase = phase, p.tables = tables, p.pref = pref, p.aten_cpu = accumulate;
+  p.totals = totals, p.span = span;
+  p.dec = os > 1 ? dec_kernel : nullptr, p.out = out;
+  p.B = B, p.Np = Np, p.hp = L.hp, p.N = L.N, p.n_out = L.n_out, p.Fw = Fw, p.P = P;
+  p.hop_tab = w_hop * os;
+  p.blocks = (L.N + p.hop_tab - 1) / p.hop_tab;
+  p.os = os, p.zeros = os > 1 ? zeros : 0, p.equal_energy = flags & 1;
+  p.kp12 = ceil_div(2 * p.zeros + 1, 12) * 12;
+  p.plen = (int)align_up((size_t)kOscTile + p.kp12 + 24, 4);
+  p.scale = lerp_scale(Np, L.hp);
+  p.ydenom = (float)((int64_t)p.hop_tab * p.blocks);
+  return p;
 }
 
 }  // namespace golf
@@ -358,22 +490,47 @@ GOLF_API int golf_glottal_osc_fwd(const float* phase, const float* w, const floa
   else
     osc_knot_prefix_kernel<<<B, 256, 0, st>>>(phase, pref, Np, L.hp, os, 0);
   GOLF_CHECK_LAUNCH();
-  OscParams p{};
-  p.phase = phase, p.tables = tables, p.pref = pref, p.aten_cpu = accumulate;
-  p.totals = totals, p.span = span;
-  p.dec = os > 1 ? dec_kernel : nullptr, p.out = out;
-  p.B = B, p.Np = Np, p.hp = L.hp, p.N = L.N, p.n_out = L.n_out, p.Fw = Fw, p.P = P;
-  p.hop_tab = w_hop * os;
-  p.blocks = (L.N + p.hop_tab - 1) / p.hop_tab;
-  p.os = os, p.zeros = os > 1 ? zeros : 0, p.equal_energy = flags & 1;
-  p.kp12 = ceil_div(2 * p.zeros + 1, 12) * 12;
-  p.plen = (int)align_up((size_t)kOscTile + p.kp12 + 24, 4);
-  p.scale = lerp_scale(Np, L.hp);
-  p.ydenom = (float)((int64_t)p.hop_tab * p.blocks);
+  OscParams p = osc_params(phase, tables, pref, totals, span, dec_kernel, out, B, Np, Fw, w_hop, P, os, zeros, accumulate, flags, L);
   const size_t sm = (size_t)os * (p.plen + p.kp12) * sizeof(float);
   if (sm > 48 * 1024) return GOLF_ERR_UNSUPPORTED;
   dim3 grid(ceil_div(L.n_out, kOscTile), B);
   osc_flow_decimate_kernel<<<grid, 128, sm, st>>>(p);
+  GOLF_CHECK_LAUNCH();
+  return GOLF_OK;
+}
+
+
+GOLF_API int golf_glottal_osc_bwd_w(const float* gout, const float* phase, const float* w, const float* table,
+                                    const float* dec_kernel, float* d_w, int B, int Np, int phase_hop, int Fw, int w_hop,
+                                    int n_tab, int P, int os, int zeros, int accumulate, int flags, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  if (!gout || !phase || !w || !table || !d_w || n_tab < 2 || w_hop <= 0 || zeros < 0) return GOLF_ERR_INVALID;
+  if (os > 1 && !dec_kernel) return GOLF_ERR_INVALID;
+  if (accumulate != 0 && accumulate != 1) return GOLF_ERR_INVALID;
+  OscLayout L;
+  if (!osc_layout(B, Np, phase_hop, Fw, P, os, &L)) return GOLF_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes < L.bytes) return GOLF_ERR_WORKSPACE;
+  if (B > 65535 || Fw > 1024) return GOLF_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = reinterpret_cast<char*>(workspace);
+  double* pref = reinterpret_cast<double*>(ws + L.off_pref);
+  unsigned long long* totals = reinterpret_cast<unsigned long long*>(ws + L.off_pref + align_up((size_t)B * Np * 8, 256));
+  const int span = ceil_div(Np, kPrefSplit);
+  // the phase prefix is recomputed (cheap) rather than saved between forward and backward
+  if (accumulate == 0)
+    osc_knot_prefix_q64_kernel<<<dim3(kPrefSplit, B), 256, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), totals, Np,
+                                                                  L.hp, (float)os, span);
+  else
+    osc_knot_prefix_kernel<<<B, 256, 0, st>>>(phase, pref, Np, L.hp, os, 0);
+  GOLF_CHECK_LAUNCH();
+  GOLF_CUDA(cudaMemsetAsync(d_w, 0, (size_t)B * Fw * sizeof(float), st));
+  OscBwdParams q{};
+  q.f = osc_params(phase, nullptr, pref, totals, span, dec_kernel, nullptr, B, Np, Fw, w_hop, P, os, zeros, accumulate, flags, L);
+  q.gout = gout, q.w = w, q.table = table, q.d_w = d_w, q.n_tab = n_tab;
+  const size_t sm = (size_t)(q.f.plen + os * q.f.kp12 + Fw) * sizeof(float);
+  if (sm > 48 * 1024) return GOLF_ERR_UNSUPPORTED;
+  dim3 grid(ceil_div(L.n_out, kOscTile), B);
+  osc_dw_kernel<<<grid, 128, sm, st>>>(q);
   GOLF_CHECK_LAUNCH();
   return GOLF_OK;
 }

@@ -347,25 +347,58 @@ def room_fir(x, k) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------- oscillator
+_OSC_MODES = {"exact": 0, "fp64": 0, "aten_cpu": 1}
+
+
+class _GlottalOsc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, phase, w, table, dec_kernel, phase_hop, w_hop, os_, equal_energy, mode):
+        phase_c, w_c, table_c = _cuda_f32(phase, "phase"), _cuda_f32(w, "w"), _cuda_f32(table, "table")
+        dk = None if dec_kernel is None else _cuda_f32(dec_kernel, "dec_kernel")
+        B, Np = phase_c.shape
+        Fw = w_c.shape[1]
+        n_tab, P = table_c.shape
+        zeros = 0 if dk is None else (dk.numel() - 1) // (2 * os_)
+        N = (Np - 1) * phase_hop * os_ + 1
+        out = torch.empty(B, (N - 1) // os_ + 1, dtype=torch.float32, device=phase_c.device)
+        lib = _lib.lib()
+        ws = _workspace(lib.golf_glottal_osc_workspace_bytes(B, Np, phase_hop, Fw, P, os_), phase_c.device)
+        with _on(phase_c.device):
+            rc = lib.golf_glottal_osc_fwd(_ptr(phase_c), _ptr(w_c), _ptr(table_c), _ptr(dk), _ptr(out), B, Np, phase_hop, Fw,
+                                          w_hop, n_tab, P, os_, zeros, mode, 1 if equal_energy else 0, _ptr(ws), ws.numel(), _stream())
+        check(rc, "golf_glottal_osc_fwd")
+        ctx.save_for_backward(phase_c, w_c, table_c, dk)
+        ctx.geom = (phase_hop, w_hop, os_, zeros, equal_energy, mode)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[2]:
+            raise GolfError("glottal_osc: gradients w.r.t. phase / table are not implemented (detach f0; trainable=False)")
+        if not ctx.needs_input_grad[1]:
+            return (None,) * 9
+        phase_c, w_c, table_c, dk = ctx.saved_tensors
+        phase_hop, w_hop, os_, zeros, equal_energy, mode = ctx.geom
+        gout = _cuda_f32(gout, "gout")
+        B, Np = phase_c.shape
+        Fw = w_c.shape[1]
+        n_tab, P = table_c.shape
+        d_w = torch.empty_like(w_c)
+        lib = _lib.lib()
+        ws = _workspace(lib.golf_glottal_osc_workspace_bytes(B, Np, phase_hop, Fw, P, os_), gout.device)
+        with _on(gout.device):
+            rc = lib.golf_glottal_osc_bwd_w(_ptr(gout), _ptr(phase_c), _ptr(w_c), _ptr(table_c), _ptr(dk), _ptr(d_w), B, Np,
+                                            phase_hop, Fw, w_hop, n_tab, P, os_, zeros, mode, 1 if equal_energy else 0,
+                                            _ptr(ws), ws.numel(), _stream())
+        check(rc, "golf_glottal_osc_bwd_w")
+        return None, d_w, None, None, None, None, None, None, None
+
+
 def glottal_osc(phase, phase_hop: int, w, w_hop: int, table, dec_kernel=None, oversampling: int = 1,
                 equal_energy: bool = False, accumulate: str = "exact") -> torch.Tensor:
-    phase, w, table = _cuda_f32(phase, "phase"), _cuda_f32(w, "w"), _cuda_f32(table, "table")
-    dec_kernel = None if dec_kernel is None else _cuda_f32(dec_kernel, "dec_kernel")
-    B, Np = phase.shape
-    Fw = w.shape[1]
-    n_tab, P = table.shape
-    os_ = int(oversampling)
-    zeros = 0 if dec_kernel is None else (dec_kernel.numel() - 1) // (2 * os_)
-    N = (Np - 1) * phase_hop * os_ + 1
-    out = torch.empty(B, (N - 1) // os_ + 1, dtype=torch.float32, device=phase.device)
-    lib = _lib.lib()
-    ws = _workspace(lib.golf_glottal_osc_workspace_bytes(B, Np, phase_hop, Fw, P, os_), phase.device)
-    mode = {"exact": 0, "fp64": 0, "aten_cpu": 1}[accumulate]
-    with _on(phase.device):
-        rc = lib.golf_glottal_osc_fwd(_ptr(phase), _ptr(w), _ptr(table), _ptr(dec_kernel), _ptr(out), B, Np, phase_hop, Fw,
-                                      w_hop, n_tab, P, os_, zeros, mode, 1 if equal_energy else 0, _ptr(ws), ws.numel(), _stream())
-    check(rc, "golf_glottal_osc_fwd")
-    return out
+    """IndexedGlottalFlowTable.forward; differentiable in the table-selection weight `w`."""
+    return _GlottalOsc.apply(phase, w, table, dec_kernel, int(phase_hop), int(w_hop), int(oversampling), bool(equal_energy),
+                             _OSC_MODES[accumulate])
 
 
 def wavetable_read(wrapped, tables, hop_tab: int) -> torch.Tensor:

@@ -153,6 +153,14 @@ int golf_glottal_osc_fwd(const float *phase, const float *w, const float *table,
                          int Fw, int w_hop, int n_tab, int P, int os, int zeros,
                          int accumulate, int flags, void *workspace, size_t workspace_bytes,
                          void *stream);
+/* Adjoint w.r.t. the selection weight: gout [B, n_out] -> d_w [B,Fw] (same geometry arguments
+ * and workspace size as the forward; the gradient w.r.t. phase is not provided -- the shipped
+ * configs detach f0).  Accumulated with float atomics (last bit not reproducible). */
+int golf_glottal_osc_bwd_w(const float *gout, const float *phase, const float *w,
+                           const float *table, const float *dec_kernel, float *d_w, int B, int Np,
+                           int phase_hop, int Fw, int w_hop, int n_tab, int P, int os, int zeros,
+                           int accumulate, int flags, void *workspace, size_t workspace_bytes,
+                           void *stream);
 /* GlottalFlowTable.generate: wrapped [B,N] in [0,1), tables [B,R,P] at hop hop_tab. */
 int golf_wavetable_read_fwd(const float *wrapped, const float *tables, float *out, int B,
                             int N, int R, int P, int hop_tab, void *stream);

@@ -460,7 +460,9 @@ def glottal_osc(
 ) -> torch.Tensor:
     """IndexedGlottalFlowTable.forward, models/synth.py:213-263.  phase [B,Np] at
     `phase_hop` (cycles/sample), w [B,Fw] at `w_hop`."""
-    phase, w, table = _f32(phase), _f32(w), _f32(table)
+    phase, table = _f32(phase), _f32(table)
+    if not w.requires_grad:
+        w = _f32(w)
     tables = select_tables(table, w)
     up = upsample_time(phase / oversampling, phase_hop * oversampling)
     wrapped = phase_accumulate(up, accumulate) if wrapped_override is None else wrapped_override

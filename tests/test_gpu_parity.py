@@ -328,6 +328,26 @@ def test_oscillator_sample_rate_f0(G, oracle):
         assert y.shape == ref.shape == (B, Tn) and rel_rms(y, ref) < 2e-5
 
 
+def test_oscillator_weight_gradient(G, oracle):
+    """d/dw of the oscillator vs torch autograd through the CPU restatement (float64 phase)"""
+    B, Tn = 2, 9600
+    gen = torch.Generator().manual_seed(14)
+    f0 = (180 + 0.5 * torch.cumsum(torch.randn(B, Tn, generator=gen), 1)).clamp(80, 400)
+    ph = f0 / 24000
+    w = (0.2 + 0.6 * torch.rand(B, Tn // 2400 + 1, generator=gen))
+    table, _ = oracle.glottal_table()
+    dk = oracle.decimate_kernel(4)
+    wr = w.clone().requires_grad_()
+    ref = oracle.glottal_osc(ph, 1, wr, 2400, table, 4, True, "fp64")
+    up = torch.randn(ref.shape, generator=gen)
+    (g_ref,) = torch.autograd.grad(ref, wr, up)
+    wg = w.to(DEV).requires_grad_()
+    y = G.glottal_osc(ph.to(DEV), 1, wg, 2400, table.to(DEV), dk.to(DEV), 4, True, "exact")
+    assert rel_rms(y, ref.detach()) < 2e-5
+    (g_w,) = torch.autograd.grad(y, wg, up.to(DEV))
+    assert rel_rms(g_w, g_ref) < 1e-3  # sums of ~1e4 terms in a different order, float atomics
+
+
 def test_wavetable_read_matches_generate(G, oracle):
     gen = torch.Generator().manual_seed(6)
     table, _ = oracle.glottal_table()
