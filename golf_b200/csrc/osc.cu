@@ -235,7 +235,7 @@ struct OscParams {
   int B, Np, hp, N, n_out, Fw, P, hop_tab, blocks, os, zeros, equal_energy;
   int plen;               // per-phase strip length (floats, multiple of 4)
   int kp12;               // per-phase taps padded to a multiple of 12
-  float scale, ydenom;
+  float scale, ydenom, inv_2hp;
 };
 
 // running phase of the `os` oversampled samples of output-rate index mj (they share one knot interval)
@@ -259,7 +259,9 @@ struct KnotPhase {
     } else {
       qx = q64_from_float(div_os(fk, os_f, inv_os_f, pow2));
       const uint64_t qn = q64_from_float(div_os(fn, os_f, inv_os_f, pow2));
-      qq = (int64_t)(qn - qx) / (int64_t)(2 * p.hp);  // slope term per r(r+1)
+      // slope term per r(r+1): (x_{k+1}-x_k)/(2hp).  A float reciprocal is plenty: its 6e-8 relative
+      // error moves the phase by < 1e-9 cycles (the term itself is a second-order correction)
+      qq = __float2ll_rn(__ll2float_rn((int64_t)(qn - qx)) * p.inv_2hp);
       qp = reinterpret_cast<const unsigned long long*>(p.pref)[(size_t)b * p.Np + k];
       const int spn = k / p.span;
       for (int q = 0; q < spn; ++q) qp += p.totals[(size_t)b * kPrefSplit + q];
@@ -278,6 +280,7 @@ struct KnotPhase {
   }
 };
 
+template <int OS>  // oversampling factor known at compile time (0: runtime)
 __global__ void __launch_bounds__(128) osc_flow_decimate_kernel(OscParams p) {
   extern __shared__ __align__(16) float smem[];
   float* vp = smem;                      // [os][plen] polyphase oversampled flow
@@ -304,8 +307,10 @@ __global__ void __launch_bounds__(128) osc_flow_decimate_kernel(OscParams p) {
     const bool in = mj >= 0 && (int64_t)mj * p.os < p.N;
     KnotPhase kp;
     if (in) kp.init(p, ph, b, mj, os_f, inv_os_f, pow2);
-    for (int phs = 0; phs < p.os; ++phs) {
-      const int t = mj * p.os + phs;
+    const int nos = OS ? OS : p.os;
+#pragma unroll
+    for (int phs = 0; phs < nos; ++phs) {
+      const int t = mj * nos + phs;
       float v = 0.f;
       if (in && t < p.N) {
         const float wr = kp.wrapped(p, phs);
@@ -321,7 +326,9 @@ __global__ void __launch_bounds__(128) osc_flow_decimate_kernel(OscParams p) {
   float acc[kR];
 #pragma unroll
   for (int i = 0; i < kR; ++i) acc[i] = 0.f;
-  for (int phs = 0; phs < p.os; ++phs) fir_tile8(vp + phs * p.plen + r0, hp_ + phs * p.kp12, p.kp12, acc);
+  const int nos2 = OS ? OS : p.os;
+#pragma unroll
+  for (int phs = 0; phs < nos2; ++phs) fir_tile8(vp + phs * p.plen + r0, hp_ + phs * p.kp12, p.kp12, acc);
   float* ob = p.out + (size_t)b * p.n_out;
 #pragma unroll
   for (int i = 0; i < kR; ++i)
@@ -452,6 +459,7 @@ static OscParams osc_params(const float* phase, const float* tables, const doubl
   p.plen = (int)align_up((size_t)kOscTile + p.kp12 + 24, 4);
   p.scale = lerp_scale(Np, L.hp);
   p.ydenom = (float)((int64_t)p.hop_tab * p.blocks);
+  p.inv_2hp = 1.f / (2.f * (float)L.hp);
   return p;
 }
 
@@ -494,7 +502,12 @@ GOLF_API int golf_glottal_osc_fwd(const float* phase, const float* w, const floa
   const size_t sm = (size_t)os * (p.plen + p.kp12) * sizeof(float);
   if (sm > 48 * 1024) return GOLF_ERR_UNSUPPORTED;
   dim3 grid(ceil_div(L.n_out, kOscTile), B);
-  osc_flow_decimate_kernel<<<grid, 128, sm, st>>>(p);
+  switch (os) {
+    case 1: osc_flow_decimate_kernel<1><<<grid, 128, sm, st>>>(p); break;
+    case 2: osc_flow_decimate_kernel<2><<<grid, 128, sm, st>>>(p); break;
+    case 4: osc_flow_decimate_kernel<4><<<grid, 128, sm, st>>>(p); break;
+    default: osc_flow_decimate_kernel<0><<<grid, 128, sm, st>>>(p); break;
+  }
   GOLF_CHECK_LAUNCH();
   return GOLF_OK;
 }
