@@ -208,18 +208,26 @@ def run_gpu(args):
 
     # one captured CUDA graph per resident input set (golf_b200.graphs.GraphedSynth, public API):
     # a replay is one launch, so the timed region measures the GPU, not Python's enqueue rate
-    from golf_b200.graphs import GraphedSynth
+    from golf_b200.graphs import GraphedSynth, PipelinedSynth
 
+    DEPTH = 3
     with torch.no_grad():
         graphed = [GraphedSynth(dec, params_of(s)) for s in dev_sets]
-    out_host = torch.empty(BATCH, T, dtype=torch.float32).pin_memory()
+        pipe = PipelinedSynth(dec, params_of(dev_sets[0]), depth=DEPTH)
+    out_host = [torch.empty(BATCH, T, dtype=torch.float32).pin_memory() for _ in range(DEPTH)]
 
     def step_dev(i):
         return graphed[i % N_SETS](**params_of(dev_sets[i % N_SETS]))
 
-    def step_e2e(i):  # host (pinned) controls -> H2D into the graph's inputs -> replay -> D2H of the waveform
+    # host (pinned) controls -> H2D into a slot's graph inputs -> replay -> D2H of the waveform into pinned
+    # host memory, EVERY step; consecutive steps overlap on three streams (PipelinedSynth, public API)
+    def step_e2e(i):
+        pipe.submit(out_host[i % DEPTH], **params_of(host_sets[i % N_SETS]))
+        return pipe.slots[0]._out
+
+    def step_e2e_serial(i):  # the same without overlap: latency of one host-to-host call
         y = graphed[0](**params_of(host_sets[i % N_SETS])).as_tensor()
-        out_host[:, : y.shape[1]].copy_(y, non_blocking=True)
+        out_host[0][:, : y.shape[1]].copy_(y, non_blocking=True)
         return y
 
     def barrier():
@@ -227,7 +235,7 @@ def run_gpu(args):
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, fork=None, join=None):
         with torch.no_grad():
             for i in range(warmup):
                 fn(i)
@@ -235,8 +243,12 @@ def run_gpu(args):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
             l0 = golf_b200.launch_count()
             ev[0].record()
+            if fork:
+                fork()  # the pipeline's streams start after ev[0] ...
             for i in range(steps):
                 out = fn(warmup + i)
+            if join:
+                join()  # ... and ev[1] waits for all of them
             ev[1].record()
             barrier()
             ms = ev[0].elapsed_time(ev[1])
@@ -246,7 +258,8 @@ def run_gpu(args):
 
     with ClockSampler(local) as clocks:
         ms, launches, out = timed(step_dev, args.steps, args.warmup)
-        ms_e2e, _, out_h = timed(step_e2e, args.steps, args.warmup)
+        ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup, pipe.fork_from, pipe.join_into)
+        ms_ser, _, _ = timed(step_e2e_serial, args.steps, args.warmup)
     launches = args.steps * graphed[0].kernels_captured  # golf_b200 kernels replayed inside the timed region
     n_out = out.shape[1]
     total = world * BATCH * T
@@ -299,7 +312,8 @@ def run_gpu(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(world), "clocks": clocks.summary(),
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps, "pipeline": f"{DEPTH} slots, H2D / graph replay / D2H on three streams",
+                "serial_ms_per_step": ms_ser / args.steps},
         "gpu_launches": int(launches), "roofline": roof, "output_samples_per_utterance": int(n_out),
         "rtf": (ms / args.steps * 1e-3) / (BATCH * SECONDS),
     }

@@ -160,8 +160,11 @@ GOLF_API size_t golf_lpc_ss_workspace_bytes(int B, int L, int M, int hop, int ch
 GOLF_API int golf_lpc_ss_fwd_passes(const float* ex, int64_t ex_stride, const float* gain, const float* a, const float* zi,
                                     float* y, int B, int L, int F, int M, int hop, int chunk, void* workspace,
                                     size_t workspace_bytes, int passes, void* stream) {
-  if (!ex || !a || !y || B <= 0 || L <= 0 || F <= 0 || M <= 0 || hop <= 0) return GOLF_ERR_INVALID;
-  if (ex_stride < L || (int64_t)L > (int64_t)(F - 1) * hop + 1) return GOLF_ERR_INVALID;
+  if (!a || B <= 0 || L <= 0 || F <= 0 || M <= 0 || hop <= 0 || passes <= 0 || passes > 31) return GOLF_ERR_INVALID;
+  // the excitation may be absent only for a responses-only call; the output only if nothing solves
+  if (!ex && passes != 1) return GOLF_ERR_INVALID;
+  if (!y && (passes & (4 | 8))) return GOLF_ERR_INVALID;
+  if ((ex && ex_stride < L) || (int64_t)L > (int64_t)(F - 1) * hop + 1) return GOLF_ERR_INVALID;
   SsPlan pl;
   if (!make_plan(B, L, M, hop, chunk, &pl)) return GOLF_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < plan_bytes(pl)) return GOLF_ERR_WORKSPACE;

@@ -97,7 +97,10 @@ __global__ void __launch_bounds__(kRespThreads, (MP <= 24 ? 2 : 1)) ss_response_
   float4* lw = reinterpret_cast<float4*>(etile + CPW * MP);          // [CPW][MP] (l0, l1, i0, i1) per row
   const float* __restrict__ ab = p.a + (size_t)b * p.F * p.M;
   const float* __restrict__ gb = p.gain ? p.gain + (size_t)b * p.F : nullptr;
-  const float* __restrict__ inb = p.in + (size_t)b * p.in_stride;
+  // in == nullptr: transition matrices only (they depend on the coefficients alone, so the host
+  // can run this launch on a side stream while the excitation is still being produced); the
+  // zero-state responses then come from ss_solve_kernel(round -1)
+  const float* __restrict__ inb = p.in ? p.in + (size_t)b * p.in_stride : nullptr;
 
   // state: FORM0 st[c][k] = output of tile position k; FORM1 st[c][k] = (negated) pending sum
   // consumed at tile position k.  Column `col` starts from the unit state `col`; column M
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(kRespThreads, (MP <= 24 ? 2 : 1)) ss_response_
       const int t = time_of<FORM>(p, ppi, tile * MP + sr);
       const bool ok = r < CPW * MP && ppi < nresp && t >= 0 && t < p.L;
       const Lerp w = lerp_at(ok ? t : 0, p.scale, p.F);
-      pre_x[j] = ok ? __ldg(inb + t) : 0.f;
+      pre_x[j] = (ok && inb) ? __ldg(inb + t) : 0.f;
       pre_g0[j] = (FORM == 0 && gb) ? __ldg(gb + w.i0) : 1.f;
       pre_g1[j] = (FORM == 0 && gb) ? __ldg(gb + w.i1) : 1.f;
       pre_w[j] = make_float4(ok ? w.l0 : 0.f, ok ? w.l1 : 0.f, __int_as_float(w.i0), __int_as_float(w.i1));
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(kRespThreads, (MP <= 24 ? 2 : 1)) ss_response_
 #pragma unroll
     for (int cc = 0; cc < kNC; ++cc) {
       const int col = kNC * li + cc;
-      if (col <= p.M) {
+      if (col < p.M || (col == p.M && inb)) {
 #pragma unroll
         for (int k4 = 0; k4 < MP / 4; ++k4) {
           float4 v;
@@ -365,6 +368,10 @@ __global__ void __launch_bounds__(32) ss_stitch_kernel(SsParams p, int refine) {
 // pair sits in registers and is reloaded at tile starts only.
 // Taps are summed oldest-first in three interleaved chains with the newest tap last, so
 // consecutive steps overlap in the FMA pipe (the serial dependency is one FMA per step).
+// round 0: solve from the stitched states S, write the output and the end states E;
+// round 1: the same after the refinement stitch, only for the sequences that need it;
+// round -1: from REST, no output -- the end state is the chunk's zero-state response z, written
+//           into the z slot of W (used when pass 1 ran without the excitation).
 template <int MP, int FORM, bool GENERIC>
 __global__ void __launch_bounds__(32) ss_solve_kernel(SsParams p, int round) {
   constexpr int TST = MP + 1;  // tile row stride (odd -> conflict-free per-lane rows)
@@ -395,7 +402,7 @@ __global__ void __launch_bounds__(32) ss_solve_kernel(SsParams p, int round) {
 #pragma unroll
     for (int k = 0; k < MP; ++k) {
       const int comp = FORM == 0 ? MP - 1 - k : k;
-      st[k] = active ? s0[comp] : 0.f;
+      st[k] = (active && round >= 0) ? s0[comp] : 0.f;
     }
   }
   float na0[MP], na1[MP];  // negated frame pair (registers; !GENERIC)
@@ -426,15 +433,20 @@ __global__ void __launch_bounds__(32) ss_solve_kernel(SsParams p, int round) {
     }
     __syncwarp();
     const bool reload = !GENERIC && (n0 % p.HB == 0);
+    // per-tile scalars: step s of this lane is at time t0 +- s; it is a real sample iff lo_s <= s < hi_s
+    const int t0 = time_of<FORM>(p, pic, n0);
+    const int lo_s = FORM == 0 ? 0 : max(0, t0 - p.L + 1);
+    const int hi_s = active ? (FORM == 0 ? min(MP, p.L - t0) : min(MP, t0 + 1)) : 0;
+    const float tf0 = (float)max(t0, 0);
 #pragma unroll
     for (int s = 0; s < MP; ++s) {
-      const int t = time_of<FORM>(p, pic, n0 + s);
-      const bool valid = active && t >= 0 && t < p.L;
-      const int tc = valid ? t : 0;
+      const bool valid = s >= lo_s && s < hi_s;
       float nc[MP];
       float gv = 1.f;
       bool slow = GENERIC;
       Lerp w;
+      int tc = 0;
+      if (GENERIC || s == 0 || s == MP - 1) tc = valid ? (FORM == 0 ? t0 + s : t0 - s) : 0;
       if (!GENERIC) {
         if (s == 0 && reload) {  // warp-uniform: load the frame pair the coming steps live in
           kreg = min(tc / p.hop, p.F - 1);
@@ -447,13 +459,14 @@ __global__ void __launch_bounds__(32) ss_solve_kernel(SsParams p, int round) {
           }
           if (gb) g0 = __ldg(gb + kreg), g1 = __ldg(gb + k1);
         }
-        const float src = __fmul_rn(p.scale, (float)tc);
         if (s == (FORM == 0 ? 0 : MP - 1)) {
           // only here can ATen's floor(src) fall outside the register pair (t % hop == 0)
           w = lerp_at(tc, p.scale, p.F);
-          slow = __any_sync(0xffffffffu, w.i0 != kreg);
+          slow = __any_sync(0xffffffffu, valid && w.i0 != kreg);
         }
         if (!slow) {
+          // float(t) = tf0 +- s exactly (t < 2^24); ATen: src = scale * float(t)
+          const float src = __fmul_rn(p.scale, FORM == 0 ? tf0 + (float)s : tf0 - (float)s);
           float l1 = __fsub_rn(src, kregf);
           l1 = fminf(fmaxf(l1, 0.f), 1.f);
           const float l0 = __fsub_rn(1.f, l1);
@@ -500,6 +513,7 @@ __global__ void __launch_bounds__(32) ss_solve_kernel(SsParams p, int round) {
       }
     }
     __syncwarp();
+    if (round < 0) continue;
     // ---- write the tile back, coalesced
 #pragma unroll
     for (int j = 0; j < NLD; ++j) {
@@ -511,6 +525,22 @@ __global__ void __launch_bounds__(32) ss_solve_kernel(SsParams p, int round) {
         if (FORM == 1 && out2b) out2b[t] = tile2[r * TST + s];
       }
     }
+  }
+  if (round < 0) {  // zero-state response of this chunk -> W[b][pi][col M][:]
+    if (active && pi < p.C - 1) {
+      float* z = p.W + ((size_t)b * (p.C - 1) + pi) * ((MP + 1) * MP) + p.M * MP;
+#pragma unroll
+      for (int k4 = 0; k4 < MP / 4; ++k4) {
+        float4 v;
+        if (FORM == 0) {
+          v = make_float4(st[MP - 1 - 4 * k4], st[MP - 2 - 4 * k4], st[MP - 3 - 4 * k4], st[MP - 4 - 4 * k4]);
+        } else {
+          v = make_float4(st[4 * k4], st[4 * k4 + 1], st[4 * k4 + 2], st[4 * k4 + 3]);
+        }
+        *reinterpret_cast<float4*>(z + 4 * k4) = v;
+      }
+    }
+    return;
   }
   // ---- the state this chunk really ended in (input of the refinement stitch), and how far
   // it is from the stitched state of the next chunk (decides whether refinement is needed)
@@ -543,7 +573,8 @@ __global__ void __launch_bounds__(32) ss_solve_kernel(SsParams p, int round) {
   }
 }
 
-// passes: bit0 responses, bit1 stitch, bit2 solve, bit3 refinement (stitch + solve again)
+// passes: bit0 responses (without z when p.in is null), bit1 stitch, bit2 solve, bit3 refinement
+// (stitch + solve again), bit4 zero-state responses by a solve from rest (before the stitch)
 template <int MP, int FORM>
 int launch_mp(const SsParams& p, bool generic, int passes, cudaStream_t st) {
   const int nresp = p.C - 1;
@@ -571,6 +602,13 @@ int launch_mp(const SsParams& p, bool generic, int passes, cudaStream_t st) {
   }
   const int G = ceil_div(p.C, 32);
   const size_t sm_solve = (FORM == 0 ? 1 : 2) * 32 * (MP + 1) * sizeof(float);
+  if (nresp > 0 && (passes & 16)) {
+    if (generic)
+      ss_solve_kernel<MP, FORM, true><<<p.B * G, 32, sm_solve, st>>>(p, -1);
+    else
+      ss_solve_kernel<MP, FORM, false><<<p.B * G, 32, sm_solve, st>>>(p, -1);
+    GOLF_CHECK_LAUNCH();
+  }
   for (int round = 0; round < 2; ++round) {
     const bool refine = round == 1;
     if (refine && !((passes & 8) && nresp > 0)) break;

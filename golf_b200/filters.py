@@ -89,6 +89,17 @@ class LTVMinimumPhaseFilterPrecise(LTVFilterInterface):
         """inverse-filter the target (models/filters.py:186-195): returns (ex*gain, A(z) y)"""
         return _reverse(ex, y, gain, a)
 
+    # two-call form used by SourceFilterSynth's concurrent inference path: the chunk transition
+    # matrices need only `a`, so they are computed on a side stream while the source is synthesised
+    def responses(self, t_ex: int, gain, a, ex_hop: int = 1):
+        g, c = plain(gain), plain(a)
+        hop = hop_of(gain) // ex_hop
+        return G.lpc_ss_responses(c, G.lpc_ss_length(t_ex, c.shape[1], hop), hop)
+
+    def finish(self, ex, gain, a, ws):
+        ex_hop = hop_of(ex)
+        return like(ex, G.lpc_ss_finish(plain(ex), plain(gain), plain(a), hop_of(gain) // ex_hop, ws), ex_hop)
+
 
 def _reverse(ex, y, gain, a):
     resid = G.lpc_inverse(plain(y), plain(a), hop_of(a) // hop_of(y))
@@ -147,6 +158,20 @@ class LTVZeroPhaseFIRFilter(LTVFilterInterface):
             self._win_cache = self.window_fn(K, device=like_t.device, dtype=torch.float32)
             self._win_key = key
         return self._win_cache
+
+    def raw_kernels(self, log_mag) -> torch.Tensor:
+        """frame-rate half of the inference path: irfft(exp(log_mag)) (cuFFT); shift + window are
+        applied by the FIR kernel while it stages the taps"""
+        return torch.fft.irfft(torch.exp(plain(log_mag)).to(torch.complex64), dim=-1)
+
+    def apply_raw(self, ex, raw, hop: int, add=None):
+        y = G.ltv_fir_blocks(plain(ex), raw, hop // hop_of(ex), None if add is None else plain(add),
+                             window=self._window(raw.shape[-1], raw))
+        return like(ex, y, hop_of(ex))
+
+    @staticmethod
+    def out_length(t_ex: int, frames: int, n_taps: int, hop: int) -> int:
+        return G._fir_blocks_count(t_ex, frames, n_taps, hop) * hop
 
     def forward(self, ex, log_mag, add=None):
         hop = hop_of(log_mag) // hop_of(ex)

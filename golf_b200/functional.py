@@ -86,7 +86,7 @@ def lpc_ss_length(t_ex: int, frames: int, hop: int) -> int:
     return min(int(t_ex), (int(frames) - 1) * int(hop) + 1)
 
 
-def _lpc_ss_fwd(ex, gain, a, zi, hop: int, chunk: int = 0, passes: int = 15):
+def _lpc_ss_fwd(ex, gain, a, zi, hop: int, chunk: int = 0, passes: int = 15, ws=None):
     ex = _rows(ex, "ex")
     a = _cuda_f32(a, "a")
     gain = None if gain is None else _cuda_f32(gain, "gain")
@@ -101,12 +101,39 @@ def _lpc_ss_fwd(ex, gain, a, zi, hop: int, chunk: int = 0, passes: int = 15):
     nbytes = lib.golf_lpc_ss_workspace_bytes(B, L, M, hop, chunk)
     if nbytes == 0:
         raise GolfError(f"lpc_ss: unsupported configuration B={B} L={L} M={M} hop={hop} chunk={chunk}")
-    ws = _workspace(nbytes, ex.device)
+    if ws is None:
+        ws = _workspace(nbytes, ex.device)
+    elif ws.numel() < nbytes or ws.device != ex.device:
+        raise GolfError("lpc_ss: the workspace handed over by lpc_ss_responses does not fit this call")
     with _on(ex.device):
         rc = lib.golf_lpc_ss_fwd_passes(_ptr(ex), ex.stride(0), _ptr(gain), _ptr(a), _ptr(zi), _ptr(y), B, L, Fr, M, hop, chunk,
                                         _ptr(ws), ws.numel(), passes, _stream())
     check(rc, "golf_lpc_ss_fwd")
     return y
+
+
+def lpc_ss_responses(a, L: int, hop: int, chunk: int = 0) -> torch.Tensor:
+    """First half of the two-call form (include/golf_b200.h): the chunk transition matrices of the
+    filter `a` [B,F,M] over L samples, enqueued on the CURRENT stream -- they do not depend on the
+    excitation, so a caller can run this on a side stream while the excitation is produced.
+    Returns the workspace to hand to lpc_ss_finish (after joining the streams)."""
+    a = _cuda_f32(a, "a")
+    B, Fr, M = a.shape
+    lib = _lib.lib()
+    nbytes = lib.golf_lpc_ss_workspace_bytes(B, L, M, hop, chunk)
+    if nbytes == 0:
+        raise GolfError(f"lpc_ss: unsupported configuration B={B} L={L} M={M} hop={hop} chunk={chunk}")
+    ws = _workspace(nbytes, a.device)
+    with _on(a.device):
+        rc = lib.golf_lpc_ss_fwd_passes(0, 0, 0, _ptr(a), 0, 0, B, L, Fr, M, hop, chunk, _ptr(ws), ws.numel(), 1, _stream())
+    check(rc, "golf_lpc_ss_fwd(responses)")
+    return ws
+
+
+def lpc_ss_finish(ex, gain, a, hop: int, ws: torch.Tensor, zi=None, chunk: int = 0, refine: bool = True) -> torch.Tensor:
+    """Second half: zero-state responses (a solve from rest), stitch, solve, refinement.  Same
+    result, bit for bit, as lpc_ss(ex, gain, a, hop).  Inference path (no autograd)."""
+    return _lpc_ss_fwd(ex, gain, a, zi, hop, chunk, 16 | 2 | 4 | (8 if refine else 0), ws=ws)
 
 
 def _lpc_ss_bwd(gy, y, ex, gain, a, zi, hop: int, need, chunk: int = 0, refine: bool = True):

@@ -55,12 +55,91 @@ class GraphedSynth:
         leaves = [like(r, s, h) if (t and h is not None) else s for s, t, h, r in zip(self._static, self._is_tensor, self._hops, self._refs)]
         return tree_unflatten(leaves, self._spec)
 
-    def __call__(self, **params):
+    def load(self, **params) -> int:
+        """copy new control tensors (device or pinned host) into the static inputs, on the current
+        stream; returns the bytes copied"""
         leaves, _ = tree_flatten(params)
+        n = 0
         for dst, src, t in zip(self._static, leaves, self._is_tensor):
             if t:
                 s = plain(src)
                 if s.data_ptr() != dst.data_ptr():
                     dst.copy_(s, non_blocking=True)
+                    n += dst.numel() * dst.element_size()
+        return n
+
+    def replay(self):
         self.graph.replay()
         return self._out
+
+    def __call__(self, **params):
+        self.load(**params)
+        return self.replay()
+
+
+class PipelinedSynth:
+    """Host-to-host synthesis as a software pipeline over `depth` GraphedSynth slots:
+
+        copy-in stream : H2D(i+1)            pinned host controls -> slot's static inputs
+        compute stream :          graph(i)   one CUDA-graph replay of the decoder
+        copy-out stream:                D2H(i-1)   waveform -> pinned host buffer
+
+    PCIe is full duplex and independent of the SMs, so in steady state a step costs
+    max(H2D, compute, D2H) instead of their sum.  Slots are recycled in order; events keep a
+    slot's inputs from being overwritten before its replay has run and its output from being
+    overwritten before it has been copied out.
+
+        pipe = PipelinedSynth(decoder, example_params, depth=3)
+        t = pipe.submit(out_host, **host_params)     # enqueue only, returns a ticket
+        pipe.wait(t)                                 # out_host[:, :pipe.out_len] is valid
+    """
+
+    def __init__(self, decoder: torch.nn.Module, example_params: Dict[str, Any], depth: int = 3):
+        self.slots = [GraphedSynth(decoder, example_params) for _ in range(depth)]
+        out = plain(self.slots[0]._out)
+        self.device = out.device
+        self.out_len = out.shape[1]
+        self.kernels_captured = self.slots[0].kernels_captured
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(device=self.device) for _ in range(3))
+        self._ran = [None] * depth    # replay of the slot's previous use finished
+        self._read = [None] * depth   # copy-out of the slot's previous use finished
+        self._n = 0
+        self.h2d_bytes = 0
+
+    def fork_from(self, stream=None):
+        """order the pipeline after everything already enqueued on `stream` (default: current)"""
+        stream = stream or torch.cuda.current_stream(self.device)
+        for s in (self.s_in, self.s_run, self.s_out):
+            s.wait_stream(stream)
+
+    def join_into(self, stream=None):
+        stream = stream or torch.cuda.current_stream(self.device)
+        for s in (self.s_in, self.s_run, self.s_out):
+            stream.wait_stream(s)
+
+    def submit(self, out_host: torch.Tensor, **host_params) -> int:
+        k = self._n % len(self.slots)
+        slot = self.slots[k]
+        with torch.cuda.stream(self.s_in):
+            if self._ran[k] is not None:
+                self.s_in.wait_event(self._ran[k])
+            self.h2d_bytes = slot.load(**host_params)
+            loaded = torch.cuda.Event()
+            loaded.record(self.s_in)
+        with torch.cuda.stream(self.s_run):
+            self.s_run.wait_event(loaded)
+            if self._read[k] is not None:
+                self.s_run.wait_event(self._read[k])
+            y = plain(slot.replay())
+            self._ran[k] = torch.cuda.Event()
+            self._ran[k].record(self.s_run)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self._ran[k])
+            out_host[:, : y.shape[1]].copy_(y, non_blocking=True)
+            self._read[k] = torch.cuda.Event()
+            self._read[k].record(self.s_out)
+        self._n += 1
+        return k
+
+    def wait(self, ticket: int) -> None:
+        self._read[ticket].synchronize()

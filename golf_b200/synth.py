@@ -119,6 +119,11 @@ class IndexedGlottalFlowTable(GlottalFlowTable):
             self.decimater = Decimate(oversampling)
             self.decimater.register_buffer("kernel", self.decimater.kernel, persistent=False)
 
+    @staticmethod
+    def out_length(phase) -> int:
+        """samples produced for a phase track [B,Np] at hop h: (Np-1)*h + 1 (synth.py:242-262)"""
+        return (plain(phase).shape[1] - 1) * hop_of(phase) + 1
+
     def forward(self, phase, table_select_weight, phase_offset=None):
         w = plain(table_select_weight)
         assert w.dim() == 2

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GOLF_B200_ABI_VERSION 1
+#define GOLF_B200_ABI_VERSION 2
 
 enum {
   GOLF_OK = 0,
@@ -70,9 +70,13 @@ int golf_lpc_ss_fwd(const float *ex, int64_t ex_stride, const float *gain, const
                     const float *zi, float *y, int B, int L, int F, int M, int hop,
                     int chunk, void *workspace, size_t workspace_bytes, void *stream);
 /* Same, running only the selected passes (bit 0: chunk responses, bit 1: stitch, bit 2:
- * solve, bit 3: one refinement round = mismatch stitch + solve again).  golf_lpc_ss_fwd is
- * passes == 15; 7 skips the refinement (faster, less accurate on high-gain filters);
- * single bits are for per-kernel timing in bench.py. */
+ * solve, bit 3: one refinement round = mismatch stitch + solve again, bit 4: zero-state chunk
+ * responses by a solve from rest, run before the stitch).  golf_lpc_ss_fwd is passes == 15; 7
+ * skips the refinement (faster, less accurate on high-gain filters).
+ * Two-call form for overlapping with the producer of `ex`: the chunk transition matrices depend
+ * on `a` alone, so  passes == 1 with ex == NULL, y == NULL  may be enqueued on a side stream as
+ * soon as `a` exists; once ex is ready (and after a stream join)  passes == 30  on the SAME
+ * workspace finishes the job.  Results are bit-identical to passes == 15. */
 int golf_lpc_ss_fwd_passes(const float *ex, int64_t ex_stride, const float *gain,
                            const float *a, const float *zi, float *y, int B, int L, int F,
                            int M, int hop, int chunk, void *workspace, size_t workspace_bytes,
