@@ -68,23 +68,45 @@ __device__ __forceinline__ int time_of(const SsParams& p, int pi, int n) {
 __device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y); }
 
 // ------------------------------------------------------------------ pass 1 --------
-// Chunk responses.  Operand bandwidth decides the mapping: shared memory hands a warp 32
-// lane-words per cycle, the FP32 pipe wants 128 lane-FMAs per cycle, so every coefficient a
-// lane reads must feed FOUR of its FMAs.  Each lane therefore owns 4 of the M+1 columns of
-// one chunk ([Phi | z]; LPC = ceil((M+1)/4) lanes per chunk) and a warp hosts
-// CPW = 32/LPC chunks side by side (M=22: 6 lanes x 4 columns, 5 chunks per warp, 30 lanes).
-// Per step a lane issues MP/4 LDS.128 for its chunk's coefficient row and 4*MP FFMA.
-constexpr int kNC = 4;          // columns per lane
-constexpr int kRespThreads = 160;  // 5 warps: 2 CTAs/SM at <= 204 registers -> 10 warps/SM, one wave at B=32
+// Chunk responses.  Two resources decide the mapping:
+//  * operand bandwidth: shared memory hands a warp 32 lane-words per cycle, the FP32 pipe wants 128
+//    lane-FMAs per cycle, so every coefficient a lane reads must feed >= 4 of its FMAs: a lane owns
+//    NC columns of one chunk's [Phi | z] (LPC = ceil((MT+1)/NC) lanes per chunk, CPW = 32/LPC chunks
+//    side by side in a warp);
+//  * the register file: 4 schedulers x 16384 registers.  NC*MP state registers + a coefficient row
+//    need ~200 registers per lane, which fits exactly TWO warps per scheduler -- so the kernel is
+//    built to run well at 8 warps per SM: CTA = one warp (the block scheduler spreads 1-warp CTAs
+//    evenly), NC = 5 for the 24-slot ring (M = 22: 5 lanes x 5 columns, 6 chunks per warp, 30 lanes,
+//    1056 warps at B = 32 = 1.8 per scheduler), and each lane's NC FMA chains are independent so one
+//    warp alone can issue an FMA per cycle.
+// MT = taps actually summed (M <= MT <= MP): the ring keeps MP outputs so that Lc % MP == 0 tiles
+// work, but only MT products per column and step are issued (M = 22: 22 of 24, 8 % fewer FMAs).
+// Per step a lane issues ceil(MT/4) LDS.128 for its chunk's coefficient row and NC*MT FFMA.
+// Coefficient rows are interpolated (ATen arithmetic, negated) tile by tile by lanes mapped to
+// (chunk, group of TPL taps) whose frame pair sits in registers.
+template <int MP>
+struct RespCfg {
+  static constexpr int NC = (MP == 24) ? 5 : 4;  // columns per lane
+};
 
-template <int MP, int FORM>
-__global__ void __launch_bounds__(kRespThreads, (MP <= 24 ? 2 : 1)) ss_response_kernel(SsParams p, int LPC, int CPW) {
-  constexpr int TSTR = MP * MP + 4;  // per-chunk tile stride: +4 floats puts the groups in different bank quads
+template <int MP, int MT, int FORM>
+__global__ void __launch_bounds__(32, (MP <= 24 ? 8 : 4)) ss_response_kernel(SsParams p) {
+  constexpr int NC = RespCfg<MP>::NC;
+  constexpr int LPC = (MT + 1 + NC - 1) / NC;  // lanes per chunk
+  constexpr int CPW = 32 / LPC;                // chunks per warp
+  constexpr int ROWS = CPW * MP;               // coefficient rows staged per tile
+  constexpr int NA = (ROWS + 31) / 32;
+  constexpr int TSTR = MP * MP + 4;  // per-chunk tile stride: +4 floats puts the chunks in different bank quads
+  constexpr int SQ0 = 32 / CPW;                          // staging lanes available per chunk
+  constexpr int TPL = ((MP + SQ0 - 1) / SQ0 + 1) / 2 * 2;  // taps per staging lane (even: 8-byte stores)
+  constexpr int SQ = (MP + TPL - 1) / TPL;                // staging lanes used per chunk
+  constexpr int NQ = (MT + 3) / 4;                        // coefficient quads read per step
+  static_assert(LPC * CPW <= 32 && SQ * CPW <= 32 && MT <= MP && MT >= 1, "response kernel geometry");
   extern __shared__ __align__(128) float smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x;
   const int nresp = p.C - 1;
   const int wps = (nresp + CPW - 1) / CPW;  // warps per sequence
-  const int wg = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int wg = blockIdx.x;
   if (wg >= p.B * wps) return;
   const int b = wg / wps, w0 = (wg % wps) * CPW;
   const int gi = min(lane / LPC, CPW - 1), li = lane % LPC;
@@ -92,9 +114,9 @@ __global__ void __launch_bounds__(kRespThreads, (MP <= 24 ? 2 : 1)) ss_response_
   const int pi = w0 + gi;
   const bool chunk_on = lane_on && pi < nresp;
 
-  float* ctile = smem + (size_t)warp * (CPW * TSTR + CPW * MP * 5);  // [CPW][MP rows][MP taps] negated coefficients
-  float* etile = ctile + CPW * TSTR;                                 // [CPW][MP] chunk inputs
-  float4* lw = reinterpret_cast<float4*>(etile + CPW * MP);          // [CPW][MP] (l0, l1, i0, i1) per row
+  float* ctile = smem;                                       // [CPW][MP rows][MP taps] negated coefficients
+  float* etile = ctile + CPW * TSTR;                         // [CPW][MP] chunk inputs
+  float4* lw = reinterpret_cast<float4*>(etile + ROWS);      // [CPW][MP] (l0, l1, i0, i1) per row
   const float* __restrict__ ab = p.a + (size_t)b * p.F * p.M;
   const float* __restrict__ gb = p.gain ? p.gain + (size_t)b * p.F : nullptr;
   // in == nullptr: transition matrices only (they depend on the coefficients alone, so the host
@@ -105,11 +127,11 @@ __global__ void __launch_bounds__(kRespThreads, (MP <= 24 ? 2 : 1)) ss_response_
   // state: FORM0 st[c][k] = output of tile position k; FORM1 st[c][k] = (negated) pending sum
   // consumed at tile position k.  Column `col` starts from the unit state `col`; column M
   // (zero-state response) starts from rest and is driven by the input.
-  float st[kNC][MP];
-  bool zsr[kNC];
+  float st[NC][MP];
+  bool zsr[NC];
 #pragma unroll
-  for (int c = 0; c < kNC; ++c) {
-    const int col = kNC * li + c;
+  for (int c = 0; c < NC; ++c) {
+    const int col = NC * li + c;
     zsr[c] = (col == p.M);
 #pragma unroll
     for (int k = 0; k < MP; ++k) {
@@ -119,69 +141,81 @@ __global__ void __launch_bounds__(kRespThreads, (MP <= 24 ? 2 : 1)) ss_response_
   }
   const float* myc = ctile + gi * TSTR;
   const float* mye = etile + gi * MP;
-  float qa0[4], qa1[4];  // stage-B frame pair of this lane's (chunk, tap quad)
+  // staging role of this lane: chunk sk, taps [TPL*sg, TPL*sg + TPL); its frame pair in registers
+  const int sk = lane / SQ, sg = lane - sk * SQ;
+  const bool stager = lane < CPW * SQ;
+  float qa0[TPL], qa1[TPL];
   int qf0 = -1, qf1 = -1;
-  // interpolation weights (l0, l1, i0, i1) + input of the (chunk, row) pairs this lane stages,
-  // fetched one tile ahead so the global-load latency hides behind the recurrence
-  constexpr int NA = 4;  // CPW * MP <= 128 rows for every (M, MP) bucket (checked on the host)
+  // inputs (+ gain pair) of the (chunk, row) pairs this lane publishes, fetched one tile ahead so
+  // the global-load latency hides behind the recurrence
   float pre_x[NA], pre_g0[NA], pre_g1[NA];
-  float4 pre_w[NA];
+  auto row_time = [&](int r, int tile, bool& ok) {
+    const int k = r / MP, sr = r - k * MP;
+    const int ppi = w0 + k;
+    const int t = time_of<FORM>(p, ppi, tile * MP + sr);
+    ok = r < ROWS && ppi < nresp && t >= 0 && t < p.L;
+    return t;
+  };
   auto prefetch = [&](int tile) {  // raw loads only: nothing here waits on them
+    if (!inb) return;
 #pragma unroll
     for (int j = 0; j < NA; ++j) {
-      const int r = lane + 32 * j;
-      const int k = r / MP, sr = r - k * MP;
-      const int ppi = w0 + k;
-      const int t = time_of<FORM>(p, ppi, tile * MP + sr);
-      const bool ok = r < CPW * MP && ppi < nresp && t >= 0 && t < p.L;
+      bool ok;
+      const int t = row_time(lane + 32 * j, tile, ok);
       const Lerp w = lerp_at(ok ? t : 0, p.scale, p.F);
-      pre_x[j] = (ok && inb) ? __ldg(inb + t) : 0.f;
+      pre_x[j] = ok ? __ldg(inb + t) : 0.f;
       pre_g0[j] = (FORM == 0 && gb) ? __ldg(gb + w.i0) : 1.f;
       pre_g1[j] = (FORM == 0 && gb) ? __ldg(gb + w.i1) : 1.f;
-      pre_w[j] = make_float4(ok ? w.l0 : 0.f, ok ? w.l1 : 0.f, __int_as_float(w.i0), __int_as_float(w.i1));
     }
   };
+#pragma unroll
+  for (int j = 0; j < NA; ++j) pre_x[j] = 0.f, pre_g0[j] = pre_g1[j] = 1.f;
   prefetch(0);
 
 #pragma unroll 1
   for (int tile = 0; tile < p.Lc / MP; ++tile) {
     __syncwarp();
-    // ---- stage A: publish the weights + inputs prefetched for this tile
+    // ---- stage A: interpolation weights of every row + the inputs prefetched for this tile
 #pragma unroll
     for (int j = 0; j < NA; ++j) {
       const int r = lane + 32 * j;
-      if (r < CPW * MP) {
+      if (r < ROWS) {
+        bool ok;
+        const int t = row_time(r, tile, ok);
+        const Lerp w = lerp_at(ok ? t : 0, p.scale, p.F);
         float e = pre_x[j];
-        if (FORM == 0 && gb) e = __fmul_rn(e, __fmaf_rn(pre_w[j].x, pre_g0[j], __fmul_rn(pre_w[j].y, pre_g1[j])));
+        if (FORM == 0 && gb) e = __fmul_rn(e, __fmaf_rn(w.l0, pre_g0[j], __fmul_rn(w.l1, pre_g1[j])));
         etile[r] = e;
-        lw[r] = pre_w[j];
+        lw[r] = make_float4(ok ? w.l0 : 0.f, ok ? w.l1 : 0.f, __int_as_float(w.i0), __int_as_float(w.i1));
       }
     }
     __syncwarp();
-    // ---- stage B: coefficient rows (ATen arithmetic, negated).  Lane = (chunk, tap quad);
-    // its frame pair sits in registers and is re-fetched only when a row's frame differs
-    // (frame change, or ATen's floor() landing one frame low at t % hop == 0).
-    if (lane < CPW * (MP / 4)) {
-      const int k = lane / (MP / 4), tq = lane - k * (MP / 4);
+    // ---- stage B: coefficient rows (ATen arithmetic, negated).  The frame pair is re-fetched only
+    // when a row's frames differ (frame change, or ATen's floor() landing one frame low at t % hop == 0).
+    if (stager) {
 #pragma unroll 4
       for (int sr = 0; sr < MP; ++sr) {
-        const float4 wv = lw[k * MP + sr];
+        const float4 wv = lw[sk * MP + sr];
         const int i0 = __float_as_int(wv.z), i1 = __float_as_int(wv.w);
         if (i0 != qf0 || i1 != qf1) {
           qf0 = i0, qf1 = i1;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const bool in = 4 * tq + i < p.M;
-            qa0[i] = in ? __ldg(ab + (size_t)i0 * p.M + 4 * tq + i) : 0.f;
-            qa1[i] = in ? __ldg(ab + (size_t)i1 * p.M + 4 * tq + i) : 0.f;
+          for (int i = 0; i < TPL; ++i) {
+            const bool in = TPL * sg + i < p.M;
+            qa0[i] = in ? -__ldg(ab + (size_t)i0 * p.M + TPL * sg + i) : 0.f;
+            qa1[i] = in ? -__ldg(ab + (size_t)i1 * p.M + TPL * sg + i) : 0.f;
           }
         }
-        float4 v;
-        v.x = -__fmaf_rn(wv.x, qa0[0], __fmul_rn(wv.y, qa1[0]));
-        v.y = -__fmaf_rn(wv.x, qa0[1], __fmul_rn(wv.y, qa1[1]));
-        v.z = -__fmaf_rn(wv.x, qa0[2], __fmul_rn(wv.y, qa1[2]));
-        v.w = -__fmaf_rn(wv.x, qa0[3], __fmul_rn(wv.y, qa1[3]));
-        *reinterpret_cast<float4*>(ctile + k * TSTR + sr * MP + 4 * tq) = v;
+        float* dst = ctile + sk * TSTR + sr * MP + TPL * sg;
+#pragma unroll
+        for (int i = 0; i < TPL; i += 2) {
+          if (TPL * sg + i < MP) {  // -(l0*a0 + l1*a1) == fma(l0, -a0, l1*(-a1)): negation is exact
+            float2 v;
+            v.x = __fmaf_rn(wv.x, qa0[i], __fmul_rn(wv.y, qa1[i]));
+            v.y = __fmaf_rn(wv.x, qa0[i + 1], __fmul_rn(wv.y, qa1[i + 1]));
+            *reinterpret_cast<float2*>(dst + i) = v;
+          }
+        }
       }
     }
     __syncwarp();
@@ -190,34 +224,34 @@ __global__ void __launch_bounds__(kRespThreads, (MP <= 24 ? 2 : 1)) ss_response_
 #pragma unroll
     for (int s = 0; s < MP; ++s) {
       const float e = mye[s];
-      float c[MP];
+      float c[4 * NQ];
 #pragma unroll
-      for (int i4 = 0; i4 < MP / 4; ++i4) {
+      for (int i4 = 0; i4 < NQ; ++i4) {
         const float4 v = *reinterpret_cast<const float4*>(myc + s * MP + 4 * i4);
         c[4 * i4] = v.x, c[4 * i4 + 1] = v.y, c[4 * i4 + 2] = v.z, c[4 * i4 + 3] = v.w;
       }
       if (FORM == 0) {
-        // oldest tap first (lag L = MP - j pairs with coefficient c[L-1]); the four columns'
-        // chains are interleaved tap by tap so the FMA pipe always has 4 independent ops
-        float acc[kNC];
+        // oldest tap first (lag L pairs coefficient c[L-1] with the output L steps back); the NC
+        // columns' chains are interleaved tap by tap so the FMA pipe always has NC independent ops
+        float acc[NC];
 #pragma unroll
-        for (int cc = 0; cc < kNC; ++cc) acc[cc] = zsr[cc] ? e : 0.f;
+        for (int cc = 0; cc < NC; ++cc) acc[cc] = zsr[cc] ? e : 0.f;
 #pragma unroll
-        for (int j = 0; j < MP; ++j)
+        for (int L = MT; L >= 1; --L)
 #pragma unroll
-          for (int cc = 0; cc < kNC; ++cc) acc[cc] = __fmaf_rn(c[MP - 1 - j], st[cc][(s + j) % MP], acc[cc]);
+          for (int cc = 0; cc < NC; ++cc) acc[cc] = __fmaf_rn(c[L - 1], st[cc][(s - L + 2 * MP) % MP], acc[cc]);
 #pragma unroll
-        for (int cc = 0; cc < kNC; ++cc) st[cc][s] = acc[cc];
+        for (int cc = 0; cc < NC; ++cc) st[cc][s] = acc[cc];
       } else {
-        float u[kNC];
+        float u[NC];
 #pragma unroll
-        for (int cc = 0; cc < kNC; ++cc) u[cc] = (zsr[cc] ? e : 0.f) + st[cc][s];
+        for (int cc = 0; cc < NC; ++cc) u[cc] = (zsr[cc] ? e : 0.f) + st[cc][s];
 #pragma unroll
-        for (int k = 0; k < MP - 1; ++k)
+        for (int k = 0; k < MT - 1; ++k)
 #pragma unroll
-          for (int cc = 0; cc < kNC; ++cc) st[cc][(s + 1 + k) % MP] = __fmaf_rn(c[k], u[cc], st[cc][(s + 1 + k) % MP]);
+          for (int cc = 0; cc < NC; ++cc) st[cc][(s + 1 + k) % MP] = __fmaf_rn(c[k], u[cc], st[cc][(s + 1 + k) % MP]);
 #pragma unroll
-        for (int cc = 0; cc < kNC; ++cc) st[cc][s] = __fmul_rn(c[MP - 1], u[cc]);
+        for (int cc = 0; cc < NC; ++cc) st[cc][(s + MT) % MP] = __fmul_rn(c[MT - 1], u[cc]);  // slot consumed MP-MT steps ago (or just now)
       }
     }
   }
@@ -225,16 +259,17 @@ __global__ void __launch_bounds__(kRespThreads, (MP <= 24 ? 2 : 1)) ss_response_
   if (chunk_on) {
     float* wb = p.W + ((size_t)b * nresp + pi) * ((MP + 1) * MP);
 #pragma unroll
-    for (int cc = 0; cc < kNC; ++cc) {
-      const int col = kNC * li + cc;
+    for (int cc = 0; cc < NC; ++cc) {
+      const int col = NC * li + cc;
       if (col < p.M || (col == p.M && inb)) {
 #pragma unroll
         for (int k4 = 0; k4 < MP / 4; ++k4) {
           float4 v;
           if (FORM == 0) {
             v = make_float4(st[cc][MP - 1 - 4 * k4], st[cc][MP - 2 - 4 * k4], st[cc][MP - 3 - 4 * k4], st[cc][MP - 4 - 4 * k4]);
-          } else {
-            v = make_float4(st[cc][4 * k4], st[cc][4 * k4 + 1], st[cc][4 * k4 + 2], st[cc][4 * k4 + 3]);
+          } else {  // slots >= MT hold sums that were already consumed: those components are zero
+            v = make_float4(4 * k4 < MT ? st[cc][4 * k4] : 0.f, 4 * k4 + 1 < MT ? st[cc][4 * k4 + 1] : 0.f,
+                            4 * k4 + 2 < MT ? st[cc][4 * k4 + 2] : 0.f, 4 * k4 + 3 < MT ? st[cc][4 * k4 + 3] : 0.f);
           }
           *reinterpret_cast<float4*>(wb + col * MP + 4 * k4) = v;
         }
@@ -249,7 +284,7 @@ __global__ void __launch_bounds__(kRespThreads, (MP <= 24 ? 2 : 1)) ss_response_
 // Each chunk's block ([Phi | z], and in refine mode the E_p and S_{p+1} rows) streams
 // through a ring of shared-memory stages filled by the TMA unit (1-D cp.async.bulk,
 // completion counted on an mbarrier per stage).
-constexpr int kStitchStages = 3;  // ring depth
+constexpr int kStitchStages = 12;  // ring depth: enough bytes in flight to cover the L2->smem latency of one CTA
 constexpr int kStitchGroup = 4;   // chunk blocks per stage (one mbarrier wait per group)
 
 template <int MP>
@@ -573,25 +608,36 @@ __global__ void __launch_bounds__(32) ss_solve_kernel(SsParams p, int round) {
   }
 }
 
+template <int MP, int MT, int FORM>
+int launch_response(const SsParams& p, cudaStream_t st) {
+  constexpr int NC = RespCfg<MP>::NC;
+  constexpr int LPC = (MT + 1 + NC - 1) / NC, CPW = 32 / LPC;
+  const int nresp = p.C - 1;
+  const int wps = ceil_div(nresp, CPW);
+  const size_t sm = (size_t)(CPW * (MP * MP + 4) + CPW * MP * 5) * sizeof(float);
+  static bool attr = false;
+  if (!attr && sm > 48 * 1024) {
+    GOLF_CUDA(cudaFuncSetAttribute(ss_response_kernel<MP, MT, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    attr = true;
+  }
+  ss_response_kernel<MP, MT, FORM><<<p.B * wps, 32, sm, st>>>(p);
+  GOLF_CHECK_LAUNCH();
+  return GOLF_OK;
+}
+
 // passes: bit0 responses (without z when p.in is null), bit1 stitch, bit2 solve, bit3 refinement
 // (stitch + solve again), bit4 zero-state responses by a solve from rest (before the stitch)
 template <int MP, int FORM>
 int launch_mp(const SsParams& p, bool generic, int passes, cudaStream_t st) {
   const int nresp = p.C - 1;
   if (nresp > 0 && (passes & 1)) {
-    const int warps = kRespThreads / 32;
-    const int LPC = ceil_div(p.M + 1, kNC);
-    const int CPW = std::min(32 / LPC, 128 / MP);  // rows staged per tile: CPW * MP <= 128
-    const int wps = ceil_div(nresp, CPW);
-    if (CPW * MP > 128 || CPW * (MP / 4) > 32) return GOLF_ERR_UNSUPPORTED;
-    const size_t sm = (size_t)warps * (CPW * (MP * MP + 4) + CPW * MP * 5) * sizeof(float);
-    static size_t sm_allowed = 48 * 1024;
-    if (sm > sm_allowed) {
-      GOLF_CUDA(cudaFuncSetAttribute(ss_response_kernel<MP, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      sm_allowed = sm;
-    }
-    ss_response_kernel<MP, FORM><<<ceil_div(p.B * wps, warps), warps * 32, sm, st>>>(p, LPC, CPW);
-    GOLF_CHECK_LAUNCH();
+    constexpr int MTS = MP >= 8 ? MP - 2 : MP;  // short-tap variant for M <= MP - 2
+    int rc;
+    if (p.M <= MTS)
+      rc = launch_response<MP, MTS, FORM>(p, st);
+    else
+      rc = launch_response<MP, MP, FORM>(p, st);
+    if (rc) return rc;
   }
   const size_t sm_stitch =
       ((size_t)kStitchStages * kStitchGroup * ((MP + 1) * MP + 2 * MP) + 2 * MP) * sizeof(float) + kStitchStages * 8 + 128;

@@ -91,7 +91,7 @@ class PipelinedSynth:
 
         pipe = PipelinedSynth(decoder, example_params, depth=3)
         t = pipe.submit(out_host, **host_params)     # enqueue only, returns a ticket
-        pipe.wait(t)                                 # out_host[:, :pipe.out_len] is valid
+        pipe.wait(t)                                 # out_host ([B, pipe.out_len], pinned, contiguous) is valid
     """
 
     def __init__(self, decoder: torch.nn.Module, example_params: Dict[str, Any], depth: int = 3):
@@ -135,7 +135,9 @@ class PipelinedSynth:
             self._ran[k].record(self.s_run)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self._ran[k])
-            out_host[:, : y.shape[1]].copy_(y, non_blocking=True)
+            # out_host must be a CONTIGUOUS pinned [B, out_len] tensor: a strided host destination makes
+            # torch stage the copy through pageable memory and block
+            out_host.copy_(y, non_blocking=True)
             self._read[k] = torch.cuda.Event()
             self._read[k].record(self.s_out)
         self._n += 1

@@ -15,11 +15,14 @@ from .filters import LTVMinimumPhaseFilterPrecise, LTVZeroPhaseFIRFilter
 from .noise import StandardNormalNoise
 from .synth import IndexedGlottalFlowTable
 
-# Inference runs the three independent branches of the decoder on separate CUDA streams
-# (forked from and joined back into the caller's stream; captured as parallel branches by a CUDA
-# graph): the oscillator, the noise draw + FIR design, and the end filter's chunk transition
-# matrices (which need only the coefficients).  "off" keeps everything on one stream.
+# Inference scheduling.  At the reference's batch sizes most kernels of the decoder are latency
+# bound (serial recurrences, short grids), so one stream leaves the GPU mostly idle.  Utterances are
+# independent, so the batch is cut into SPLIT groups that run the whole decoder on their own CUDA
+# streams (forked from and joined back into the caller's stream; a CUDA graph captures them as
+# parallel branches): one group's serial stitch/solve overlaps another group's throughput kernels.
+# Within a group the noise draw + FIR design run beside the oscillator.  "off" = one stream.
 CONCURRENT = "auto"
+SPLIT = 1
 _SIDE_STREAMS = {}
 
 
@@ -71,34 +74,44 @@ class SourceFilterSynth(Synth):
                 and hop_of(noise_filter_params[0]) == hop_of(end_filter_params[0]))
 
     def _forward_concurrent(self, phase, harm_oscillator_params, noise_filter_params, end_filter_params):
-        """Same arithmetic as the sequential path (bit-identical output for the same noise); only
-        the launch order / stream assignment differs:
-
-            main : oscillator ------------------------------+-> noise FIR (+harm) -+-> z, stitch, solve -> room
-            s_fir: randn, exp, irfft (FIR design) ----------+                      |
-            s_phi: end-filter chunk transition matrices  ---------------------------+
-        """
-        log_mag = noise_filter_params[0]
-        gain, a = end_filter_params
+        """Same arithmetic per utterance as the sequential path; the noise generator is called once
+        per group, so the draw differs from a single full-batch randn (same distribution)."""
         dev = plain(phase).device
+        B = plain(phase).shape[0]
+        n = max(1, min(int(SPLIT), B))
         main = torch.cuda.current_stream(dev)
-        s_phi, s_fir = _side_streams(dev, 2)
-        t_osc = self.harm_oscillator.out_length(phase)
-        n_taps = 2 * (plain(log_mag).shape[-1] - 1)
+        streams = _side_streams(dev, 2 * n)
+        bounds = [(B * i) // n for i in range(n + 1)]
+        cut = lambda x, lo, hi: like(x, plain(x)[lo:hi], hop_of(x))
+        outs = []
+        for i in range(n):
+            lo, hi = bounds[i], bounds[i + 1]
+            s_run, s_fir = streams[2 * i], streams[2 * i + 1]
+            s_run.wait_stream(main)
+            with torch.cuda.stream(s_run):
+                y = self._forward_group(s_run, s_fir, cut(phase, lo, hi), tuple(cut(x, lo, hi) for x in harm_oscillator_params),
+                                        cut(noise_filter_params[0], lo, hi), tuple(cut(x, lo, hi) for x in end_filter_params))
+                plain(y).record_stream(main)
+            outs.append(y)
+        for i in range(n):
+            main.wait_stream(streams[2 * i])
+        if n == 1:
+            return outs[0]
+        return like(outs[0], torch.cat([plain(o) for o in outs], 0), hop_of(outs[0]))
+
+    def _forward_group(self, s_run, s_fir, phase, harm_oscillator_params, log_mag, end_filter_params):
+        """one group on its own stream:  s_run: oscillator --+-> noise FIR (+harm) -> end filter -> room
+                                         s_fir: randn, exp, irfft (FIR design) ---+"""
+        dev = plain(phase).device
         hop = hop_of(log_mag)
-        t_src = self.noise_filter.out_length(t_osc, plain(log_mag).shape[1], n_taps, hop)
-        s_phi.wait_stream(main)
-        s_fir.wait_stream(main)
-        with torch.cuda.stream(s_phi):
-            ws = self.end_filter.responses(t_src, gain, a)
-            ws.record_stream(main)
+        t_osc = self.harm_oscillator.out_length(phase)
+        s_fir.wait_stream(s_run)
         with torch.cuda.stream(s_fir):
             noise = torch.randn(plain(phase).shape[0], t_osc, dtype=torch.float32, device=dev)
             raw = self.noise_filter.raw_kernels(log_mag)
-            noise.record_stream(main)
-            raw.record_stream(main)
+            noise.record_stream(s_run)
+            raw.record_stream(s_run)
         harm = self.harm_oscillator(phase, *harm_oscillator_params)
-        main.wait_stream(s_fir)
+        s_run.wait_stream(s_fir)
         src = self.noise_filter.apply_raw(like(harm, noise, 1), raw, hop, add=harm)
-        main.wait_stream(s_phi)
-        return self.room_filter(self.end_filter.finish(src, gain, a, ws))
+        return self.room_filter(self.end_filter(src, *end_filter_params))

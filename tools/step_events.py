@@ -26,12 +26,17 @@ def t(fn, n=n):
         e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
 
-for mode in ("off", "auto"):
-    sf.CONCURRENT = mode
+for mode, split in (("off", 1), ("auto", 1), ("auto", 2), ("auto", 4), ("auto", 8), ("auto", 16)):
+    sf.CONCURRENT, sf.SPLIT = mode, split
     with torch.no_grad():
         gs = [GraphedSynth(dec, P(s)) for s in sets]
-    print(f"graph replay, CONCURRENT={mode}: {t(lambda i: gs[i % len(gs)].replay()):8.1f} us  ({gs[0].kernels_captured} kernels)")
-sf.CONCURRENT = "auto"
+    print(f"graph replay, CONCURRENT={mode} SPLIT={split}: {t(lambda i: gs[i % len(gs)].replay()):8.1f} us  ({gs[0].kernels_captured} kernels)")
+    del gs
+sf.CONCURRENT, sf.SPLIT = "auto", 1
+# raw PCIe: pinned host <-> device copies of the bench's per-step payloads
+hp = torch.empty(13289088 // 4).pin_memory(); dp = torch.empty_like(hp, device=dev)
+ho = torch.empty(6113280 // 4).pin_memory(); do = torch.empty_like(ho, device=dev)
+print(f"H2D 13.3 MB pinned: {t(lambda i: dp.copy_(hp, non_blocking=True)):8.1f} us   D2H 6.1 MB pinned: {t(lambda i: ho.copy_(do, non_blocking=True)):8.1f} us")
 s = sets[0]
 with torch.no_grad():
     harm = dec.harm_oscillator(A(s, "phase", 1), A(s, "w", 2400))
