@@ -22,6 +22,7 @@ _SIGS = {
     "golf_lpc_ss_workspace_bytes": (c_size_t, [c_int] * 5),
     "golf_lpc_ss_set_refine_tolerance": (None, [c_float]),
     "golf_lpc_ss_get_refine_tolerance": (c_float, []),
+    "golf_lpc_ss_set_solver": (None, [c_int]),
     "golf_lpc_ss_fwd": (c_int, [P, c_int64, P, P, P, P] + [c_int] * 6 + [P, c_size_t, P]),
     "golf_lpc_ss_fwd_passes": (c_int, [P, c_int64, P, P, P, P] + [c_int] * 6 + [P, c_size_t, c_int, P]),
     "golf_lpc_ss_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
@@ -36,6 +37,7 @@ _SIGS = {
     "golf_room_fir_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P]),
     "golf_room_fir_bwd": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     "golf_glottal_osc_workspace_bytes": (c_size_t, [c_int] * 6),
+    "golf_glottal_osc_set_variant": (None, [c_int]),
     "golf_glottal_osc_fwd": (c_int, [P, P, P, P, P] + [c_int] * 11 + [P, c_size_t, P]),
     "golf_glottal_osc_bwd_w": (c_int, [P, P, P, P, P, P] + [c_int] * 11 + [P, c_size_t, P]),
     "golf_wavetable_read_fwd": (c_int, [P, P, P] + [c_int] * 5 + [P]),

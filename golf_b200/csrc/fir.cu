@@ -25,16 +25,16 @@ __global__ void __launch_bounds__(256) noise_fir_kernel(const float* __restrict_
                                                         float* __restrict__ y, int T, int F, int K, int hop, int n_blocks,
                                                         int K12, int xs_len) {
   extern __shared__ __align__(16) float smem[];
-  float* xs = smem;
-  float* ks = smem + xs_len;
+  float* xs = smem;                      // input strip, fir_sw() layout
+  float* ks = smem + fir_sw(xs_len) + 4;
   const int k = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int p = (K - 1) / 2;
   const float* exb = ex + (size_t)b * ex_stride;
   const float* kb = kernel + ((size_t)b * F + k) * K;
-  const int start = k * hop - p;  // signal position of xs[0]
+  const int start = k * hop - p;  // signal position of logical xs[0]
   for (int i = tid; i < xs_len; i += blockDim.x) {
     const int pos = start + i;
-    xs[i] = (pos >= 0 && pos < T && i < hop + K - 1) ? exb[pos] : 0.f;
+    xs[fir_sw(i)] = (pos >= 0 && pos < T && i < hop + K - 1) ? exb[pos] : 0.f;
   }
   // taps: either final, or (window given) the raw irfft output: fftshift + windowing fused here
   for (int i = tid; i < K12; i += blockDim.x) {
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) noise_fir_kernel(const float* __restrict_
   float acc[kR];
 #pragma unroll
   for (int i = 0; i < kR; ++i) acc[i] = 0.f;
-  fir_tile8(xs + r0, ks, K12, acc);
+  fir_tile8_sw(xs, r0, ks, K12, acc);
   float* yb = y + (size_t)b * n_blocks * hop + (size_t)k * hop;
   const float* ab = add ? add + (size_t)b * add_stride + (size_t)k * hop : nullptr;
 #pragma unroll
@@ -63,8 +63,8 @@ constexpr int kRoomTile = 1024;
 __global__ void __launch_bounds__(128) room_fir_kernel(const float* __restrict__ x, const float* __restrict__ k,
                                                        float* __restrict__ out, int T, int n, int K12, int xs_len) {
   extern __shared__ __align__(16) float smem[];
-  float* xs = smem;
-  float* ks = smem + xs_len;
+  float* xs = smem;                      // input strip, fir_sw() layout
+  float* ks = smem + fir_sw(xs_len) + 4;
   const int b = blockIdx.y, tid = threadIdx.x;
   const int t0 = blockIdx.x * kRoomTile;
   const float* xb = x + (size_t)b * T;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) room_fir_kernel(const float* __restrict__
     const int pos = t0 - n + i;
     // the reference pads x[:-1]: the last sample never feeds the taps (it is never needed:
     // tap j < n reaches at most t-1 <= T-2), only the direct path
-    xs[i] = (pos >= 0 && pos < T) ? xb[pos] : 0.f;
+    xs[fir_sw(i)] = (pos >= 0 && pos < T) ? xb[pos] : 0.f;
   }
   for (int i = tid; i < K12; i += blockDim.x) ks[i] = i < n ? k[i] : (i == n ? 1.f : 0.f);
   __syncthreads();
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128) room_fir_kernel(const float* __restrict__
   float acc[kR];
 #pragma unroll
   for (int i = 0; i < kR; ++i) acc[i] = 0.f;
-  fir_tile8(xs + r0, ks, K12, acc);
+  fir_tile8_sw(xs, r0, ks, K12, acc);
   float* ob = out + (size_t)b * T;
 #pragma unroll
   for (int i = 0; i < kR; ++i)
@@ -272,7 +272,7 @@ GOLF_API int golf_noise_fir_fwd(const float* ex, int64_t ex_stride, const float*
   const int K12 = ceil_div(K, 12) * 12;
   const int threads = 32 * ceil_div(hop, 32 * kR);
   const int xs_len = (int)align_up((size_t)threads * kR + K12 + 24, 4);
-  const size_t sm = (size_t)(xs_len + K12) * sizeof(float);
+  const size_t sm = (size_t)(fir_sw(xs_len) + 4 + K12) * sizeof(float);
   if (sm > 48 * 1024) return GOLF_ERR_UNSUPPORTED;
   dim3 grid(n_blocks, B);
   if (window && (K & 1)) return GOLF_ERR_UNSUPPORTED;  // fused fftshift assumes an even tap count (2*(n_mag-1))
@@ -286,7 +286,7 @@ GOLF_API int golf_room_fir_fwd(const float* x, const float* k, float* out, int B
   if (!x || !k || !out || B <= 0 || T <= 0 || n <= 0) return GOLF_ERR_INVALID;
   const int K12 = ceil_div(n + 1, 12) * 12;
   const int xs_len = (int)align_up((size_t)kRoomTile + K12 + 24, 4);
-  const size_t sm = (size_t)(xs_len + K12) * sizeof(float);
+  const size_t sm = (size_t)(fir_sw(xs_len) + 4 + K12) * sizeof(float);
   if (sm > 48 * 1024) return GOLF_ERR_UNSUPPORTED;
   dim3 grid(ceil_div(T, kRoomTile), B);
   room_fir_kernel<<<grid, 128, sm, (cudaStream_t)stream>>>(x, k, out, T, n, K12, xs_len);

@@ -67,6 +67,7 @@ __global__ void ss_dzi_kernel(const float* __restrict__ u, const float* __restri
 // 0 refines always; the default skips it where the stitched states already agree with the
 // solve to a few float32 ulps (well-conditioned filters) -- see DESIGN.md 3.1.
 static float g_refine_tol = 1e-4f;
+int g_solve_systolic = 1;
 
 struct SsPlan {
   int B, MP, Lc, C, HB;
@@ -150,6 +151,7 @@ using namespace golf;
 
 GOLF_API void golf_lpc_ss_set_refine_tolerance(float tol) { g_refine_tol = tol >= 0.f ? tol : 0.f; }
 GOLF_API float golf_lpc_ss_get_refine_tolerance(void) { return g_refine_tol; }
+GOLF_API void golf_lpc_ss_set_solver(int systolic) { g_solve_systolic = systolic ? 1 : 0; }
 
 GOLF_API size_t golf_lpc_ss_workspace_bytes(int B, int L, int M, int hop, int chunk) {
   SsPlan pl;

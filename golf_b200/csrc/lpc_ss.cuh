@@ -42,6 +42,8 @@
 
 namespace golf {
 
+extern int g_solve_systolic;  // 1 (default): 4-lanes-per-chunk solve where it applies; 0: lane-per-chunk
+
 struct SsParams {
   const float* in;     // FORM0: ex [B, in_stride]; FORM1: gy [B, L]
   int64_t in_stride;
@@ -284,10 +286,14 @@ __global__ void __launch_bounds__(32, (MP <= 24 ? 8 : 4)) ss_response_kernel(SsP
 // Each chunk's block ([Phi | z], and in refine mode the E_p and S_{p+1} rows) streams
 // through a ring of shared-memory stages filled by the TMA unit (1-D cp.async.bulk,
 // completion counted on an mbarrier per stage).
-constexpr int kStitchStages = 12;  // ring depth: enough bytes in flight to cover the L2->smem latency of one CTA
+constexpr int kStitchStages = 4;  // ring depth (the kernel is bound by its dependent chain, not by the copies)
 constexpr int kStitchGroup = 4;   // chunk blocks per stage (one mbarrier wait per group)
 
-template <int MP>
+// MC: number of Phi columns when known at compile time (M == MC), 0: runtime p.M.
+// The loop over a group is software-pipelined by hand: the Phi row of the NEXT chunk is loaded in the
+// latency shadow of the state broadcast of the current one, so a step costs the dependent chain
+// (state LDS -> 6-deep FMA chains -> STS -> __syncwarp) plus ~60 issue slots.
+template <int MP, int MC>
 __global__ void __launch_bounds__(32) ss_stitch_kernel(SsParams p, int refine) {
   constexpr int Q = (MP + 31) / 32;
   constexpr int SLOT = (MP + 1) * MP;           // floats per chunk block
@@ -300,6 +306,7 @@ __global__ void __launch_bounds__(32) ss_stitch_kernel(SsParams p, int refine) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(svec + 2 * MP);
   const int nresp = p.C - 1;
   const int ngroups = (nresp + kStitchGroup - 1) / kStitchGroup;
+  const int ncol = MC ? MC : p.M;
   const float* wb = p.W + (size_t)b * nresp * SLOT;
   float* sb = p.S + (size_t)b * p.C * MP;
   const float* eb = p.E + (size_t)b * p.C * MP;
@@ -343,6 +350,25 @@ __global__ void __launch_bounds__(32) ss_stitch_kernel(SsParams p, int refine) {
   if (lane == 0)
     for (int g = 0; g < kStitchStages && g < ngroups; ++g) issue(g);
 
+  // row `k` of chunk block `blk`: Phi[k][0..ncol) and the additive term (z, or E - S when refining)
+  float phi[Q][MP], base[Q], old[Q];
+  auto load_row = [&](const float* grp, int c, float (&ph)[Q][MP], float (&bs)[Q], float (&od)[Q]) {
+    const float* blk = grp + c * SLOT;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int k = min(lane + 32 * q, MP - 1);
+#pragma unroll
+      for (int j = 0; j < MP; ++j) ph[q][j] = j < ncol ? blk[j * MP + k] : 0.f;
+      if (refine) {
+        od[q] = grp[GW + kStitchGroup * MP + c * MP + k];
+        bs[q] = grp[GW + c * MP + k] - od[q];
+      } else {
+        od[q] = 0.f;
+        bs[q] = blk[p.M * MP + k];
+      }
+    }
+  };
+
   int buf = 0;
 #pragma unroll 1
   for (int g = 0; g < ngroups; ++g) {
@@ -350,46 +376,45 @@ __global__ void __launch_bounds__(32) ss_stitch_kernel(SsParams p, int refine) {
     mbar_wait(&bars[stg], (uint32_t)((g / kStitchStages) & 1));
     const float* grp = ring + stg * STAGE;
     const int n = min(kStitchGroup, nresp - g * kStitchGroup);
-#pragma unroll 1
-    for (int c = 0; c < n; ++c) {
-      const int pi = g * kStitchGroup + c;
-      const float* blk = grp + c * SLOT;
-      // everything that does not depend on the running state first ...
-      float phi[Q][MP], base[Q], old[Q];
+    load_row(grp, 0, phi, base, old);
 #pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const int k = min(lane + 32 * q, MP - 1);
+    for (int c = 0; c < kStitchGroup; ++c) {
+      if (c < n) {
+        const int pi = g * kStitchGroup + c;
+        // dependent part first in program order: broadcast-read the running state ...
+        float sv[MP];
 #pragma unroll
-        for (int j = 0; j < MP; ++j) phi[q][j] = j < p.M ? blk[j * MP + k] : 0.f;
-        if (refine) {
-          old[q] = grp[GW + kStitchGroup * MP + c * MP + k];
-          base[q] = grp[GW + c * MP + k] - old[q];
-        } else {
-          old[q] = 0.f;
-          base[q] = blk[p.M * MP + k];
+        for (int j4 = 0; j4 < MP / 4; ++j4) {
+          const float4 v = *reinterpret_cast<const float4*>(svec + buf * MP + 4 * j4);
+          sv[4 * j4] = v.x, sv[4 * j4 + 1] = v.y, sv[4 * j4 + 2] = v.z, sv[4 * j4 + 3] = v.w;
+        }
+        // ... and, while those loads are in flight, fetch the next chunk's row
+        float nphi[Q][MP], nbase[Q], nold[Q];
+        if (c + 1 < kStitchGroup && c + 1 < n) load_row(grp, c + 1, nphi, nbase, nold);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const int k = lane + 32 * q;
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < MP; ++j)
+            if (MC == 0 || j < MC) acc[j & 3] = __fmaf_rn(phi[q][j], sv[j], acc[j & 3]);
+          const float nxt = base[q] + ((acc[0] + acc[1]) + (acc[2] + acc[3]));
+          if (k < MP) {
+            svec[(buf ^ 1) * MP + k] = nxt;
+            sb[(size_t)(pi + 1) * MP + k] = old[q] + nxt;
+          }
+        }
+        buf ^= 1;
+        __syncwarp();
+        if (c + 1 < kStitchGroup && c + 1 < n) {
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {
+#pragma unroll
+            for (int j = 0; j < MP; ++j) phi[q][j] = nphi[q][j];
+            base[q] = nbase[q], old[q] = nold[q];
+          }
         }
       }
-      // ... then the dependent part: broadcast-read the state, 4 FMA chains per component
-      float sv[MP];
-#pragma unroll
-      for (int j4 = 0; j4 < MP / 4; ++j4) {
-        const float4 v = *reinterpret_cast<const float4*>(svec + buf * MP + 4 * j4);
-        sv[4 * j4] = v.x, sv[4 * j4 + 1] = v.y, sv[4 * j4 + 2] = v.z, sv[4 * j4 + 3] = v.w;
-      }
-#pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const int k = lane + 32 * q;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < MP; ++j) acc[j & 3] = __fmaf_rn(phi[q][j], sv[j], acc[j & 3]);
-        const float nxt = base[q] + ((acc[0] + acc[1]) + (acc[2] + acc[3]));
-        if (k < MP) {
-          svec[(buf ^ 1) * MP + k] = nxt;
-          sb[(size_t)(pi + 1) * MP + k] = old[q] + nxt;
-        }
-      }
-      buf ^= 1;
-      __syncwarp();
     }
     // the whole warp has consumed this stage: refill it with the group kStitchStages ahead
     if (lane == 0 && g + kStitchStages < ngroups) issue(g + kStitchStages);
@@ -608,6 +633,222 @@ __global__ void __launch_bounds__(32) ss_solve_kernel(SsParams p, int round) {
   }
 }
 
+// ------------------------------------------------------- pass 3, systolic form ----
+// The lane-per-chunk solve above is bound by ONE warp's in-order issue: ~50 instructions per
+// sample, 240 dependent samples.  Here a chunk is solved by LB = 4 neighbouring lanes instead:
+// lane j owns the taps of lags TB*j+1 .. TB*j+TB (TB = MP/4) and their interpolation, so a sample
+// costs every lane ~TB FMAs + TB coefficient lerps.  Only lane 0's block touches the newest
+// outputs; the older blocks can be summed ahead of time, so lane j runs D*j samples AHEAD of lane 0
+// and the partial sums ripple down (lane 3 -> 2 -> 1 -> 0, one __shfl_down per sample, consumed D
+// iterations later) while the outputs ripple up through a delay line (lane j+1's newest history
+// element is lane j's lag-(TB-D) element, one __shfl_up per sample).  Both shuffles have D
+// iterations of slack, so the only serial dependency per sample is lane 0's last FMA.
+//   iteration n (n = -PRE .. Lc-1, PRE = D*(LB-1)), lane j, local time tl = n + D*j:
+//     ring_j[k] = y[n - (TB-D)*j - (k+1)],  k < TB          (y[m < 0] = initial state)
+//     out = q_in + (j == 0 ? e[n] : 0) + sum_k c[tl][TB*j + k] * ring_j[k]       oldest k first
+//     lane 0: out = y[n];  lane j > 0: out = partial sum over lags > TB*j for time tl
+// Coefficient frames are (re)loaded when a lane's local time enters a new frame; the first sample
+// of a frame (where ATen's floor() may land one frame low) uses coefficients computed with the
+// exact reference arithmetic at load time.  FORM 0, frame-aligned chunks only.
+template <int MP>
+__global__ void __launch_bounds__(32) ss_solve_sys_kernel(SsParams p, int round) {
+  constexpr int LB = 4, TB = MP / LB, D = 2, HOPD = TB - D, GPW = 32 / LB, PRE = D * (LB - 1);
+  constexpr int NLD = (GPW * MP + 31) / 32;  // staged elements per lane per tile
+  static_assert(MP % LB == 0 && HOPD >= 1 && TB % 2 == 0, "systolic solve geometry");
+  __shared__ __align__(16) float xin[2][GPW * MP];
+  __shared__ __align__(16) float yout[GPW * MP];
+  const int lane = threadIdx.x, grp = lane / LB, j = lane % LB;
+  const int G = (p.C + GPW - 1) / GPW;
+  const int b = blockIdx.x / G, g = blockIdx.x % G;
+  if (round == 1) {  // refinement round: only for the sequences that need it
+    const float mism = __uint_as_float(p.flags[2 * b]), smax = __uint_as_float(p.flags[2 * b + 1]);
+    if (!(mism > p.refine_tol * smax)) return;
+  }
+  const int pi = g * GPW + grp;
+  const bool active = pi < p.C;
+  const int pic = active ? pi : p.C - 1;
+  const float* __restrict__ ab = p.a + (size_t)b * p.F * p.M;
+  const float* __restrict__ gb = p.gain ? p.gain + (size_t)b * p.F : nullptr;
+  const float* __restrict__ inb = p.in + (size_t)b * p.in_stride;
+  float* __restrict__ outb = p.out ? p.out + (size_t)b * p.L : nullptr;
+  const int tap0 = TB * j;  // this lane's taps: tap0 .. tap0+TB-1 (tap i multiplies y[t-1-i])
+
+  // history ring and the initial-state values lane 0 pushes during the PRE warm-up iterations
+  float ring[TB], pre[PRE];
+  {
+    const float* s0 = p.S + ((size_t)b * p.C + pic) * MP;
+    const bool ld = active && round >= 0;
+#pragma unroll
+    for (int k = 0; k < TB; ++k) ring[k] = ld ? s0[PRE + HOPD * j + k] : 0.f;
+#pragma unroll
+    for (int i = 0; i < PRE; ++i) pre[i] = ld ? s0[PRE - 1 - i] : 0.f;
+  }
+  // coefficient frames (negated) of this lane's taps, gain pair, and the exact set for the first
+  // sample of the frame
+  float na0[TB], na1[TB], cg[TB];
+  float g0 = 1.f, g1 = 1.f, gg = 1.f, kregf = 0.f;
+  int tnext = 0;           // local time at which this lane (re)loads its frames
+  int tl = -PRE + D * j;   // local time of this lane's output in the coming iteration
+  const int base_t = pic * p.Lc;
+#pragma unroll
+  for (int i = 0; i < TB; ++i) na0[i] = na1[i] = cg[i] = 0.f;
+  bool first = false;      // the coming iteration is the first sample of a freshly loaded frame
+  auto reload = [&]() {
+    const int t = base_t + tl;
+    if (t < p.L) {
+      const int kreg = min(t / p.hop, p.F - 1), k1 = min(kreg + 1, p.F - 1);
+      const Lerp w = lerp_at(t, p.scale, p.F);
+      const float* r0 = ab + (size_t)kreg * p.M + tap0;
+      const float* r1 = ab + (size_t)k1 * p.M + tap0;
+      const float* e0 = ab + (size_t)w.i0 * p.M + tap0;
+      const float* e1 = ab + (size_t)w.i1 * p.M + tap0;
+#pragma unroll
+      for (int i = 0; i < TB; ++i) {
+        const bool in = tap0 + i < p.M;
+        na0[i] = in ? -__ldg(r0 + i) : 0.f;
+        na1[i] = in ? -__ldg(r1 + i) : 0.f;
+        cg[i] = in ? -lerp_apply(w, __ldg(e0 + i), __ldg(e1 + i)) : 0.f;
+      }
+      if (gb) {
+        g0 = __ldg(gb + kreg), g1 = __ldg(gb + k1);
+        gg = lerp_apply(w, __ldg(gb + w.i0), __ldg(gb + w.i1));
+      }
+      kregf = (float)kreg;
+      first = true;
+    }
+    tnext = p.hop < p.Lc ? tnext + p.hop : 0x7fffffff;
+  };
+  float f0 = 0.f, f1 = 0.f;  // partial sums received from lane j+1, consumed D iterations later
+  float tf = (float)(base_t + tl);  // float(t), advanced by exact +1 (t < 2^24)
+
+  // one iteration; X = excitation sample of lane 0's time (unused by the other lanes)
+  auto step = [&](float x, bool push_out, float pre_v) -> float {
+    float c[TB], gv;
+    if (first) {  // (divergent at most once per frame and lane)
+#pragma unroll
+      for (int i = 0; i < TB; ++i) c[i] = cg[i];
+      gv = gg;
+      first = false;
+    } else {
+      const float src = __fmul_rn(p.scale, tf);
+      float l1 = __fsub_rn(src, kregf);
+      l1 = fminf(fmaxf(l1, 0.f), 1.f);
+      const float l0 = __fsub_rn(1.f, l1);
+      const float2 l0p = f2(l0, l0), l1p = f2(l1, l1);
+#pragma unroll
+      for (int i = 0; i < TB; i += 2) {
+        const float2 c2 = __ffma2_rn(l0p, f2(na0[i], na0[i + 1]), __fmul2_rn(l1p, f2(na1[i], na1[i + 1])));
+        c[i] = c2.x, c[i + 1] = c2.y;
+      }
+      gv = __fmaf_rn(l0, g0, __fmul_rn(l1, g1));
+    }
+    const float q_in = (j == LB - 1) ? 0.f : f0;
+    f0 = f1;
+    float acc = q_in + (j == 0 ? (gb ? __fmul_rn(x, gv) : x) : 0.f);
+#pragma unroll
+    for (int k = TB - 1; k >= 0; --k) acc = __fmaf_rn(c[k], ring[k], acc);
+    f1 = __shfl_down_sync(0xffffffffu, acc, 1);
+    const float up = __shfl_up_sync(0xffffffffu, ring[HOPD - 1], 1);
+    const float nv = (j == 0) ? (push_out ? acc : pre_v) : up;
+#pragma unroll
+    for (int k = TB - 1; k > 0; --k) ring[k] = ring[k - 1];
+    ring[0] = nv;
+    tf = __fadd_rn(tf, 1.f);
+    ++tl;
+    return acc;
+  };
+
+  // ---- stage tile 0 of the inputs
+  const int ntiles = p.Lc / MP;
+  float v[NLD];
+  auto fetch = [&](int tile) {
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+      const int idx = lane + 32 * i, r = idx / MP, sx = idx - r * MP;
+      const int prr = g * GPW + r;
+      const int t = prr * p.Lc + tile * MP + sx;
+      v[i] = (idx < GPW * MP && prr < p.C && t < p.L) ? __ldg(inb + t) : 0.f;
+    }
+  };
+  auto publish = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < GPW * MP) xin[buf][idx] = v[i];
+    }
+  };
+  fetch(0);
+  // ---- warm-up: the lanes ahead of lane 0 start their partial sums; lane 0 replays the initial state
+#pragma unroll
+  for (int i = 0; i < PRE; ++i) {
+    if (tl == tnext) reload();
+    step(0.f, false, pre[i]);
+  }
+  publish(0);
+  __syncwarp();
+#pragma unroll 1
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int buf = tile & 1;
+    if (tile + 1 < ntiles) fetch(tile + 1);
+    const float* xg = xin[buf] + grp * MP;
+#pragma unroll
+    for (int sx = 0; sx < MP; ++sx) {
+      // frame changes of lane j happen D*j iterations before lane 0's (which are tile aligned)
+      if ((sx == 0 || sx >= MP - PRE) && tl == tnext) reload();
+      const float y = step(xg[sx], true, 0.f);
+      if (j == 0) yout[grp * MP + sx] = y;
+    }
+    __syncwarp();
+    if (round >= 0) {  // write the tile back: GPW segments of MP contiguous samples
+#pragma unroll
+      for (int i = 0; i < NLD; ++i) {
+        const int idx = lane + 32 * i, r = idx / MP, sx = idx - r * MP;
+        const int prr = g * GPW + r;
+        const int t = prr * p.Lc + tile * MP + sx;
+        if (idx < GPW * MP && prr < p.C && t < p.L) outb[t] = yout[idx];
+      }
+    }
+    if (tile + 1 < ntiles) publish(buf ^ 1);
+    if (tile + 1 < ntiles) __syncwarp();
+  }
+  // ---- end state of each chunk = its last MP outputs (still in yout): component k = y[Lc-1-k]
+  if (round < 0) {  // zero-state response -> W[b][pi][col M][:]
+    if (active && pi < p.C - 1) {
+      float* z = p.W + ((size_t)b * (p.C - 1) + pi) * ((MP + 1) * MP) + p.M * MP;
+#pragma unroll
+      for (int k = 0; k < TB; ++k) z[TB * j + k] = yout[grp * MP + MP - 1 - (TB * j + k)];
+    }
+    return;
+  }
+  if (round == 0 && p.E) {
+    float mism = 0.f, smax = 0.f;
+    if (active) {
+      float* e0 = p.E + ((size_t)b * p.C + pi) * MP;
+      const float* s1 = p.S + ((size_t)b * p.C + min(pi + 1, p.C - 1)) * MP;
+#pragma unroll
+      for (int k = 0; k < TB; ++k) {
+        const int comp = TB * j + k;
+        const float ev = yout[grp * MP + MP - 1 - comp];
+        e0[comp] = ev;
+        if (pi + 1 < p.C && comp < p.M) {
+          const float sv = s1[comp];
+          mism = fmaxf(mism, fabsf(ev - sv));
+          smax = fmaxf(smax, fabsf(sv));
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      mism = fmaxf(mism, __shfl_xor_sync(0xffffffffu, mism, d));
+      smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, d));
+    }
+    if (lane == 0) {  // non-negative floats order like their bit patterns
+      atomicMax(p.flags + 2 * b, __float_as_uint(mism));
+      atomicMax(p.flags + 2 * b + 1, __float_as_uint(smax));
+    }
+  }
+}
+
 template <int MP, int MT, int FORM>
 int launch_response(const SsParams& p, cudaStream_t st) {
   constexpr int NC = RespCfg<MP>::NC;
@@ -641,33 +882,51 @@ int launch_mp(const SsParams& p, bool generic, int passes, cudaStream_t st) {
   }
   const size_t sm_stitch =
       ((size_t)kStitchStages * kStitchGroup * ((MP + 1) * MP + 2 * MP) + 2 * MP) * sizeof(float) + kStitchStages * 8 + 128;
+  constexpr int MCS = MP >= 8 ? MP - 2 : 0;  // compile-time column counts: M == MP - 2 and M == MP
+  const int mc = p.M == MP ? MP : (MCS && p.M == MCS ? MCS : 0);
   static bool attr2 = false;
   if (!attr2) {
-    GOLF_CUDA(cudaFuncSetAttribute(ss_stitch_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stitch));
+    GOLF_CUDA(cudaFuncSetAttribute(ss_stitch_kernel<MP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stitch));
+    GOLF_CUDA(cudaFuncSetAttribute(ss_stitch_kernel<MP, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stitch));
+    if (MCS) GOLF_CUDA(cudaFuncSetAttribute(ss_stitch_kernel<MP, (MCS ? MCS : MP)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stitch));
     attr2 = true;
   }
   const int G = ceil_div(p.C, 32);
   const size_t sm_solve = (FORM == 0 ? 1 : 2) * 32 * (MP + 1) * sizeof(float);
-  if (nresp > 0 && (passes & 16)) {
+  auto solve = [&](int round) -> int {
+    if constexpr (FORM == 0 && MP >= 16 && MP % 8 == 0) {
+      if (!generic && g_solve_systolic) {
+        ss_solve_sys_kernel<MP><<<p.B * ceil_div(p.C, 8), 32, 0, st>>>(p, round);
+        GOLF_CHECK_LAUNCH();
+        return GOLF_OK;
+      }
+    }
     if (generic)
-      ss_solve_kernel<MP, FORM, true><<<p.B * G, 32, sm_solve, st>>>(p, -1);
+      ss_solve_kernel<MP, FORM, true><<<p.B * G, 32, sm_solve, st>>>(p, round);
     else
-      ss_solve_kernel<MP, FORM, false><<<p.B * G, 32, sm_solve, st>>>(p, -1);
+      ss_solve_kernel<MP, FORM, false><<<p.B * G, 32, sm_solve, st>>>(p, round);
     GOLF_CHECK_LAUNCH();
+    return GOLF_OK;
+  };
+  if (nresp > 0 && (passes & 16)) {
+    const int rc = solve(-1);
+    if (rc) return rc;
   }
   for (int round = 0; round < 2; ++round) {
     const bool refine = round == 1;
     if (refine && !((passes & 8) && nresp > 0)) break;
     if (refine || (passes & 2)) {
-      ss_stitch_kernel<MP><<<p.B, 32, sm_stitch, st>>>(p, refine ? 1 : 0);
+      if (mc == MP)
+        ss_stitch_kernel<MP, MP><<<p.B, 32, sm_stitch, st>>>(p, refine ? 1 : 0);
+      else if (mc != 0)
+        ss_stitch_kernel<MP, (MCS ? MCS : MP)><<<p.B, 32, sm_stitch, st>>>(p, refine ? 1 : 0);
+      else
+        ss_stitch_kernel<MP, 0><<<p.B, 32, sm_stitch, st>>>(p, refine ? 1 : 0);
       GOLF_CHECK_LAUNCH();
     }
     if (refine || (passes & 4)) {
-      if (generic)
-        ss_solve_kernel<MP, FORM, true><<<p.B * G, 32, sm_solve, st>>>(p, round);
-      else
-        ss_solve_kernel<MP, FORM, false><<<p.B * G, 32, sm_solve, st>>>(p, round);
-      GOLF_CHECK_LAUNCH();
+      const int rc = solve(round);
+      if (rc) return rc;
     }
   }
   return GOLF_OK;

@@ -106,58 +106,56 @@ __device__ __forceinline__ uint64_t q64_interval(uint64_t xk, uint64_t xn, int h
   return xk * (uint64_t)hp + (uint64_t)(half * (int64_t)(hp - 1));
 }
 
-// grid (kPrefSplit, B): each CTA scans a contiguous 1/kPrefSplit of the knots, stores prefixes local
-// to its span plus the span total; readers add the totals of the earlier spans (<= kPrefSplit-1 adds).
-constexpr int kPrefSplit = 8;
-__global__ void __launch_bounds__(256) osc_knot_prefix_q64_kernel(const float* __restrict__ phase,
-                                                                  unsigned long long* __restrict__ pref,
-                                                                  unsigned long long* __restrict__ totals, int Np, int hp,
-                                                                  float os_f, int span) {
-  __shared__ unsigned long long wsum[8];
-  const int sp = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// One CTA per utterance, one WARP per span of the knots (kPrefSplit spans): the warp walks its span
+// 32 knots at a time -- coalesced loads, a shuffle scan of the 64-bit interval sums, coalesced
+// stores of the span-local exclusive prefix -- and carries the running sum in a register.  The span
+// totals are then scanned by warp 0 into exclusive span offsets soff[b][span]; readers add
+// pref[k] + soff[k / span] (integer adds wrap at one cycle, any order gives the same bits).
+constexpr int kPrefSplit = 32;
+__global__ void __launch_bounds__(32 * kPrefSplit) osc_knot_prefix_q64_kernel(const float* __restrict__ phase,
+                                                                              unsigned long long* __restrict__ pref,
+                                                                              unsigned long long* __restrict__ soff, int Np,
+                                                                              int hp, float os_f, int span) {
+  __shared__ unsigned long long tot[kPrefSplit];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* __restrict__ ph = phase + (size_t)b * Np;
   unsigned long long* pb = pref + (size_t)b * Np;
   const bool pow2 = ((int)os_f & ((int)os_f - 1)) == 0;
   const float inv_os_f = 1.f / os_f;
-  const int s0 = sp * span, s1 = min(Np, s0 + span);
-  const int per = (span + 255) / 256;
-  const int k0 = min(s0 + tid * per, s1), k1 = min(s1, k0 + per);
-  unsigned long long s = 0;
-  uint64_t xk = k0 < k1 ? q64_from_float(div_os(__ldg(ph + k0), os_f, inv_os_f, pow2)) : 0ull;
-#pragma unroll 4
-  for (int k = k0; k < k1; ++k) {
-    const uint64_t xn = q64_from_float(div_os(__ldg(ph + min(k + 1, Np - 1)), os_f, inv_os_f, pow2));
-    s += q64_interval(xk, xn, hp);
-    xk = xn;
-  }
-  // exclusive block scan of the per-thread sums (integer adds: order does not matter)
-  unsigned long long inc = s;
+  const int s0 = min(warp * span, Np), s1 = min(Np, s0 + span);
+  unsigned long long carry = 0;
+  float f_cur = s0 + lane < Np ? __ldg(ph + s0 + lane) : 0.f;
+  float f_nxt = __ldg(ph + min(s0 + lane + 1, Np - 1));
+  for (int base = s0; base < s1; base += 32) {
+    const int k = base + lane;
+    const float fk = f_cur, fn = f_nxt;
+    if (base + 32 < s1) {  // next round's loads fly during this round's scan
+      f_cur = k + 32 < Np ? __ldg(ph + k + 32) : 0.f;
+      f_nxt = __ldg(ph + min(k + 33, Np - 1));
+    }
+    const uint64_t xk = q64_from_float(div_os(fk, os_f, inv_os_f, pow2));
+    const uint64_t xn = q64_from_float(div_os(fn, os_f, inv_os_f, pow2));
+    const unsigned long long v = k < s1 ? q64_interval(xk, xn, hp) : 0ull;
+    unsigned long long inc = v;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc += v;
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += u;
+    }
+    if (k < s1) pb[k] = carry + inc - v;
+    carry += __shfl_sync(0xffffffffu, inc, 31);
   }
-  if (lane == 31) wsum[warp] = inc;
+  if (lane == 0) tot[warp] = carry;
   __syncthreads();
   if (warp == 0) {
-    unsigned long long w = lane < 8 ? wsum[lane] : 0ull, winc = w;
+    const unsigned long long w = tot[lane];
+    unsigned long long winc = w;
 #pragma unroll
-    for (int d = 1; d < 8; d <<= 1) {
-      const unsigned long long v = __shfl_up_sync(0xffffffffu, winc, d);
-      if (lane >= d) winc += v;
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long u = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += u;
     }
-    if (lane < 8) wsum[lane] = winc - w;
-    if (lane == 7) totals[(size_t)b * kPrefSplit + sp] = winc;
-  }
-  __syncthreads();
-  unsigned long long run = wsum[warp] + (inc - s);
-  xk = k0 < k1 ? q64_from_float(div_os(__ldg(ph + k0), os_f, inv_os_f, pow2)) : 0ull;
-#pragma unroll 4
-  for (int k = k0; k < k1; ++k) {
-    pb[k] = run;
-    const uint64_t xn = q64_from_float(div_os(__ldg(ph + min(k + 1, Np - 1)), os_f, inv_os_f, pow2));
-    run += q64_interval(xk, xn, hp);
-    xk = xn;
+    soff[(size_t)b * kPrefSplit + lane] = winc - w;
   }
 }
 
@@ -228,7 +226,7 @@ struct OscParams {
   const float* tables;    // [B,Fw,P]
   const double* pref;     // [B,Np] exclusive knot prefix (frac part, or unwrapped when aten_cpu)
   int aten_cpu;           // 1: round the running sum to float32 before mod 1 (ATen CPU cumsum semantics)
-  const unsigned long long* totals;  // [B][kPrefSplit] span totals of the Q0.64 prefix
+  const unsigned long long* totals;  // [B][kPrefSplit] exclusive span offsets of the Q0.64 prefix
   int span;               // knots per span
   const float* dec;       // [2*zeros*os+1]
   float* out;             // [B,n_out]
@@ -263,8 +261,7 @@ struct KnotPhase {
       // error moves the phase by < 1e-9 cycles (the term itself is a second-order correction)
       qq = __float2ll_rn(__ll2float_rn((int64_t)(qn - qx)) * p.inv_2hp);
       qp = reinterpret_cast<const unsigned long long*>(p.pref)[(size_t)b * p.Np + k];
-      const int spn = k / p.span;
-      for (int q = 0; q < spn; ++q) qp += p.totals[(size_t)b * kPrefSplit + q];
+      qp += p.totals[(size_t)b * kPrefSplit + k / p.span];  // exclusive span offset
     }
   }
   __device__ __forceinline__ float wrapped(const OscParams& p, int phs) const {
@@ -335,6 +332,173 @@ __global__ void __launch_bounds__(128) osc_flow_decimate_kernel(OscParams p) {
     if (m0 + r0 + i < p.n_out) ob[m0 + r0 + i] = acc[i];
 }
 
+
+// ---- fused flow + decimation, v2 (exact-phase mode, compile-time oversampling) --------------
+// Same arithmetic as osc_flow_decimate_kernel, restructured so a sample costs ~1/3 of the instructions
+// and none of its loads leave the SM:
+//  * the (at most three) interpolated table rows a tile can touch are built straight from the base
+//    table into shared memory (osc_tables_kernel's arithmetic; that launch and its [B,Fw,P] tensor
+//    disappear), so the four bilinear taps are LDS instead of dependent L2 gathers;
+//  * the Q0.64 phase of the `os` samples of one output index advances by exact integer increments
+//    (phi += d; d += 2q) instead of re-evaluating the closed form;
+//  * the upsampled increment (equal-energy scaling) reuses the knot pair already in registers and
+//    only takes ATen's general path where floor(src) can differ from the knot (r == 0);
+//  * the polyphase strips use the conflict-free fir_sw() layout.
+constexpr int kOscRows = 3;
+template <int OS>
+__global__ void __launch_bounds__(128) osc_flow_v2_kernel(OscParams p, const float* __restrict__ w,
+                                                          const float* __restrict__ table, int n_tab) {
+  extern __shared__ __align__(16) float smem[];
+  const int plen_sw = fir_sw(p.plen) + 4;
+  float* vp = smem;                         // [OS][plen_sw] polyphase oversampled flow, fir_sw() layout
+  float* hp_ = vp + OS * plen_sw;           // [OS][kp12] polyphase taps
+  float* rows = hp_ + OS * p.kp12;          // [kOscRows][P] interpolated table rows ybase .. ybase+2
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int m0 = blockIdx.x * kOscTile;
+  const float* __restrict__ ph = p.phase + (size_t)b * p.Np;
+  const int Z = p.zeros, P = p.P;
+  const float os_f = (float)OS, inv_os_f = 1.f / os_f, inv_yd = 1.f / p.ydenom;
+  constexpr bool pow2 = (OS & (OS - 1)) == 0;
+  // first table row this tile can touch.  The tile (with its FIR halo) is shorter than one row
+  // interval (checked on the host), so its samples see at most two consecutive values of
+  // y0 = floor(row coordinate) -> rows ya .. ya+2.  Only a sample EXACTLY on a row boundary can land one
+  // row low in float arithmetic; that can only be the tile's first sample, hence the -1 there.
+  const int t_first = max((m0 - Z) * OS, 0);
+  const int ya = t_first / p.hop_tab;
+  const int ybase = min(max(ya - ((t_first % p.hop_tab == 0) ? 1 : 0), 0), p.Fw - 1);
+  // ---- polyphase taps
+  for (int i = tid; i < OS * p.kp12; i += blockDim.x) {
+    const int phs = i / p.kp12, q = i % p.kp12;
+    const int n = q * OS + phs;
+    hp_[i] = (n <= 2 * Z * OS) ? (p.dec ? p.dec[n] : 1.f) : 0.f;
+  }
+  // ---- table rows: rows[i][c] = table[lo]*(1-frac) + table[lo+1]*frac of control frame min(ybase+i, Fw-1)
+  for (int i = 0; i < kOscRows; ++i) {
+    const int f = min(ybase + i, p.Fw - 1);
+    const float raw = __fmul_rn(__ldg(w + (size_t)b * p.Fw + f), (float)(n_tab - 1));
+    int lo = (int)raw;
+    lo = min(max(lo, 0), n_tab - 2);
+    const float fr = __fsub_rn(raw, (float)lo), fr1 = __fsub_rn(1.f, fr);
+    const float4* t0 = reinterpret_cast<const float4*>(table + (size_t)lo * P);
+    const float4* t1 = reinterpret_cast<const float4*>(table + (size_t)(lo + 1) * P);
+    float4* dst = reinterpret_cast<float4*>(rows + i * P);
+    for (int c = tid; c < P / 4; c += blockDim.x) {
+      const float4 a = __ldg(t0 + c), d = __ldg(t1 + c);
+      float4 o;
+      o.x = __fadd_rn(__fmul_rn(a.x, fr1), __fmul_rn(d.x, fr));
+      o.y = __fadd_rn(__fmul_rn(a.y, fr1), __fmul_rn(d.y, fr));
+      o.z = __fadd_rn(__fmul_rn(a.z, fr1), __fmul_rn(d.z, fr));
+      o.w = __fadd_rn(__fmul_rn(a.w, fr1), __fmul_rn(d.w, fr));
+      dst[c] = o;
+    }
+  }
+  __syncthreads();
+  // ---- flow: strip index j <-> output-rate index mj = m0 - Z + j, samples t = mj*OS + phs
+  const int phase_hop = p.hp / OS;
+  const float Pf = (float)P, blocks_f = (float)p.blocks;
+  for (int j = tid; j < p.plen; j += blockDim.x) {
+    const int mj = m0 - Z + j;
+    const bool in = mj >= 0 && (int64_t)mj * OS < p.N;
+    float v[OS];
+#pragma unroll
+    for (int phs = 0; phs < OS; ++phs) v[phs] = 0.f;
+    if (in) {
+      int k = phase_hop == 1 ? mj : mj / phase_hop;
+      k = min(k, p.Np - 1);
+      const int k1 = min(k + 1, p.Np - 1);
+      const int r0 = (mj - k * phase_hop) * OS;
+      const float xk = div_os(__ldg(ph + k), os_f, inv_os_f, pow2), xn = div_os(__ldg(ph + k1), os_f, inv_os_f, pow2);
+      const uint64_t qx = q64_from_float(xk), qn = q64_from_float(xn);
+      const int64_t qq = __float2ll_rn(__ll2float_rn((int64_t)(qn - qx)) * p.inv_2hp);
+      uint64_t qp = reinterpret_cast<const unsigned long long*>(p.pref)[(size_t)b * p.Np + k] +
+                    p.totals[(size_t)b * kPrefSplit + k / p.span];
+      // phi(r) = qp + (r+1) qx + qq r (r+1);  phi(r+1) - phi(r) = qx + 2 qq (r+1)
+      uint64_t phi = qp + (uint64_t)(r0 + 1) * qx + (uint64_t)(qq * (int64_t)(r0 * (r0 + 1)));
+      uint64_t d = qx + (uint64_t)(2 * qq * (int64_t)(r0 + 1));
+      const uint64_t dd = (uint64_t)(2 * qq);
+      const float kf = (float)k;
+      const int t0 = mj * OS;
+#pragma unroll
+      for (int phs = 0; phs < OS; ++phs) {
+        const int t = t0 + phs;
+        if (t < p.N) {
+          float wr = __fmul_rn(__ull2float_rn(phi), 5.42101086242752217e-20f);  // * 2^-64
+          wr = wr >= 1.f ? 0.f : wr;
+          const float tf = (float)t;
+          // bilinear taps, F.grid_sample(align_corners=True) arithmetic (see osc_taps)
+          const float gx = __fsub_rn(__fmul_rn(wr, 2.f), 1.f);
+          const float gy = __fsub_rn(__fmul_rn(__fmul_rn(tf, inv_yd), 2.f), 1.f);
+          const float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), Pf);
+          const float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), blocks_f);
+          const float x0f = floorf(ix), y0f = floorf(iy);
+          const float fx = __fsub_rn(ix, x0f), fy = __fsub_rn(iy, y0f);
+          const int x0 = min(max((int)x0f, 0), P), y0 = min(max((int)y0f, 0), p.blocks);
+          const int c0 = x0 == P ? 0 : x0;
+          const int c1 = x0 + 1 >= P ? (x0 + 1 == P ? 0 : -1) : x0 + 1;
+          // staged rows: index relative to ybase; rows beyond Fw-1 replicate the last one
+          const int ra = min(y0, p.Fw - 1) - ybase, rb = min(y0 + 1, p.Fw - 1) - ybase;
+          const bool has1 = y0 + 1 <= p.blocks;
+          const float gx1 = __fsub_rn(1.f, fx), gy1 = __fsub_rn(1.f, fy);
+          float val;
+          if ((unsigned)ra < (unsigned)kOscRows && (unsigned)rb < (unsigned)kOscRows) {
+            const float* r0p = rows + ra * P;
+            const float* r1p = rows + rb * P;
+            const float t00 = r0p[c0], t01 = c1 >= 0 ? r0p[c1] : 0.f;
+            const float t10 = has1 ? r1p[c0] : 0.f, t11 = (has1 && c1 >= 0) ? r1p[c1] : 0.f;
+            val = __fmul_rn(t00, __fmul_rn(gx1, gy1));
+            val = __fmaf_rn(t01, __fmul_rn(fx, gy1), val);
+            val = __fmaf_rn(t10, __fmul_rn(gx1, fy), val);
+            val = __fmaf_rn(t11, __fmul_rn(fx, fy), val);
+          } else {  // not reached for tiles shorter than a row interval; correct (and slow) if it ever is
+            auto rowval = [&](int f, int c) -> float {
+              const float raw = __fmul_rn(__ldg(w + (size_t)b * p.Fw + f), (float)(n_tab - 1));
+              const int lo = min(max((int)raw, 0), n_tab - 2);
+              const float fr = __fsub_rn(raw, (float)lo);
+              return __fadd_rn(__fmul_rn(__ldg(table + (size_t)lo * P + c), __fsub_rn(1.f, fr)),
+                               __fmul_rn(__ldg(table + (size_t)(lo + 1) * P + c), fr));
+            };
+            const int fa = min(y0, p.Fw - 1), fb = min(y0 + 1, p.Fw - 1);
+            val = __fmul_rn(rowval(fa, c0), __fmul_rn(gx1, gy1));
+            val = __fmaf_rn(c1 >= 0 ? rowval(fa, c1) : 0.f, __fmul_rn(fx, gy1), val);
+            val = __fmaf_rn(has1 ? rowval(fb, c0) : 0.f, __fmul_rn(gx1, fy), val);
+            val = __fmaf_rn((has1 && c1 >= 0) ? rowval(fb, c1) : 0.f, __fmul_rn(fx, fy), val);
+          }
+          if (p.equal_energy) {
+            // ATen's upsample of phase/os at t: src = scale*t, i0 = floor(src); inside the knot
+            // interval i0 == k except possibly at r == 0 -> general path there
+            const float src = __fmul_rn(p.scale, tf);
+            float l1 = __fsub_rn(src, kf);
+            float inc;
+            if (l1 >= 0.f && l1 < 1.f) {
+              const float l0 = __fsub_rn(1.f, l1);
+              inc = __fmaf_rn(l0, xk, __fmul_rn(l1, xn));
+            } else {
+              inc = osc_inc(ph, t, p.scale, p.Np, os_f, inv_os_f, pow2);
+            }
+            val = __fmul_rn(val, rsqrtf(inc));
+          }
+          v[phs] = val;
+        }
+        phi += d;
+        d += dd;
+      }
+    }
+    const int js = fir_sw(j);
+#pragma unroll
+    for (int phs = 0; phs < OS; ++phs) vp[phs * plen_sw + js] = v[phs];
+  }
+  __syncthreads();
+  const int r0 = tid * kR;  // outputs m0 + r0 .. m0 + r0 + 7
+  float acc[kR];
+#pragma unroll
+  for (int i = 0; i < kR; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int phs = 0; phs < OS; ++phs) fir_tile8_sw(vp + phs * plen_sw, r0, hp_ + phs * p.kp12, p.kp12, acc);
+  float* ob = p.out + (size_t)b * p.n_out;
+#pragma unroll
+  for (int i = 0; i < kR; ++i)
+    if (m0 + r0 + i < p.n_out) ob[m0 + r0 + i] = acc[i];
+}
 
 // ---- adjoint w.r.t. the table-selection weight -----------------------------------------
 // d_w[b,f] = (n_tab-1) * sum_t gv[t] rs(t) * sum_{taps of t in row f} weight * (T[lo_f+1][col] - T[lo_f][col])
@@ -463,9 +627,13 @@ static OscParams osc_params(const float* phase, const float* tables, const doubl
   return p;
 }
 
+static int g_osc_v2 = 1;
+
 }  // namespace golf
 
 using namespace golf;
+
+GOLF_API void golf_glottal_osc_set_variant(int v2) { g_osc_v2 = v2 ? 1 : 0; }
 
 GOLF_API size_t golf_glottal_osc_workspace_bytes(int B, int Np, int phase_hop, int Fw, int P, int os) {
   OscLayout L;
@@ -487,21 +655,45 @@ GOLF_API int golf_glottal_osc_fwd(const float* phase, const float* w, const floa
   float* tables = reinterpret_cast<float*>(ws + L.off_tables);
   double* pref = reinterpret_cast<double*>(ws + L.off_pref);
 
-  osc_tables_kernel<<<ceil_div(B * Fw * P, 256), 256, 0, st>>>(w, table, tables, B * Fw, n_tab, P);
-  GOLF_CHECK_LAUNCH();
   if (accumulate != 0 && accumulate != 1) return GOLF_ERR_INVALID;
   unsigned long long* totals = reinterpret_cast<unsigned long long*>(ws + L.off_pref + align_up((size_t)B * Np * 8, 256));
   const int span = ceil_div(Np, kPrefSplit);
+  OscParams p = osc_params(phase, tables, pref, totals, span, dec_kernel, out, B, Np, Fw, w_hop, P, os, zeros, accumulate, flags, L);
+  dim3 grid(ceil_div(L.n_out, kOscTile), B);
+  // v2: exact-phase mode, compile-time oversampling, table rows built in shared memory.  Needs a tile
+  // (plus FIR halo) shorter than one table-row interval so three staged rows always suffice.
+  const size_t sm2 = ((size_t)os * (fir_sw(p.plen) + 4 + p.kp12) + (size_t)kOscRows * P) * sizeof(float);
+  const bool v2 = g_osc_v2 && accumulate == 0 && (os == 1 || os == 2 || os == 4) && P % 4 == 0 && sm2 <= 200 * 1024 &&
+                  (int64_t)p.plen * os < (int64_t)p.hop_tab;
+  if (v2) {
+    osc_knot_prefix_q64_kernel<<<B, 32 * kPrefSplit, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), totals, Np, L.hp,
+                                                            (float)os, span);
+    GOLF_CHECK_LAUNCH();
+    static bool attr = false;
+    if (!attr) {
+      GOLF_CUDA(cudaFuncSetAttribute(osc_flow_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GOLF_CUDA(cudaFuncSetAttribute(osc_flow_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GOLF_CUDA(cudaFuncSetAttribute(osc_flow_v2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    switch (os) {
+      case 1: osc_flow_v2_kernel<1><<<grid, 128, sm2, st>>>(p, w, table, n_tab); break;
+      case 2: osc_flow_v2_kernel<2><<<grid, 128, sm2, st>>>(p, w, table, n_tab); break;
+      default: osc_flow_v2_kernel<4><<<grid, 128, sm2, st>>>(p, w, table, n_tab); break;
+    }
+    GOLF_CHECK_LAUNCH();
+    return GOLF_OK;
+  }
+  osc_tables_kernel<<<ceil_div(B * Fw * P, 256), 256, 0, st>>>(w, table, tables, B * Fw, n_tab, P);
+  GOLF_CHECK_LAUNCH();
   if (accumulate == 0)
-    osc_knot_prefix_q64_kernel<<<dim3(kPrefSplit, B), 256, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), totals, Np,
-                                                                  L.hp, (float)os, span);
+    osc_knot_prefix_q64_kernel<<<B, 32 * kPrefSplit, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), totals, Np, L.hp,
+                                                            (float)os, span);
   else
     osc_knot_prefix_kernel<<<B, 256, 0, st>>>(phase, pref, Np, L.hp, os, 0);
   GOLF_CHECK_LAUNCH();
-  OscParams p = osc_params(phase, tables, pref, totals, span, dec_kernel, out, B, Np, Fw, w_hop, P, os, zeros, accumulate, flags, L);
   const size_t sm = (size_t)os * (p.plen + p.kp12) * sizeof(float);
   if (sm > 48 * 1024) return GOLF_ERR_UNSUPPORTED;
-  dim3 grid(ceil_div(L.n_out, kOscTile), B);
   switch (os) {
     case 1: osc_flow_decimate_kernel<1><<<grid, 128, sm, st>>>(p); break;
     case 2: osc_flow_decimate_kernel<2><<<grid, 128, sm, st>>>(p); break;
@@ -531,8 +723,8 @@ GOLF_API int golf_glottal_osc_bwd_w(const float* gout, const float* phase, const
   const int span = ceil_div(Np, kPrefSplit);
   // the phase prefix is recomputed (cheap) rather than saved between forward and backward
   if (accumulate == 0)
-    osc_knot_prefix_q64_kernel<<<dim3(kPrefSplit, B), 256, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), totals, Np,
-                                                                  L.hp, (float)os, span);
+    osc_knot_prefix_q64_kernel<<<B, 32 * kPrefSplit, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), totals, Np, L.hp,
+                                                            (float)os, span);
   else
     osc_knot_prefix_kernel<<<B, 256, 0, st>>>(phase, pref, Np, L.hp, os, 0);
   GOLF_CHECK_LAUNCH();

@@ -66,6 +66,10 @@ size_t golf_lpc_ss_workspace_bytes(int B, int L, int M, int hop, int chunk);
  * Process-wide setting. */
 void golf_lpc_ss_set_refine_tolerance(float tol);
 float golf_lpc_ss_get_refine_tolerance(void);
+/* Solve-pass variant of the forward filter: 1 (default) = four lanes per chunk (tap blocks pipelined
+ * across lanes), 0 = one lane per chunk.  Same recurrence, different summation order
+ * (results agree to float32 rounding).  Process-wide; for A/B timing and tests. */
+void golf_lpc_ss_set_solver(int systolic);
 int golf_lpc_ss_fwd(const float *ex, int64_t ex_stride, const float *gain, const float *a,
                     const float *zi, float *y, int B, int L, int F, int M, int hop,
                     int chunk, void *workspace, size_t workspace_bytes, void *stream);
@@ -152,6 +156,10 @@ int golf_room_fir_bwd(const float *gy, const float *x, const float *k, float *d_
  * before `% 1`, the arithmetic of ATen's CPU cumsum (parity checks).
  * flags bit0: equal_energy (multiply by rsqrt(upsampled phase)). */
 size_t golf_glottal_osc_workspace_bytes(int B, int Np, int phase_hop, int Fw, int P, int os);
+/* Forward kernel variant in exact-phase mode: 1 (default) = table rows staged in shared memory,
+ * incremental fixed-point phase; 0 = the first-generation kernel.  Same arithmetic.
+ * Process-wide; for A/B timing and tests. */
+void golf_glottal_osc_set_variant(int v2);
 int golf_glottal_osc_fwd(const float *phase, const float *w, const float *table,
                          const float *dec_kernel, float *out, int B, int Np, int phase_hop,
                          int Fw, int w_hop, int n_tab, int P, int os, int zeros,

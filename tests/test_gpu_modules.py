@@ -222,3 +222,26 @@ def test_pipelined_synth_matches_graph_replay():
     r = [float(o.pow(2).mean().sqrt()) for o in outs]
     for s in range(1, 5):  # rms scales with the gain factor (noise differs per draw: 5 % slack)
         assert abs(r[s] / r[0] - (1 + 0.1 * s)) < 0.05 * (1 + 0.1 * s), r
+
+
+def test_solver_variants_agree():
+    """four-lanes-per-chunk (systolic) solve vs lane-per-chunk solve: same recurrence, different
+    summation order -> equal to float32 rounding, and both within tolerance of the reference golden"""
+    from golf_b200 import _lib, functional as G
+
+    g = golden("grads_ss")
+    H = int(g["hop"])
+    ex, gain, a = (T(g[k]).to(DEV) for k in ("ex", "gain", "a"))
+    outs = {}
+    try:
+        for mode in (0, 1):
+            _lib.lib().golf_lpc_ss_set_solver(mode)
+            outs[mode] = G.lpc_ss(ex, gain, a, H)
+            ws = G.lpc_ss_responses(a, outs[mode].shape[1], H)
+            outs[(mode, "two-call")] = G.lpc_ss_finish(ex, gain, a, H, ws)
+    finally:
+        _lib.lib().golf_lpc_ss_set_solver(1)
+    ref = T(g["ss_y"])
+    for k, v in outs.items():
+        assert rel_rms(v, ref) < REL_TOL, k
+        assert rel_rms(v, outs[0]) < 1e-5, k
