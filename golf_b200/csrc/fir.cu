@@ -17,6 +17,8 @@
 
 namespace golf {
 
+int g_fir_x2 = 1;  // 1 (default): packed-FP32 (FFMA2) kernels where they apply; 0: scalar register tile
+
 // ---- time-varying block FIR ---------------------------------------------------------
 // grid (n_blocks, B), 32*ceil(hop/256) threads.  smem: xs[hop + K12 + 32] | ks[K12]
 __global__ void __launch_bounds__(256) noise_fir_kernel(const float* __restrict__ ex, int64_t ex_stride,
@@ -54,6 +56,96 @@ __global__ void __launch_bounds__(256) noise_fir_kernel(const float* __restrict_
 #pragma unroll
   for (int i = 0; i < kR; ++i)
     if (r0 + i < hop) yb[r0 + i] = ab ? ab[r0 + i] + acc[i] : acc[i];
+}
+
+// ---- time-varying block FIR, packed-FP32 (FFMA2) version ------------------------------------
+// One WARP per CTA, NBW consecutive blocks of one utterance per warp (TPB = ceil(hop/16) lanes per block,
+// NBW = 32 / TPB: hop 240 -> 2 blocks on 30 lanes), so the grid is thousands of small CTAs that the block
+// scheduler keeps balanced over the 148 SMs.  smem: xs0[XS] | xs1[XS] | kd[NBW][2*K20]  (fir_tile.cuh).
+__global__ void __launch_bounds__(32) noise_fir_x2_kernel(const float* __restrict__ ex, int64_t ex_stride,
+                                                          const float* __restrict__ kernel, const float* __restrict__ window,
+                                                          const float* __restrict__ add, int64_t add_stride,
+                                                          float* __restrict__ y, int T, int F, int K, int hop, int n_blocks,
+                                                          int K20, int xs_len, int XS, int TPB, int NBW, int vec_ok) {
+  extern __shared__ __align__(16) float smem[];
+  float* xs0 = smem;
+  float* xs1 = smem + XS;
+  float* kd = smem + 2 * XS;
+  const int lane = threadIdx.x, b = blockIdx.y;
+  const int k0 = blockIdx.x * NBW;
+  const int p = (K - 1) / 2;
+  const float* __restrict__ exb = ex + (size_t)b * ex_stride;
+  const int start = k0 * hop - p;  // signal position of logical strip index 0
+  // staging is latency bound (a warp alone, every element one global load): all loads of a batch are
+  // issued before any is consumed, and they are branch free (clamped address + select) so that the
+  // compiler can actually batch them
+  constexpr int kStageU = 8;
+  for (int i0 = lane; i0 <= xs_len; i0 += 32 * kStageU) {
+    float v[kStageU];
+#pragma unroll
+    for (int u = 0; u < kStageU; ++u) {
+      const int pos = start + i0 + 32 * u;
+      const float raw = __ldg(exb + min(max(pos, 0), T - 1));
+      v[u] = (pos >= 0 && pos < T) ? raw : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kStageU; ++u) {
+      const int i = i0 + 32 * u;  // the strips are allocated up to XS >= xs_len + 32*kStageU: no bound checks on xs0
+      xs0[fir_sw16(i)] = v[u];
+      if (i > 0) xs1[fir_sw16(i - 1)] = v[u];
+    }
+  }
+  // taps, duplicated: either final, or (window given) the raw irfft output: fftshift + windowing fused here
+  const int nb = min(NBW, n_blocks - k0);
+  for (int bi = 0; bi < nb; ++bi) {
+    const float* __restrict__ kb = kernel + ((size_t)b * F + k0 + bi) * K;
+    float2* dst = reinterpret_cast<float2*>(kd + (size_t)bi * 2 * K20);
+    const int half = window ? K / 2 : 0;
+    for (int i0 = lane; i0 < K20; i0 += 32 * kStageU) {
+      float v[kStageU], wv[kStageU];
+#pragma unroll
+      for (int u = 0; u < kStageU; ++u) {
+        const int i = min(i0 + 32 * u, K - 1);
+        const int src = i + half >= K ? i + half - K : i + half;
+        v[u] = __ldg(kb + src);
+        wv[u] = window ? __ldg(window + i) : 1.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kStageU; ++u) {
+        const int i = i0 + 32 * u;
+        const float t = i < K ? (window ? __fmul_rn(v[u], wv[u]) : v[u]) : 0.f;
+        if (i < K20) dst[i] = make_float2(t, t);
+      }
+    }
+  }
+  __syncwarp();
+  const int bi = lane / TPB, c = lane - bi * TPB;
+  if (bi >= nb) return;
+  const int r0 = c * kR2;
+  f32x2 acc[kR2 / 2];
+#pragma unroll
+  for (int i = 0; i < kR2 / 2; ++i) acc[i] = 0ull;
+  fir_tile16_x2(xs0, xs1, bi * hop + r0, kd + (size_t)bi * 2 * K20, K20, acc);
+  float o[kR2];
+#pragma unroll
+  for (int i = 0; i < kR2 / 2; ++i) unpack2(acc[i], o[2 * i], o[2 * i + 1]);
+  float* yb = y + (size_t)b * n_blocks * hop + (size_t)(k0 + bi) * hop + r0;
+  const float* ab = add ? add + (size_t)b * add_stride + (size_t)(k0 + bi) * hop + r0 : nullptr;
+  if (vec_ok && r0 + kR2 <= hop) {
+#pragma unroll
+    for (int v = 0; v < kR2 / 4; ++v) {
+      float4 r = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+      if (ab) {
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(ab) + v);
+        r.x = a4.x + r.x, r.y = a4.y + r.y, r.z = a4.z + r.z, r.w = a4.w + r.w;
+      }
+      reinterpret_cast<float4*>(yb)[v] = r;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kR2; ++i)
+      if (r0 + i < hop) yb[i] = ab ? ab[i] + o[i] : o[i];
+  }
 }
 
 // ---- room FIR: out[t] = x[t] + sum_{j<n} k[j] x[t-n+j] ---------------------------------
@@ -260,6 +352,8 @@ __global__ void rc2lpc_kernel(const float* __restrict__ logits, float* __restric
 
 using namespace golf;
 
+GOLF_API void golf_fir_set_variant(int x2) { g_fir_x2 = x2 ? 1 : 0; }
+
 GOLF_API int golf_noise_fir_fwd(const float* ex, int64_t ex_stride, const float* kernel, const float* window,
                                 const float* add, int64_t add_stride, float* y, int B, int T, int F, int K, int hop,
                                 void* stream) {
@@ -269,13 +363,29 @@ GOLF_API int golf_noise_fir_fwd(const float* ex, int64_t ex_stride, const float*
   int n_blocks = (T + 2 * p - (K + hop - 1)) / hop + 1;
   if (n_blocks > F) n_blocks = F;
   if (hop > 2048) return GOLF_ERR_UNSUPPORTED;
+  if (window && (K & 1)) return GOLF_ERR_UNSUPPORTED;  // fused fftshift assumes an even tap count (2*(n_mag-1))
+  if (B > 65535) return GOLF_ERR_UNSUPPORTED;
+  // packed-FP32 kernel: hop a multiple of 4 (float4 strip reads), at most 32 lanes per block
+  if (g_fir_x2 && hop % 4 == 0 && hop <= 32 * kR2) {
+    const int TPB = ceil_div(hop, kR2), NBW = 32 / TPB;
+    const int K20 = ceil_div(K, kTapStep) * kTapStep;
+    const int xs_len = (NBW - 1) * hop + (TPB - 1) * kR2 + K20 + 24;  // last strip index a lane reads, + 1
+    const int XS = (int)align_up((size_t)xs_len + 1, 256);  // whole staging batches of 8 x 32 elements
+    const size_t sm = ((size_t)2 * XS + (size_t)NBW * 2 * K20) * sizeof(float);
+    if (sm <= 48 * 1024) {
+      const bool aligned = ((uintptr_t)y % 16 == 0) && (!add || ((uintptr_t)add % 16 == 0 && add_stride % 4 == 0));
+      noise_fir_x2_kernel<<<dim3(ceil_div(n_blocks, NBW), B), 32, sm, (cudaStream_t)stream>>>(
+          ex, ex_stride, kernel, window, add, add_stride, y, T, F, K, hop, n_blocks, K20, xs_len, XS, TPB, NBW, aligned ? 1 : 0);
+      GOLF_CHECK_LAUNCH();
+      return GOLF_OK;
+    }
+  }
   const int K12 = ceil_div(K, 12) * 12;
   const int threads = 32 * ceil_div(hop, 32 * kR);
   const int xs_len = (int)align_up((size_t)threads * kR + K12 + 24, 4);
   const size_t sm = (size_t)(fir_sw(xs_len) + 4 + K12) * sizeof(float);
   if (sm > 48 * 1024) return GOLF_ERR_UNSUPPORTED;
   dim3 grid(n_blocks, B);
-  if (window && (K & 1)) return GOLF_ERR_UNSUPPORTED;  // fused fftshift assumes an even tap count (2*(n_mag-1))
   noise_fir_kernel<<<grid, threads, sm, (cudaStream_t)stream>>>(ex, ex_stride, kernel, window, add, add_stride, y, T, F, K,
                                                               hop, n_blocks, K12, xs_len);
   GOLF_CHECK_LAUNCH();

@@ -106,57 +106,75 @@ __device__ __forceinline__ uint64_t q64_interval(uint64_t xk, uint64_t xn, int h
   return xk * (uint64_t)hp + (uint64_t)(half * (int64_t)(hp - 1));
 }
 
-// One CTA per utterance, one WARP per span of the knots (kPrefSplit spans): the warp walks its span
-// 32 knots at a time -- coalesced loads, a shuffle scan of the 64-bit interval sums, coalesced
-// stores of the span-local exclusive prefix -- and carries the running sum in a register.  The span
-// totals are then scanned by warp 0 into exclusive span offsets soff[b][span]; readers add
+// One WARP per span of the knots (kPrefSplit spans per utterance, kPrefWarps of them per CTA: the grid is
+// B * kPrefSplit / kPrefWarps CTAs, 256 at B = 32, so the scan runs on every SM -- its first version used one
+// CTA per utterance, 32 of 148 SMs, 38 us).  The warp walks its span 32*kPrefR knots at a time: a lane owns
+// kPrefR CONSECUTIVE knots (serial adds in registers), only the 32 lane totals go through a shuffle scan.
+// Output: the span-local exclusive prefix pref[b][k] and the span totals tot[b][span]; readers turn the
+// 32 totals into exclusive span offsets with one warp scan in their prologue (span_offsets) and add
 // pref[k] + soff[k / span] (integer adds wrap at one cycle, any order gives the same bits).
 constexpr int kPrefSplit = 32;
-__global__ void __launch_bounds__(32 * kPrefSplit) osc_knot_prefix_q64_kernel(const float* __restrict__ phase,
+constexpr int kPrefWarps = 4;
+constexpr int kPrefR = 8;
+__global__ void __launch_bounds__(32 * kPrefWarps) osc_knot_prefix_q64_kernel(const float* __restrict__ phase,
                                                                               unsigned long long* __restrict__ pref,
-                                                                              unsigned long long* __restrict__ soff, int Np,
+                                                                              unsigned long long* __restrict__ tot, int Np,
                                                                               int hp, float os_f, int span) {
-  __shared__ unsigned long long tot[kPrefSplit];
-  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = blockIdx.x * kPrefWarps + (threadIdx.x >> 5);
   const float* __restrict__ ph = phase + (size_t)b * Np;
   unsigned long long* pb = pref + (size_t)b * Np;
   const bool pow2 = ((int)os_f & ((int)os_f - 1)) == 0;
   const float inv_os_f = 1.f / os_f;
   const int s0 = min(warp * span, Np), s1 = min(Np, s0 + span);
   unsigned long long carry = 0;
-  float f_cur = s0 + lane < Np ? __ldg(ph + s0 + lane) : 0.f;
-  float f_nxt = __ldg(ph + min(s0 + lane + 1, Np - 1));
-  for (int base = s0; base < s1; base += 32) {
-    const int k = base + lane;
-    const float fk = f_cur, fn = f_nxt;
-    if (base + 32 < s1) {  // next round's loads fly during this round's scan
-      f_cur = k + 32 < Np ? __ldg(ph + k + 32) : 0.f;
-      f_nxt = __ldg(ph + min(k + 33, Np - 1));
+  float f[kPrefR + 1], fnext[kPrefR + 1];
+  auto fetch = [&](int k0, float (&dst)[kPrefR + 1]) {
+#pragma unroll
+    for (int i = 0; i <= kPrefR; ++i) dst[i] = __ldg(ph + min(k0 + i, Np - 1));
+  };
+  fetch(s0 + lane * kPrefR, f);
+  for (int base = s0; base < s1; base += 32 * kPrefR) {
+    const int k0 = base + lane * kPrefR;
+    if (base + 32 * kPrefR < s1) fetch(k0 + 32 * kPrefR, fnext);  // next round's loads fly during this round's scan
+    uint64_t x[kPrefR + 1], v[kPrefR];
+#pragma unroll
+    for (int i = 0; i <= kPrefR; ++i) x[i] = q64_from_float(div_os(f[i], os_f, inv_os_f, pow2));
+    unsigned long long mine = 0;
+#pragma unroll
+    for (int i = 0; i < kPrefR; ++i) {
+      v[i] = k0 + i < s1 ? q64_interval(x[i], x[i + 1], hp) : 0ull;
+      mine += v[i];
     }
-    const uint64_t xk = q64_from_float(div_os(fk, os_f, inv_os_f, pow2));
-    const uint64_t xn = q64_from_float(div_os(fn, os_f, inv_os_f, pow2));
-    const unsigned long long v = k < s1 ? q64_interval(xk, xn, hp) : 0ull;
-    unsigned long long inc = v;
+    unsigned long long inc = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, d);
       if (lane >= d) inc += u;
     }
-    if (k < s1) pb[k] = carry + inc - v;
-    carry += __shfl_sync(0xffffffffu, inc, 31);
-  }
-  if (lane == 0) tot[warp] = carry;
-  __syncthreads();
-  if (warp == 0) {
-    const unsigned long long w = tot[lane];
-    unsigned long long winc = w;
+    unsigned long long acc = carry + inc - mine;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned long long u = __shfl_up_sync(0xffffffffu, winc, d);
-      if (lane >= d) winc += u;
+    for (int i = 0; i < kPrefR; ++i) {
+      if (k0 + i < s1) pb[k0 + i] = acc;
+      acc += v[i];
     }
-    soff[(size_t)b * kPrefSplit + lane] = winc - w;
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+    for (int i = 0; i <= kPrefR; ++i) f[i] = fnext[i];
   }
+  if (lane == 0) tot[(size_t)b * kPrefSplit + warp] = carry;
+}
+
+// reader prologue (first warp of the CTA): exclusive scan of the utterance's span totals into shared memory
+__device__ __forceinline__ void span_offsets(const unsigned long long* __restrict__ tot_b, unsigned long long* soff_s) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long w = tot_b[lane];
+  unsigned long long winc = w;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long u = __shfl_up_sync(0xffffffffu, winc, d);
+    if (lane >= d) winc += u;
+  }
+  soff_s[lane] = winc - w;
 }
 
 // upsampled increment at oversampled time t, ATen arithmetic on phase/os
@@ -226,7 +244,7 @@ struct OscParams {
   const float* tables;    // [B,Fw,P]
   const double* pref;     // [B,Np] exclusive knot prefix (frac part, or unwrapped when aten_cpu)
   int aten_cpu;           // 1: round the running sum to float32 before mod 1 (ATen CPU cumsum semantics)
-  const unsigned long long* totals;  // [B][kPrefSplit] exclusive span offsets of the Q0.64 prefix
+  const unsigned long long* totals;  // [B][kPrefSplit] span totals of the Q0.64 prefix (readers: span_offsets)
   int span;               // knots per span
   const float* dec;       // [2*zeros*os+1]
   float* out;             // [B,n_out]
@@ -243,7 +261,7 @@ struct KnotPhase {
   uint64_t qx, qp;     // default: Q0.64 fixed point
   int64_t qq;
   __device__ __forceinline__ void init(const OscParams& p, const float* __restrict__ ph, int b, int mj, float os_f,
-                                       float inv_os_f, bool pow2) {
+                                       float inv_os_f, bool pow2, const unsigned long long* soff_s) {
     const int phase_hop = p.hp / p.os;
     int k = phase_hop == 1 ? mj : mj / phase_hop;
     k = min(k, p.Np - 1);
@@ -261,7 +279,7 @@ struct KnotPhase {
       // error moves the phase by < 1e-9 cycles (the term itself is a second-order correction)
       qq = __float2ll_rn(__ll2float_rn((int64_t)(qn - qx)) * p.inv_2hp);
       qp = reinterpret_cast<const unsigned long long*>(p.pref)[(size_t)b * p.Np + k];
-      qp += p.totals[(size_t)b * kPrefSplit + k / p.span];  // exclusive span offset
+      qp += soff_s[k / p.span];  // exclusive span offset
     }
   }
   __device__ __forceinline__ float wrapped(const OscParams& p, int phs) const {
@@ -282,6 +300,8 @@ __global__ void __launch_bounds__(128) osc_flow_decimate_kernel(OscParams p) {
   extern __shared__ __align__(16) float smem[];
   float* vp = smem;                      // [os][plen] polyphase oversampled flow
   float* hp_ = smem + p.os * p.plen;     // [os][kp12] polyphase taps
+  __shared__ unsigned long long soff_s[kPrefSplit];
+  if (threadIdx.x < 32 && !p.aten_cpu) span_offsets(p.totals + (size_t)blockIdx.y * kPrefSplit, soff_s);
   const int b = blockIdx.y, tid = threadIdx.x;
   const int m0 = blockIdx.x * kOscTile;
   const float* ph = p.phase + (size_t)b * p.Np;
@@ -299,11 +319,12 @@ __global__ void __launch_bounds__(128) osc_flow_decimate_kernel(OscParams p) {
   // prefix / slope are fetched once per j:  vp[phs][j] = v[mj*os + phs]
   const bool pow2 = (p.os & (p.os - 1)) == 0;
   const float inv_os_f = 1.f / os_f, inv_yd = 1.f / p.ydenom;
+  __syncthreads();  // soff_s
   for (int j = tid; j < p.plen; j += blockDim.x) {
     const int mj = m0 - Z + j;
     const bool in = mj >= 0 && (int64_t)mj * p.os < p.N;
     KnotPhase kp;
-    if (in) kp.init(p, ph, b, mj, os_f, inv_os_f, pow2);
+    if (in) kp.init(p, ph, b, mj, os_f, inv_os_f, pow2, soff_s);
     const int nos = OS ? OS : p.os;
 #pragma unroll
     for (int phs = 0; phs < nos; ++phs) {
@@ -334,15 +355,20 @@ __global__ void __launch_bounds__(128) osc_flow_decimate_kernel(OscParams p) {
 
 
 // ---- fused flow + decimation, v2 (exact-phase mode, compile-time oversampling) --------------
-// Same arithmetic as osc_flow_decimate_kernel, restructured so a sample costs ~1/3 of the instructions
-// and none of its loads leave the SM:
+// Same function as osc_flow_decimate_kernel in its exact-phase mode, restructured so a sample costs a
+// fraction of the instructions and none of its loads leave the SM:
 //  * the (at most three) interpolated table rows a tile can touch are built straight from the base
 //    table into shared memory (osc_tables_kernel's arithmetic; that launch and its [B,Fw,P] tensor
 //    disappear), so the four bilinear taps are LDS instead of dependent L2 gathers;
 //  * the Q0.64 phase of the `os` samples of one output index advances by exact integer increments
 //    (phi += d; d += 2q) instead of re-evaluating the closed form;
-//  * the upsampled increment (equal-energy scaling) reuses the knot pair already in registers and
-//    only takes ATen's general path where floor(src) can differ from the knot (r == 0);
+//  * table coordinates come straight from the integers: with P a power of two the column is the top
+//    log2(P) bits of the Q0.64 phase and the column fraction the next 32 bits; the row is t / hop_tab
+//    and the row fraction (t % hop_tab) / hop_tab, found by one compare because a tile is shorter than a
+//    row interval.  grid_sample's float detour (normalise to [-1,1], unnormalise, floor) rounds these
+//    same quantities to 24 bits on the way: the two agree to ~1e-7 of a column / row, far inside what the
+//    exact phase already differs from the reference's float32 cumsum by;
+//  * the upsampled increment (equal-energy scaling) reuses the knot pair already in registers;
 //  * the polyphase strips use the conflict-free fir_sw() layout.
 constexpr int kOscRows = 3;
 template <int OS>
@@ -353,6 +379,8 @@ __global__ void __launch_bounds__(128) osc_flow_v2_kernel(OscParams p, const flo
   float* vp = smem;                         // [OS][plen_sw] polyphase oversampled flow, fir_sw() layout
   float* hp_ = vp + OS * plen_sw;           // [OS][kp12] polyphase taps
   float* rows = hp_ + OS * p.kp12;          // [kOscRows][P] interpolated table rows ybase .. ybase+2
+  __shared__ unsigned long long soff_s[kPrefSplit];
+  if (threadIdx.x < 32 && !p.aten_cpu) span_offsets(p.totals + (size_t)blockIdx.y * kPrefSplit, soff_s);
   const int b = blockIdx.y, tid = threadIdx.x;
   const int m0 = blockIdx.x * kOscTile;
   const float* __restrict__ ph = p.phase + (size_t)b * p.Np;
@@ -360,12 +388,11 @@ __global__ void __launch_bounds__(128) osc_flow_v2_kernel(OscParams p, const flo
   const float os_f = (float)OS, inv_os_f = 1.f / os_f, inv_yd = 1.f / p.ydenom;
   constexpr bool pow2 = (OS & (OS - 1)) == 0;
   // first table row this tile can touch.  The tile (with its FIR halo) is shorter than one row
-  // interval (checked on the host), so its samples see at most two consecutive values of
-  // y0 = floor(row coordinate) -> rows ya .. ya+2.  Only a sample EXACTLY on a row boundary can land one
-  // row low in float arithmetic; that can only be the tile's first sample, hence the -1 there.
+  // interval (checked on the host), so its samples see y0 = t / hop_tab in {ybase, ybase+1} and read
+  // rows ybase .. ybase+2; staged row i is control frame min(ybase+i, Fw-1) (replicate padding).
   const int t_first = max((m0 - Z) * OS, 0);
-  const int ya = t_first / p.hop_tab;
-  const int ybase = min(max(ya - ((t_first % p.hop_tab == 0) ? 1 : 0), 0), p.Fw - 1);
+  const int ybase = t_first / p.hop_tab;
+  const int trow0 = ybase * p.hop_tab;
   // ---- polyphase taps
   for (int i = tid; i < OS * p.kp12; i += blockDim.x) {
     const int phs = i / p.kp12, q = i % p.kp12;
@@ -395,7 +422,12 @@ __global__ void __launch_bounds__(128) osc_flow_v2_kernel(OscParams p, const flo
   __syncthreads();
   // ---- flow: strip index j <-> output-rate index mj = m0 - Z + j, samples t = mj*OS + phs
   const int phase_hop = p.hp / OS;
-  const float Pf = (float)P, blocks_f = (float)p.blocks;
+  const bool ph1 = phase_hop == 1;                   // sample-rate f0 (training mode): r0 == 0 everywhere
+  const int lgP = 31 - __clz(P);                     // P is a power of two (host dispatch)
+  const int lg2hp = 31 - __clz(2 * p.hp);
+  const bool hp_pow2 = (p.hp & (p.hp - 1)) == 0;
+  const float inv_hop_tab = 1.f / (float)p.hop_tab, inv_hp = 1.f / (float)p.hp, inv_span = 1.f / (float)p.span;
+  const unsigned long long* __restrict__ prefb = reinterpret_cast<const unsigned long long*>(p.pref) + (size_t)b * p.Np;
   for (int j = tid; j < p.plen; j += blockDim.x) {
     const int mj = m0 - Z + j;
     const bool in = mj >= 0 && (int64_t)mj * OS < p.N;
@@ -403,78 +435,48 @@ __global__ void __launch_bounds__(128) osc_flow_v2_kernel(OscParams p, const flo
 #pragma unroll
     for (int phs = 0; phs < OS; ++phs) v[phs] = 0.f;
     if (in) {
-      int k = phase_hop == 1 ? mj : mj / phase_hop;
+      int k = ph1 ? mj : mj / phase_hop;
       k = min(k, p.Np - 1);
       const int k1 = min(k + 1, p.Np - 1);
-      const int r0 = (mj - k * phase_hop) * OS;
+      const int r0 = ph1 ? 0 : (mj - k * phase_hop) * OS;
       const float xk = div_os(__ldg(ph + k), os_f, inv_os_f, pow2), xn = div_os(__ldg(ph + k1), os_f, inv_os_f, pow2);
       const uint64_t qx = q64_from_float(xk), qn = q64_from_float(xn);
-      const int64_t qq = __float2ll_rn(__ll2float_rn((int64_t)(qn - qx)) * p.inv_2hp);
-      uint64_t qp = reinterpret_cast<const unsigned long long*>(p.pref)[(size_t)b * p.Np + k] +
-                    p.totals[(size_t)b * kPrefSplit + k / p.span];
+      // slope term per r(r+1): (x_{k+1}-x_k)/(2hp)
+      const int64_t dq = (int64_t)(qn - qx);
+      const int64_t qq = hp_pow2 ? (dq >> lg2hp) : __float2ll_rn(__ll2float_rn(dq) * p.inv_2hp);
+      int sp = (int)((float)k * inv_span);  // k / span without the integer division
+      sp -= (sp * p.span > k) ? 1 : 0;
+      sp += ((sp + 1) * p.span <= k) ? 1 : 0;
+      const uint64_t qp = prefb[k] + soff_s[sp];
       // phi(r) = qp + (r+1) qx + qq r (r+1);  phi(r+1) - phi(r) = qx + 2 qq (r+1)
       uint64_t phi = qp + (uint64_t)(r0 + 1) * qx + (uint64_t)(qq * (int64_t)(r0 * (r0 + 1)));
       uint64_t d = qx + (uint64_t)(2 * qq * (int64_t)(r0 + 1));
       const uint64_t dd = (uint64_t)(2 * qq);
-      const float kf = (float)k;
       const int t0 = mj * OS;
+      const int trel = t0 - trow0;
 #pragma unroll
       for (int phs = 0; phs < OS; ++phs) {
-        const int t = t0 + phs;
-        if (t < p.N) {
-          float wr = __fmul_rn(__ull2float_rn(phi), 5.42101086242752217e-20f);  // * 2^-64
-          wr = wr >= 1.f ? 0.f : wr;
-          const float tf = (float)t;
-          // bilinear taps, F.grid_sample(align_corners=True) arithmetic (see osc_taps)
-          const float gx = __fsub_rn(__fmul_rn(wr, 2.f), 1.f);
-          const float gy = __fsub_rn(__fmul_rn(__fmul_rn(tf, inv_yd), 2.f), 1.f);
-          const float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), Pf);
-          const float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), blocks_f);
-          const float x0f = floorf(ix), y0f = floorf(iy);
-          const float fx = __fsub_rn(ix, x0f), fy = __fsub_rn(iy, y0f);
-          const int x0 = min(max((int)x0f, 0), P), y0 = min(max((int)y0f, 0), p.blocks);
-          const int c0 = x0 == P ? 0 : x0;
-          const int c1 = x0 + 1 >= P ? (x0 + 1 == P ? 0 : -1) : x0 + 1;
-          // staged rows: index relative to ybase; rows beyond Fw-1 replicate the last one
-          const int ra = min(y0, p.Fw - 1) - ybase, rb = min(y0 + 1, p.Fw - 1) - ybase;
-          const bool has1 = y0 + 1 <= p.blocks;
+        if (t0 + phs < p.N) {
+          // column: top lgP bits of the phase; fraction: the next 32 bits (rounded to float)
+          const uint32_t hi = (uint32_t)(phi >> 32), lo = (uint32_t)phi;
+          const int c0 = (int)(hi >> (32 - lgP));
+          const int c1 = (c0 + 1) & (P - 1);  // column P wraps to column 0
+          const float fx = __fmul_rn(__uint2float_rn(__funnelshift_l(lo, hi, lgP)), 2.3283064365386963e-10f);  // * 2^-32
+          // row: t / hop_tab relative to the first staged row (0 or 1), fraction (t % hop_tab) / hop_tab
+          const int tr = trel + phs;
+          const bool up = tr >= p.hop_tab;
+          const float fy = __fmul_rn((float)(up ? tr - p.hop_tab : tr), inv_hop_tab);
+          const float* r0p = rows + (up ? P : 0);
+          const float* r1p = r0p + P;
+          const float t00 = r0p[c0], t01 = r0p[c1], t10 = r1p[c0], t11 = r1p[c1];
           const float gx1 = __fsub_rn(1.f, fx), gy1 = __fsub_rn(1.f, fy);
-          float val;
-          if ((unsigned)ra < (unsigned)kOscRows && (unsigned)rb < (unsigned)kOscRows) {
-            const float* r0p = rows + ra * P;
-            const float* r1p = rows + rb * P;
-            const float t00 = r0p[c0], t01 = c1 >= 0 ? r0p[c1] : 0.f;
-            const float t10 = has1 ? r1p[c0] : 0.f, t11 = (has1 && c1 >= 0) ? r1p[c1] : 0.f;
-            val = __fmul_rn(t00, __fmul_rn(gx1, gy1));
-            val = __fmaf_rn(t01, __fmul_rn(fx, gy1), val);
-            val = __fmaf_rn(t10, __fmul_rn(gx1, fy), val);
-            val = __fmaf_rn(t11, __fmul_rn(fx, fy), val);
-          } else {  // not reached for tiles shorter than a row interval; correct (and slow) if it ever is
-            auto rowval = [&](int f, int c) -> float {
-              const float raw = __fmul_rn(__ldg(w + (size_t)b * p.Fw + f), (float)(n_tab - 1));
-              const int lo = min(max((int)raw, 0), n_tab - 2);
-              const float fr = __fsub_rn(raw, (float)lo);
-              return __fadd_rn(__fmul_rn(__ldg(table + (size_t)lo * P + c), __fsub_rn(1.f, fr)),
-                               __fmul_rn(__ldg(table + (size_t)(lo + 1) * P + c), fr));
-            };
-            const int fa = min(y0, p.Fw - 1), fb = min(y0 + 1, p.Fw - 1);
-            val = __fmul_rn(rowval(fa, c0), __fmul_rn(gx1, gy1));
-            val = __fmaf_rn(c1 >= 0 ? rowval(fa, c1) : 0.f, __fmul_rn(fx, gy1), val);
-            val = __fmaf_rn(has1 ? rowval(fb, c0) : 0.f, __fmul_rn(gx1, fy), val);
-            val = __fmaf_rn((has1 && c1 >= 0) ? rowval(fb, c1) : 0.f, __fmul_rn(fx, fy), val);
-          }
-          if (p.equal_energy) {
-            // ATen's upsample of phase/os at t: src = scale*t, i0 = floor(src); inside the knot
-            // interval i0 == k except possibly at r == 0 -> general path there
-            const float src = __fmul_rn(p.scale, tf);
-            float l1 = __fsub_rn(src, kf);
-            float inc;
-            if (l1 >= 0.f && l1 < 1.f) {
-              const float l0 = __fsub_rn(1.f, l1);
-              inc = __fmaf_rn(l0, xk, __fmul_rn(l1, xn));
-            } else {
-              inc = osc_inc(ph, t, p.scale, p.Np, os_f, inv_os_f, pow2);
-            }
+          float val = __fmul_rn(t00, __fmul_rn(gx1, gy1));
+          val = __fmaf_rn(t01, __fmul_rn(fx, gy1), val);
+          val = __fmaf_rn(t10, __fmul_rn(gx1, fy), val);
+          val = __fmaf_rn(t11, __fmul_rn(fx, fy), val);
+          if (p.equal_energy) {  // upsampled increment at t: lerp of the knot pair at r / hp
+            const float l1 = __fmul_rn((float)(r0 + phs), inv_hp);
+            const float inc = __fmaf_rn(__fsub_rn(1.f, l1), xk, __fmul_rn(l1, xn));
             val = __fmul_rn(val, rsqrtf(inc));
           }
           v[phs] = val;
@@ -521,6 +523,8 @@ __global__ void __launch_bounds__(128) osc_dw_kernel(OscBwdParams q) {
   float* gs = smem;                       // gout[m0 - Z + i]
   float* hr = smem + p.plen;              // [os][kp12] reversed polyphase taps
   float* dws = hr + p.os * p.kp12;        // [Fw] partial sums
+  __shared__ unsigned long long soff_s[kPrefSplit];
+  if (threadIdx.x < 32 && !p.aten_cpu) span_offsets(p.totals + (size_t)blockIdx.y * kPrefSplit, soff_s);
   const int b = blockIdx.y, tid = threadIdx.x;
   const int m0 = blockIdx.x * kOscTile;
   const float* ph = p.phase + (size_t)b * p.Np;
@@ -561,7 +565,7 @@ __global__ void __launch_bounds__(128) osc_dw_kernel(OscBwdParams q) {
       const int t = mj * p.os + phs;
       if (mj >= p.n_out || t >= p.N) continue;
       KnotPhase kp;
-      kp.init(p, ph, b, mj, os_f, inv_os_f, pow2);
+      kp.init(p, ph, b, mj, os_f, inv_os_f, pow2, soff_s);
       const float wr = kp.wrapped(p, phs);
       const OscTaps o = osc_taps(p.Fw, p.P, wr, t, inv_yd, p.blocks);
       float g = gv[i];
@@ -663,10 +667,10 @@ GOLF_API int golf_glottal_osc_fwd(const float* phase, const float* w, const floa
   // v2: exact-phase mode, compile-time oversampling, table rows built in shared memory.  Needs a tile
   // (plus FIR halo) shorter than one table-row interval so three staged rows always suffice.
   const size_t sm2 = ((size_t)os * (fir_sw(p.plen) + 4 + p.kp12) + (size_t)kOscRows * P) * sizeof(float);
-  const bool v2 = g_osc_v2 && accumulate == 0 && (os == 1 || os == 2 || os == 4) && P % 4 == 0 && sm2 <= 200 * 1024 &&
+  const bool v2 = g_osc_v2 && accumulate == 0 && (os == 1 || os == 2 || os == 4) && P >= 4 && (P & (P - 1)) == 0 && sm2 <= 200 * 1024 &&
                   (int64_t)p.plen * os < (int64_t)p.hop_tab;
   if (v2) {
-    osc_knot_prefix_q64_kernel<<<B, 32 * kPrefSplit, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), totals, Np, L.hp,
+    osc_knot_prefix_q64_kernel<<<dim3(kPrefSplit / kPrefWarps, B), 32 * kPrefWarps, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), totals, Np, L.hp,
                                                             (float)os, span);
     GOLF_CHECK_LAUNCH();
     static bool attr = false;
@@ -687,7 +691,7 @@ GOLF_API int golf_glottal_osc_fwd(const float* phase, const float* w, const floa
   osc_tables_kernel<<<ceil_div(B * Fw * P, 256), 256, 0, st>>>(w, table, tables, B * Fw, n_tab, P);
   GOLF_CHECK_LAUNCH();
   if (accumulate == 0)
-    osc_knot_prefix_q64_kernel<<<B, 32 * kPrefSplit, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), totals, Np, L.hp,
+    osc_knot_prefix_q64_kernel<<<dim3(kPrefSplit / kPrefWarps, B), 32 * kPrefWarps, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), totals, Np, L.hp,
                                                             (float)os, span);
   else
     osc_knot_prefix_kernel<<<B, 256, 0, st>>>(phase, pref, Np, L.hp, os, 0);
@@ -723,7 +727,7 @@ GOLF_API int golf_glottal_osc_bwd_w(const float* gout, const float* phase, const
   const int span = ceil_div(Np, kPrefSplit);
   // the phase prefix is recomputed (cheap) rather than saved between forward and backward
   if (accumulate == 0)
-    osc_knot_prefix_q64_kernel<<<B, 32 * kPrefSplit, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), totals, Np, L.hp,
+    osc_knot_prefix_q64_kernel<<<dim3(kPrefSplit / kPrefWarps, B), 32 * kPrefWarps, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), totals, Np, L.hp,
                                                             (float)os, span);
   else
     osc_knot_prefix_kernel<<<B, 256, 0, st>>>(phase, pref, Np, L.hp, os, 0);

@@ -133,6 +133,9 @@ int golf_lpc_inverse_fwd(const float *y, int64_t y_stride, const float *a, float
 int golf_noise_fir_fwd(const float *ex, int64_t ex_stride, const float *kernel,
                        const float *window, const float *add, int64_t add_stride, float *y,
                        int B, int T, int F, int K, int hop, void *stream);
+/* 1 (default): packed-FP32 (fma.rn.f32x2) FIR kernels where they apply; 0: the scalar register
+ * tile.  Both sum each output's taps in the same order: results are bit-identical. */
+void golf_fir_set_variant(int x2);
 /* Adjoint w.r.t. the input (d_ex [B,T]) and the final taps (d_kernel [B,F,K]); either may be
  * NULL.  gy [B, n_blocks*hop]. */
 int golf_noise_fir_bwd(const float *gy, const float *ex, int64_t ex_stride,

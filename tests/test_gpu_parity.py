@@ -261,6 +261,31 @@ def test_noise_fir_ragged_sizes(G, oracle):
         assert y.shape == ref.shape and rel_rms(y, ref) < 1e-5
 
 
+def test_noise_fir_packed_fp32_variant_is_bit_identical(G, oracle):
+    """fma.rn.f32x2 kernel (16 outputs per lane, duplicated strip) vs the scalar register tile: every
+    output sums its taps in the same order, so the results must agree bit for bit -- across hops
+    (2, 4 and 1 blocks per warp; a hop that is not a multiple of 16), odd lengths, an `add` operand
+    whose rows are not 16-byte aligned, and the fused fftshift + window staging."""
+    from golf_b200 import _lib
+
+    g = torch.Generator().manual_seed(3)
+    cases = [(4801, 240, 510, 25, 0), (2000, 120, 254, 10, 1), (3000, 200, 510, 20, 0), (5000, 480, 510, 9, 3), (700, 100, 62, 9, 0)]
+    try:
+        for (Tn, H, K, Fr, off) in cases:
+            ex, kern = torch.randn(3, Tn, generator=g), 0.05 * torch.randn(3, Fr, K, generator=g)
+            add = torch.randn(3, Tn + 8, generator=g).to(DEV)[:, off : off + Tn]
+            outs = []
+            for mode in (0, 1):
+                _lib.lib().golf_fir_set_variant(mode)
+                outs.append((G.ltv_fir_blocks(*cu(ex, kern), H), G.ltv_fir_blocks(*cu(ex, kern), H, add=add),
+                             G.ltv_fir_blocks(*cu(ex, kern), H, window=torch.hann_window(K).to(DEV))))
+            for y0, y1 in zip(*outs):
+                assert torch.equal(y0, y1), (Tn, H, K, Fr)
+            assert rel_rms(outs[1][0], oracle.ltv_fir_blocks(ex, kern, H)) < 1e-5
+    finally:
+        _lib.lib().golf_fir_set_variant(1)
+
+
 def test_fir_gradients_match_autograd_of_the_oracle(G, oracle):
     """adjoints of the block FIR and the room FIR vs torch autograd through the CPU restatement"""
     g = torch.Generator().manual_seed(12)
