@@ -76,25 +76,18 @@ __global__ void __launch_bounds__(32) noise_fir_x2_kernel(const float* __restric
   const int p = (K - 1) / 2;
   const float* __restrict__ exb = ex + (size_t)b * ex_stride;
   const int start = k0 * hop - p;  // signal position of logical strip index 0
-  // staging is latency bound (a warp alone, every element one global load): all loads of a batch are
-  // issued before any is consumed, and they are branch free (clamped address + select) so that the
-  // compiler can actually batch them
-  constexpr int kStageU = 8;
-  for (int i0 = lane; i0 <= xs_len; i0 += 32 * kStageU) {
-    float v[kStageU];
-#pragma unroll
-    for (int u = 0; u < kStageU; ++u) {
-      const int pos = start + i0 + 32 * u;
-      const float raw = __ldg(exb + min(max(pos, 0), T - 1));
-      v[u] = (pos >= 0 && pos < T) ? raw : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < kStageU; ++u) {
-      const int i = i0 + 32 * u;  // the strips are allocated up to XS >= xs_len + 32*kStageU: no bound checks on xs0
-      xs0[fir_sw16(i)] = v[u];
-      if (i > 0) xs1[fir_sw16(i - 1)] = v[u];
-    }
+  // staging is latency bound (a warp alone, every element one global load).  The strip goes through
+  // cp.async (LDGSTS: global -> shared without a register in between, zero-filled outside the signal), all
+  // copies in flight at once; the taps (which need a multiply on the way) follow in register batches
+  // while the strip lands.
+  for (int i = lane; i <= xs_len; i += 32) {
+    const int pos = start + i;
+    const bool ok = pos >= 0 && pos < T;
+    const float* src = exb + min(max(pos, 0), T - 1);
+    if (i < xs_len) cp_async4(xs0 + fir_sw16(i), src, ok);
+    if (i > 0) cp_async4(xs1 + fir_sw16(i - 1), src, ok);
   }
+  constexpr int kStageU = 17;  // 510 taps: one batch per block
   // taps, duplicated: either final, or (window given) the raw irfft output: fftshift + windowing fused here
   const int nb = min(NBW, n_blocks - k0);
   for (int bi = 0; bi < nb; ++bi) {
@@ -118,6 +111,7 @@ __global__ void __launch_bounds__(32) noise_fir_x2_kernel(const float* __restric
       }
     }
   }
+  cp_async_wait_all();
   __syncwarp();
   const int bi = lane / TPB, c = lane - bi * TPB;
   if (bi >= nb) return;
@@ -178,6 +172,7 @@ __global__ void __launch_bounds__(128) room_fir_kernel(const float* __restrict__
   for (int i = 0; i < kR; ++i)
     if (t0 + r0 + i < T) ob[t0 + r0 + i] = acc[i];
 }
+
 
 
 // ---- adjoints of the block FIR --------------------------------------------------------
@@ -370,7 +365,7 @@ GOLF_API int golf_noise_fir_fwd(const float* ex, int64_t ex_stride, const float*
     const int TPB = ceil_div(hop, kR2), NBW = 32 / TPB;
     const int K20 = ceil_div(K, kTapStep) * kTapStep;
     const int xs_len = (NBW - 1) * hop + (TPB - 1) * kR2 + K20 + 24;  // last strip index a lane reads, + 1
-    const int XS = (int)align_up((size_t)xs_len + 1, 256);  // whole staging batches of 8 x 32 elements
+    const int XS = (int)align_up((size_t)xs_len + 1, 32);
     const size_t sm = ((size_t)2 * XS + (size_t)NBW * 2 * K20) * sizeof(float);
     if (sm <= 48 * 1024) {
       const bool aligned = ((uintptr_t)y % 16 == 0) && (!add || ((uintptr_t)add % 16 == 0 && add_stride % 4 == 0));
@@ -394,6 +389,7 @@ GOLF_API int golf_noise_fir_fwd(const float* ex, int64_t ex_stride, const float*
 
 GOLF_API int golf_room_fir_fwd(const float* x, const float* k, float* out, int B, int T, int n, void* stream) {
   if (!x || !k || !out || B <= 0 || T <= 0 || n <= 0) return GOLF_ERR_INVALID;
+  if (B > 65535) return GOLF_ERR_UNSUPPORTED;
   const int K12 = ceil_div(n + 1, 12) * 12;
   const int xs_len = (int)align_up((size_t)kRoomTile + K12 + 24, 4);
   const size_t sm = (size_t)(fir_sw(xs_len) + 4 + K12) * sizeof(float);

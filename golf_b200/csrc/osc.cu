@@ -93,12 +93,11 @@ __device__ __forceinline__ float div_os(float x, float os_f, float inv_os_f, boo
 // Default accumulation.  A phase in cycles only matters mod 1, so it is kept as an unsigned
 // Q0.64 fraction: adding increments is exact integer arithmetic that wraps exactly at one
 // cycle, is associative (any scan order gives the same bits) and needs no FP64 unit.
-__device__ __forceinline__ uint64_t q64_from_float(float x) {  // x in [0, 1): x * 2^64 (exact for x >= 2^-40)
+__device__ __forceinline__ uint64_t q64_from_float(float x) {  // x in [0, 1): x * 2^64, exact for x >= 2^-41
   const uint32_t u = __float_as_uint(x);
-  const int e = (int)((u >> 23) & 0xff);
-  const uint64_t m = (uint64_t)((u & 0x7fffffu) | (e ? 0x800000u : 0u));
-  const int sh = (e ? e : 1) - 86;  // value = m * 2^(e-150); times 2^64
-  return sh >= 0 ? (sh < 64 ? m << sh : 0ull) : (sh > -64 ? m >> (-sh) : 0ull);
+  const int sh = (int)((u >> 23) & 0xff) - 86;  // value = m * 2^(e-150); times 2^64
+  const uint64_t m = (uint64_t)((u & 0x7fffffu) | 0x800000u);
+  return (sh >= 0 && sh < 64) ? m << sh : 0ull;  // increments below 2^-41 cycles per sample (and zero) flush to zero
 }
 // increment sum of knot interval k: hp*X_k + (X_{k+1}-X_k)(hp-1)/2   (mod 2^64)
 __device__ __forceinline__ uint64_t q64_interval(uint64_t xk, uint64_t xn, int hp) {
@@ -428,18 +427,34 @@ __global__ void __launch_bounds__(128) osc_flow_v2_kernel(OscParams p, const flo
   const bool hp_pow2 = (p.hp & (p.hp - 1)) == 0;
   const float inv_hop_tab = 1.f / (float)p.hop_tab, inv_hp = 1.f / (float)p.hp, inv_span = 1.f / (float)p.span;
   const unsigned long long* __restrict__ prefb = reinterpret_cast<const unsigned long long*>(p.pref) + (size_t)b * p.Np;
+  // the knot pair and its prefix are fetched one iteration ahead: the loop is otherwise bound by the
+  // latency of these three global loads
+  struct Knot {
+    int k;
+    float fk, fn;
+    unsigned long long pk;
+  };
+  auto fetch = [&](int j) {
+    Knot q;
+    const int mj = min(max(m0 - Z + j, 0), p.n_out - 1);
+    q.k = min(ph1 ? mj : mj / phase_hop, p.Np - 1);
+    q.fk = __ldg(ph + q.k), q.fn = __ldg(ph + min(q.k + 1, p.Np - 1));
+    q.pk = __ldg(prefb + q.k);
+    return q;
+  };
+  Knot nx = fetch(min(tid, p.plen - 1));
   for (int j = tid; j < p.plen; j += blockDim.x) {
     const int mj = m0 - Z + j;
     const bool in = mj >= 0 && (int64_t)mj * OS < p.N;
+    const Knot kn = nx;
+    nx = fetch(min(j + (int)blockDim.x, p.plen - 1));
     float v[OS];
 #pragma unroll
     for (int phs = 0; phs < OS; ++phs) v[phs] = 0.f;
     if (in) {
-      int k = ph1 ? mj : mj / phase_hop;
-      k = min(k, p.Np - 1);
-      const int k1 = min(k + 1, p.Np - 1);
+      const int k = kn.k;
       const int r0 = ph1 ? 0 : (mj - k * phase_hop) * OS;
-      const float xk = div_os(__ldg(ph + k), os_f, inv_os_f, pow2), xn = div_os(__ldg(ph + k1), os_f, inv_os_f, pow2);
+      const float xk = div_os(kn.fk, os_f, inv_os_f, pow2), xn = div_os(kn.fn, os_f, inv_os_f, pow2);
       const uint64_t qx = q64_from_float(xk), qn = q64_from_float(xn);
       // slope term per r(r+1): (x_{k+1}-x_k)/(2hp)
       const int64_t dq = (int64_t)(qn - qx);
@@ -447,42 +462,52 @@ __global__ void __launch_bounds__(128) osc_flow_v2_kernel(OscParams p, const flo
       int sp = (int)((float)k * inv_span);  // k / span without the integer division
       sp -= (sp * p.span > k) ? 1 : 0;
       sp += ((sp + 1) * p.span <= k) ? 1 : 0;
-      const uint64_t qp = prefb[k] + soff_s[sp];
+      const uint64_t qp = kn.pk + soff_s[sp];
       // phi(r) = qp + (r+1) qx + qq r (r+1);  phi(r+1) - phi(r) = qx + 2 qq (r+1)
-      uint64_t phi = qp + (uint64_t)(r0 + 1) * qx + (uint64_t)(qq * (int64_t)(r0 * (r0 + 1)));
-      uint64_t d = qx + (uint64_t)(2 * qq * (int64_t)(r0 + 1));
       const uint64_t dd = (uint64_t)(2 * qq);
+      uint64_t phi = qp + qx, d = qx + dd;
+      if (!ph1) {
+        phi = qp + (uint64_t)(r0 + 1) * qx + (uint64_t)(qq * (int64_t)(r0 * (r0 + 1)));
+        d = qx + (uint64_t)(2 * qq * (int64_t)(r0 + 1));
+      }
       const int t0 = mj * OS;
       const int trel = t0 - trow0;
-#pragma unroll
-      for (int phs = 0; phs < OS; ++phs) {
-        if (t0 + phs < p.N) {
-          // column: top lgP bits of the phase; fraction: the next 32 bits (rounded to float)
-          const uint32_t hi = (uint32_t)(phi >> 32), lo = (uint32_t)phi;
-          const int c0 = (int)(hi >> (32 - lgP));
-          const int c1 = (c0 + 1) & (P - 1);  // column P wraps to column 0
-          const float fx = __fmul_rn(__uint2float_rn(__funnelshift_l(lo, hi, lgP)), 2.3283064365386963e-10f);  // * 2^-32
-          // row: t / hop_tab relative to the first staged row (0 or 1), fraction (t % hop_tab) / hop_tab
-          const int tr = trel + phs;
-          const bool up = tr >= p.hop_tab;
-          const float fy = __fmul_rn((float)(up ? tr - p.hop_tab : tr), inv_hop_tab);
-          const float* r0p = rows + (up ? P : 0);
-          const float* r1p = r0p + P;
-          const float t00 = r0p[c0], t01 = r0p[c1], t10 = r1p[c0], t11 = r1p[c1];
-          const float gx1 = __fsub_rn(1.f, fx), gy1 = __fsub_rn(1.f, fy);
-          float val = __fmul_rn(t00, __fmul_rn(gx1, gy1));
-          val = __fmaf_rn(t01, __fmul_rn(fx, gy1), val);
-          val = __fmaf_rn(t10, __fmul_rn(gx1, fy), val);
-          val = __fmaf_rn(t11, __fmul_rn(fx, fy), val);
-          if (p.equal_energy) {  // upsampled increment at t: lerp of the knot pair at r / hp
-            const float l1 = __fmul_rn((float)(r0 + phs), inv_hp);
-            const float inc = __fmaf_rn(__fsub_rn(1.f, l1), xk, __fmul_rn(l1, xn));
-            val = __fmul_rn(val, rsqrtf(inc));
-          }
-          v[phs] = val;
+      auto sample = [&](int phs) -> float {
+        // column: top lgP bits of the phase; fraction: the next 32 bits (rounded to float)
+        const uint32_t hi = (uint32_t)(phi >> 32), lo = (uint32_t)phi;
+        const int c0 = (int)(hi >> (32 - lgP));
+        const int c1 = (c0 + 1) & (P - 1);  // column P wraps to column 0
+        const float fx = __fmul_rn(__uint2float_rn(__funnelshift_l(lo, hi, lgP)), 2.3283064365386963e-10f);  // * 2^-32
+        // row: t / hop_tab relative to the first staged row (0 or 1), fraction (t % hop_tab) / hop_tab
+        const int tr = trel + phs;
+        const bool up = tr >= p.hop_tab;
+        const float fy = __fmul_rn((float)(up ? tr - p.hop_tab : tr), inv_hop_tab);
+        const float* r0p = rows + (up ? P : 0);
+        const float* r1p = r0p + P;
+        const float t00 = r0p[c0], t01 = r0p[c1], t10 = r1p[c0], t11 = r1p[c1];
+        const float gx1 = __fsub_rn(1.f, fx), gy1 = __fsub_rn(1.f, fy);
+        float val = __fmul_rn(t00, __fmul_rn(gx1, gy1));
+        val = __fmaf_rn(t01, __fmul_rn(fx, gy1), val);
+        val = __fmaf_rn(t10, __fmul_rn(gx1, fy), val);
+        val = __fmaf_rn(t11, __fmul_rn(fx, fy), val);
+        if (p.equal_energy) {  // upsampled increment at t: lerp of the knot pair at r / hp
+          const float l1 = __fmul_rn((float)(r0 + phs), inv_hp);
+          const float inc = __fmaf_rn(__fsub_rn(1.f, l1), xk, __fmul_rn(l1, xn));
+          float rs;
+          asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(inc));  // one MUFU.RSQ, within 2 ulp of 1/sqrt
+          val = __fmul_rn(val, rs);
         }
         phi += d;
         d += dd;
+        return val;
+      };
+      if (t0 + OS <= p.N) {  // all `os` samples exist (every index but possibly the last): no per-sample branch
+#pragma unroll
+        for (int phs = 0; phs < OS; ++phs) v[phs] = sample(phs);
+      } else {
+#pragma unroll
+        for (int phs = 0; phs < OS; ++phs)
+          if (t0 + phs < p.N) v[phs] = sample(phs);
       }
     }
     const int js = fir_sw(j);
