@@ -19,6 +19,7 @@ _SIGS = {
     "golf_strerror": (ctypes.c_char_p, [c_int]),
     "golf_last_cuda_error": (c_int, []),
     "golf_launch_count": (c_uint64, []),
+    "golf_set_pdl": (None, [c_int]),
     "golf_lpc_ss_workspace_bytes": (c_size_t, [c_int] * 5),
     "golf_lpc_ss_set_refine_tolerance": (None, [c_float]),
     "golf_lpc_ss_get_refine_tolerance": (c_float, []),

@@ -6,6 +6,7 @@
 namespace golf {
 static std::atomic<uint64_t> g_launches{0};
 static thread_local int g_last_cuda = 0;
+int g_pdl = 1;
 
 void note_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 int note_cuda(cudaError_t e) {
@@ -30,3 +31,5 @@ GOLF_API const char* golf_strerror(int code) {
 
 GOLF_API int golf_last_cuda_error(void) { return golf::g_last_cuda; }
 GOLF_API uint64_t golf_launch_count(void) { return golf::g_launches.load(std::memory_order_relaxed); }
+
+GOLF_API void golf_set_pdl(int on) { golf::g_pdl = on ? 1 : 0; }

@@ -26,6 +26,30 @@ int note_cuda(cudaError_t e);  // records e, returns GOLF_ERR_CUDA if e != cudaS
     if (_e != cudaSuccess) return golf::note_cuda(_e);   \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may have its CTAs scheduled as
+// soon as every CTA of the previous kernel in the stream has called pdl_trigger() (or exited); it runs
+// whatever does not depend on that kernel and blocks in pdl_wait() until it has completed and its writes
+// are visible.  Both are no-ops in a kernel launched the ordinary way.  Used for ONE edge: knot prefix ->
+// flow kernel, whose long prologue (polyphase taps, three interpolated table rows) then runs beside the
+// scan.  Measured on the other edges of the decoder chain (wait at the top of the dependent kernel) it
+// gained nothing: early-launched CTAs only hold registers while they wait (profiles/README.md).
+// golf_set_pdl(0) turns the attribute off.
+extern int g_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(32 * kPrefWarps) osc_knot_prefix_q64_kernel(co
                                                                               unsigned long long* __restrict__ pref,
                                                                               unsigned long long* __restrict__ tot, int Np,
                                                                               int hp, float os_f, int span) {
+  pdl_trigger();  // the flow kernel's prologue (taps, table rows) runs beside this scan
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = blockIdx.x * kPrefWarps + (threadIdx.x >> 5);
   const float* __restrict__ ph = phase + (size_t)b * Np;
   unsigned long long* pb = pref + (size_t)b * Np;
@@ -379,7 +380,6 @@ __global__ void __launch_bounds__(128) osc_flow_v2_kernel(OscParams p, const flo
   float* hp_ = vp + OS * plen_sw;           // [OS][kp12] polyphase taps
   float* rows = hp_ + OS * p.kp12;          // [kOscRows][P] interpolated table rows ybase .. ybase+2
   __shared__ unsigned long long soff_s[kPrefSplit];
-  if (threadIdx.x < 32 && !p.aten_cpu) span_offsets(p.totals + (size_t)blockIdx.y * kPrefSplit, soff_s);
   const int b = blockIdx.y, tid = threadIdx.x;
   const int m0 = blockIdx.x * kOscTile;
   const float* __restrict__ ph = p.phase + (size_t)b * p.Np;
@@ -418,6 +418,8 @@ __global__ void __launch_bounds__(128) osc_flow_v2_kernel(OscParams p, const flo
       dst[c] = o;
     }
   }
+  pdl_wait();  // everything above read launch inputs only; the knot prefix comes from the previous kernel
+  if (threadIdx.x < 32) span_offsets(p.totals + (size_t)blockIdx.y * kPrefSplit, soff_s);
   __syncthreads();
   // ---- flow: strip index j <-> output-rate index mj = m0 - Z + j, samples t = mj*OS + phs
   const int phase_hop = p.hp / OS;
@@ -695,8 +697,8 @@ GOLF_API int golf_glottal_osc_fwd(const float* phase, const float* w, const floa
   const bool v2 = g_osc_v2 && accumulate == 0 && (os == 1 || os == 2 || os == 4) && P >= 4 && (P & (P - 1)) == 0 && sm2 <= 200 * 1024 &&
                   (int64_t)p.plen * os < (int64_t)p.hop_tab;
   if (v2) {
-    osc_knot_prefix_q64_kernel<<<dim3(kPrefSplit / kPrefWarps, B), 32 * kPrefWarps, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), totals, Np, L.hp,
-                                                            (float)os, span);
+    osc_knot_prefix_q64_kernel<<<dim3(kPrefSplit / kPrefWarps, B), 32 * kPrefWarps, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), totals, Np,
+                                                                                          L.hp, (float)os, span);
     GOLF_CHECK_LAUNCH();
     static bool attr = false;
     if (!attr) {
@@ -706,9 +708,9 @@ GOLF_API int golf_glottal_osc_fwd(const float* phase, const float* w, const floa
       attr = true;
     }
     switch (os) {
-      case 1: osc_flow_v2_kernel<1><<<grid, 128, sm2, st>>>(p, w, table, n_tab); break;
-      case 2: osc_flow_v2_kernel<2><<<grid, 128, sm2, st>>>(p, w, table, n_tab); break;
-      default: osc_flow_v2_kernel<4><<<grid, 128, sm2, st>>>(p, w, table, n_tab); break;
+      case 1: GOLF_CUDA(launch_pdl(osc_flow_v2_kernel<1>, grid, dim3(128), sm2, st, p, w, table, n_tab)); break;
+      case 2: GOLF_CUDA(launch_pdl(osc_flow_v2_kernel<2>, grid, dim3(128), sm2, st, p, w, table, n_tab)); break;
+      default: GOLF_CUDA(launch_pdl(osc_flow_v2_kernel<4>, grid, dim3(128), sm2, st, p, w, table, n_tab)); break;
     }
     GOLF_CHECK_LAUNCH();
     return GOLF_OK;

@@ -187,6 +187,48 @@ class LTVZeroPhaseFIRFilter(LTVFilterInterface):
         return like(ex, y, hop_of(ex))
 
 
+class LTVZeroPhaseFIRFilterPrecise(LTVZeroPhaseFIRFilter):
+    """Sample-wise twin of LTVZeroPhaseFIRFilter (models/filters.py:286-337): the K-tap kernel applied at
+    sample t is the linear interpolation (AudioTensor.reduce_hop_length) of the two frame kernels around t,
+
+        y[t] = sum_j xpad[t + j] * (l0(t) k_f[j] + l1(t) k_{f+1}[j]),   f = t // hop,
+
+    output length min(T, (F-1)*hop + 1).  The filter is linear in the kernel, so this is
+    l0(t) * (block FIR with k_f)(t) + l1(t) * (block FIR with k_{f+1})(t): two launches of the block-FIR
+    kernel (golf_noise_fir_fwd) over the same input, one with the kernel tensor shifted by a frame, and an
+    element-wise blend -- the [B, T, K] interpolated-kernel tensor of the reference (K floats per SAMPLE)
+    never exists.  Differentiable through the block FIR's adjoints."""
+
+    def __init__(self, window: str, n_mag: int = None):
+        super().__init__(window, "direct", n_mag)
+
+    def forward(self, ex, log_mag):
+        hop = hop_of(log_mag) // hop_of(ex)
+        lm, x = plain(log_mag), plain(ex)
+        assert x.ndim == 2 and lm.ndim == 3
+        B, T = x.shape
+        Fr = lm.shape[1]
+        kernel = self.windowing(self.get_zero_phase_fir(lm))  # [B, F, K] frame rate (torch / cuFFT)
+        K = kernel.shape[-1]
+        n_out = min(T, (Fr - 1) * hop + 1)
+        n_blk = -(-n_out // hop)
+        # the block FIR pads (K-1)//2 on both sides and emits whole blocks: extend the input with zeros (the
+        # reference's right padding) so that blocks 0 .. n_blk-1 exist
+        p = (K - 1) // 2
+        need = (n_blk - 1) * hop + (K + hop - 1) - 2 * p
+        xe = F.pad(x, (0, max(need - T, 0)))
+        k0 = kernel[:, :n_blk]
+        k1 = kernel[:, torch.arange(1, n_blk + 1, device=kernel.device).clamp(max=Fr - 1)]
+        y0 = G.ltv_fir_blocks(xe, k0.contiguous(), hop)[:, :n_out]
+        y1 = G.ltv_fir_blocks(xe, k1.contiguous(), hop)[:, :n_out]
+        # ATen's upsample weights at sample t (align_corners=True): src = scale * t, l1 = src - floor(src)
+        t = torch.arange(n_out, device=x.device, dtype=torch.float32)
+        scale = torch.tensor((Fr - 1) / max((Fr - 1) * hop, 1), dtype=torch.float32, device=x.device)
+        blk = torch.div(torch.arange(n_out, device=x.device), hop, rounding_mode="floor").to(torch.float32)
+        l1 = (scale * t - blk).clamp(0.0, 1.0)
+        return like(ex, (1.0 - l1) * y0 + l1 * y1, hop_of(ex))
+
+
 class LTIAcousticFilter(FilterInterface):
     """Learned room response: out = ex + conv(ex delayed, kernel) with `length-1` free taps
     (parameter name `kernel`, as in the checkpoints)."""
@@ -214,6 +256,10 @@ def convert2samplewise(config: dict) -> dict:
             config["class_path"] = value.rsplit(".", 1)[0] + ".LTVMinimumPhaseFilterPrecise"
             for k in ("window", "window_length", "centred"):
                 config.get("init_args", {}).pop(k, None)
+            return config
+        if key == "class_path" and value.endswith(".LTVZeroPhaseFIRFilter"):
+            config["class_path"] = value + "Precise"
+            config.get("init_args", {}).pop("conv_method", None)
             return config
         if isinstance(value, dict):
             config[key] = convert2samplewise(value)

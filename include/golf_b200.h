@@ -49,6 +49,10 @@ int golf_abi_version(void);
 const char *golf_strerror(int code);
 /* last cudaError_t seen by this library on the calling thread (0 = none) */
 int golf_last_cuda_error(void);
+/* 1 (default): the oscillator's flow kernel is launched with programmatic stream serialization
+ * (its prologue -- taps, table rows -- runs beside the knot-prefix scan and it waits on-device for the
+ * scan); 0: ordinary launches.  Results are identical. */
+void golf_set_pdl(int on);
 /* number of kernel launches issued by this library since load (all threads) */
 uint64_t golf_launch_count(void);
 

@@ -292,6 +292,22 @@ def noise_fir(ex, log_mag, hop: int, window: str = "hanning") -> torch.Tensor:
     return ltv_fir_blocks(ex, zero_phase_fir(_f32(log_mag), window), hop)
 
 
+def noise_fir_precise(ex: torch.Tensor, log_mag: torch.Tensor, hop: int, window: str = "hanning") -> torch.Tensor:
+    """LTVZeroPhaseFIRFilterPrecise.forward, models/filters.py:308-337: the frame kernels are upsampled
+    to sample rate (reduce_hop_length -> F.interpolate linear, align_corners=True, audiotensor.py:11-17),
+    the input is padded (K-1)//2 left / K-1-(K-1)//2 right and unfolded into K-windows, and every sample is
+    the dot product of its window with its own kernel; the mixed-rate matmul truncates to the shorter
+    operand: min(T, (F-1)*hop + 1) samples."""
+    kernel = zero_phase_fir(log_mag if log_mag.requires_grad else _f32(log_mag), window)  # [B, F, K]
+    B, Fr, K = kernel.shape
+    n_up = (Fr - 1) * hop + 1
+    up = F.interpolate(kernel.transpose(1, 2), n_up, mode="linear", align_corners=True).transpose(1, 2)  # [B, n_up, K]
+    pl = (K - 1) // 2
+    win = F.pad(ex, (pl, K - 1 - pl)).unfold(1, K, 1)  # [B, T, K]
+    n = min(win.shape[1], n_up)
+    return (win[:, :n] * up[:, :n]).sum(-1)
+
+
 # ------------------------------------------------------------------ room FIR (a18)
 def room_fir(x: torch.Tensor, k: torch.Tensor) -> torch.Tensor:
     """LTIAcousticFilter.forward, models/filters.py:443-450:

@@ -191,6 +191,40 @@ def test_concurrent_decoder_path_same_arithmetic():
         assert torch.equal(base, v), k
 
 
+def test_programmatic_dependent_launch_same_results():
+    """PDL only changes WHEN the kernels of the chain may start (each waits on-device for its
+    predecessor): eager and CUDA-graph replays of the concurrent inference path give the same bits with
+    the attribute on and off, for the same noise seed."""
+    from golf_b200 import _lib
+    from golf_b200.graphs import GraphedSynth
+
+    g = golden("stages_ss")
+    dec = build_decoder("ss", g)
+    params = _ss_params(g)
+    outs = {}
+    try:
+        for on in (0, 1):
+            _lib.lib().golf_set_pdl(on)
+            with torch.no_grad():
+                for rep in range(3):  # back-to-back calls: the chain of one call follows the chain of the previous one
+                    torch.manual_seed(7)
+                    outs[(on, "eager", rep)] = dec(**params).as_tensor().clone()
+                graphed = GraphedSynth(dec, params)
+                for rep in range(3):
+                    outs[(on, "graph", rep)] = graphed(**params).as_tensor().clone()
+    finally:
+        _lib.lib().golf_set_pdl(1)
+    torch.cuda.synchronize()
+    for rep in range(3):
+        assert torch.equal(outs[(0, "eager", rep)], outs[(1, "eager", rep)]), rep
+        assert torch.equal(outs[(0, "eager", 0)], outs[(1, "eager", rep)]), rep
+    for on in (0, 1):  # graph replays draw fresh noise: same deterministic part -> same rms to a few percent
+        for rep in range(3):
+            o = outs[(on, "graph", rep)]
+            assert torch.isfinite(o).all()
+            assert abs(float(o.pow(2).mean().sqrt()) / float(outs[(0, "eager", 0)].pow(2).mean().sqrt()) - 1) < 0.05
+
+
 def test_pipelined_synth_matches_graph_replay():
     """H2D / replay / D2H pipeline over 3 slots returns, per step, what a plain replay returns"""
     from golf_b200.graphs import GraphedSynth, PipelinedSynth
@@ -245,3 +279,27 @@ def test_solver_variants_agree():
     for k, v in outs.items():
         assert rel_rms(v, ref) < REL_TOL, k
         assert rel_rms(v, outs[0]) < 1e-5, k
+
+
+def test_precise_zero_phase_fir_reference_golden():
+    """drop-in LTVZeroPhaseFIRFilterPrecise vs the reference module (golden), forward and autograd"""
+    from golf_b200 import filters
+    from golf_b200.audiotensor import AudioTensor
+
+    g = golden("fir_precise")
+    H = int(g["hop"])
+    f = filters.LTVZeroPhaseFIRFilterPrecise("hanning", n_mag=g["log_mag"].shape[-1]).to(DEV)
+    lm = T(g["log_mag"]).to(DEV)
+    for tag in ("long", "short"):
+        with torch.no_grad():
+            y = f(AudioTensor(T(g[f"ex_{tag}"]).to(DEV)), AudioTensor(lm, hop_length=H))
+        assert y.hop_length == 1 and tuple(y.shape) == g[f"y_{tag}"].shape
+        assert rel_rms(y.as_tensor(), T(g[f"y_{tag}"])) < 1e-5
+    ex = T(g["ex_long"]).to(DEV).requires_grad_()
+    lmg = lm.clone().requires_grad_()
+    y = f(AudioTensor(ex), AudioTensor(lmg, hop_length=H)).as_tensor()
+    d_ex, d_lm = torch.autograd.grad(y, (ex, lmg), T(g["up"]).to(DEV))
+    assert rel_rms(d_ex, T(g["d_ex"])) < 1e-5 and rel_rms(d_lm.flatten(1), T(g["d_log_mag"]).flatten(1)) < 1e-4
+    cfg = {"class_path": "golf_b200.filters.LTVZeroPhaseFIRFilter", "init_args": {"window": "hanning", "conv_method": "direct", "n_mag": 256}}
+    assert filters.convert2samplewise({"noise_filter": cfg})["noise_filter"] == {
+        "class_path": "golf_b200.filters.LTVZeroPhaseFIRFilterPrecise", "init_args": {"window": "hanning", "n_mag": 256}}

@@ -144,3 +144,14 @@ def test_oracle_against_live_reference(oracle, reference):
         room = LTIAcousticFilter(128, "fft")
         room.kernel.data = torch.randn(127, generator=g) * 0.05
         assert rel_rms(oracle.room_fir(ex, room.kernel.data), room(AudioTensor(ex)).as_tensor()) < 1e-6
+
+
+def test_precise_fir_oracle_matches_reference_golden(oracle):
+    """LTVZeroPhaseFIRFilterPrecise (models/filters.py:286-337): restatement vs the reference module's own
+    output (tests/golden/make_golden_precise_fir.py), long and short inputs"""
+    g = golden("fir_precise")
+    H = int(g["hop"])
+    for tag in ("long", "short"):
+        y = oracle.noise_fir_precise(T(g[f"ex_{tag}"]), T(g["log_mag"]), H)
+        assert y.shape == g[f"y_{tag}"].shape
+        assert rel_rms(y, T(g[f"y_{tag}"])) < 2e-6
