@@ -13,6 +13,8 @@
 // (warp broadcast) and one LDS.128 of new input for 32 FMAs.  Input segment and taps are
 // staged once per CTA in shared memory (coalesced), so HBM sees each sample once:
 // algorithmic bytes per output sample = 4 (in) + 4 (out) + 4*K/hop (kernels) (+4 `add`).
+#include <algorithm>
+
 #include "fir_tile.cuh"
 
 namespace golf {
@@ -291,24 +293,126 @@ __global__ void __launch_bounds__(32) room_fir_dk_kernel(const float* __restrict
   float* gs = smem + xs_len;
   const int b = blockIdx.y, tid = threadIdx.x;
   const int t0 = blockIdx.x * tile_len;
-  const float* xb = x + (size_t)b * T;
-  const float* gb = gy + (size_t)b * T;
-  for (int i = tid; i < xs_len; i += blockDim.x) {
-    const int pos = t0 - n + i;
-    xs[i] = (pos >= 0 && pos < T) ? xb[pos] : 0.f;
+  const float* __restrict__ xb = x + (size_t)b * T;
+  const float* __restrict__ gb = gy + (size_t)b * T;
+  // a lone warp per CTA: stage with batched, branch-free loads (the loop was bound by one global-load
+  // latency per 32 elements)
+  constexpr int U = 8;
+  for (int i0 = tid; i0 < xs_len; i0 += 32 * U) {
+    float v[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int pos = t0 - n + i0 + 32 * q;
+      const float raw = __ldg(xb + min(max(pos, 0), T - 1));
+      v[q] = (pos >= 0 && pos < T) ? raw : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < U; ++q)
+      if (i0 + 32 * q < xs_len) xs[i0 + 32 * q] = v[q];
   }
-  for (int i = tid; i < G12; i += blockDim.x) gs[i] = (i < tile_len && t0 + i < T) ? gb[t0 + i] : 0.f;
+  for (int i0 = tid; i0 < G12; i0 += 32 * U) {
+    float v[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int i = i0 + 32 * q;
+      const float raw = __ldg(gb + min(t0 + i, T - 1));
+      v[q] = (i < tile_len && t0 + i < T) ? raw : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < U; ++q)
+      if (i0 + 32 * q < G12) gs[i0 + 32 * q] = v[q];
+  }
   __syncthreads();
-  // d_k[j] += sum_r gs[r] * xs[r + j]
-  for (int j0 = tid * kR; j0 < n; j0 += blockDim.x * kR) {
+  // d_k[j] += sum_r gs[r] * xs[r + j].  With n <= 128 taps only 16 lanes own a group of 8 taps: the two
+  // half-warps then split the tile's samples (G12 / 2 each, a multiple of 12)
+  const int groups = (n + kR - 1) / kR;
+  const bool split = groups <= 16 && (G12 / 2) % 12 == 0;
+  const int h = split ? tid / 16 : 0, q = split ? tid % 16 : tid;
+  const int span = split ? G12 / 2 : G12;
+  for (int j0 = q * kR; j0 < n; j0 += (split ? 16 : 32) * kR) {
     float acc[kR];
 #pragma unroll
     for (int i = 0; i < kR; ++i) acc[i] = 0.f;
-    fir_tile8(xs + j0, gs, G12, acc);
+    fir_tile8(xs + j0 + h * span, gs + h * span, span, acc);
 #pragma unroll
     for (int i = 0; i < kR; ++i)
       if (j0 + i < n) atomicAdd(d_k + j0 + i, acc[i]);
   }
+}
+
+// Persistent version for n <= 128 taps.  The kernel above issues one atomicAdd per (CTA, tap): at B = 32 x 2 s
+// that is ~2000 float atomics on each of 127 addresses, and same-address atomics serialise in L2 (~40 ns
+// each: 97 us, IPC 0.3).  Here a grid of one CTA per SM walks the (tile, utterance) tasks, four warps per CTA
+// each with its own strip, partial sums stay in registers across tasks, the half-warps and the warps are
+// combined through shuffles / shared memory, and each CTA issues ONE atomic per tap (148 per address).
+constexpr int kDkWarps = 4;
+__global__ void __launch_bounds__(32 * kDkWarps) room_fir_dk2_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                                                                     float* __restrict__ d_k, int B, int T, int n, int tile_len,
+                                                                     int G12, int xs_len, int n_tiles) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* xs = smem + (size_t)warp * (xs_len + G12);
+  float* gs = xs + xs_len;
+  float* red = smem + (size_t)kDkWarps * (xs_len + G12);  // [kDkWarps][128]
+  const int h = lane / 16, q = lane % 16, span = G12 / 2, j0 = q * kR;
+  float acc[kR];
+#pragma unroll
+  for (int i = 0; i < kR; ++i) acc[i] = 0.f;
+  const int n_tasks = n_tiles * B;
+  constexpr int U = 8;
+  for (int task = blockIdx.x * kDkWarps + warp; task < n_tasks; task += gridDim.x * kDkWarps) {
+    const int b = task / n_tiles, t0 = (task % n_tiles) * tile_len;
+    const float* __restrict__ xb = x + (size_t)b * T;
+    const float* __restrict__ gb = gy + (size_t)b * T;
+    __syncwarp();
+    for (int i0 = lane; i0 < xs_len; i0 += 32 * U) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pos = t0 - n + i0 + 32 * u;
+        const float raw = __ldg(xb + min(max(pos, 0), T - 1));
+        v[u] = (pos >= 0 && pos < T) ? raw : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i0 + 32 * u < xs_len) xs[i0 + 32 * u] = v[u];
+    }
+    for (int i0 = lane; i0 < G12; i0 += 32 * U) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + 32 * u;
+        const float raw = __ldg(gb + min(t0 + i, T - 1));
+        v[u] = (i < tile_len && t0 + i < T) ? raw : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i0 + 32 * u < G12) gs[i0 + 32 * u] = v[u];
+    }
+    __syncwarp();
+    if (j0 < n) fir_tile8(xs + j0 + h * span, gs + h * span, span, acc);  // acc[i] += sum_r gs[r] xs[r + j0 + i]
+  }
+#pragma unroll
+  for (int i = 0; i < kR; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  if (h == 0) {
+#pragma unroll
+    for (int i = 0; i < kR; ++i) red[warp * 128 + j0 + i] = acc[i];
+  }
+  __syncthreads();
+  const int j = threadIdx.x;
+  if (j < n) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < kDkWarps; ++w) sum += red[w * 128 + j];
+    atomicAdd(d_k + j, sum);
+  }
+}
+
+// ---- FIR design, first step: spectrum = exp(log_mag) + 0j (models/filters.py:295-296) -----------------
+// One pass instead of torch's exp kernel + real->complex copy; expf is the same libdevice routine ATen calls.
+__global__ void exp_to_complex_kernel(const float* __restrict__ x, float2* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_float2(expf(x[i]), 0.f);
 }
 
 // ---- linear upsample -----------------------------------------------------------------
@@ -457,9 +561,31 @@ GOLF_API int golf_room_fir_bwd(const float* gy, const float* x, const float* k, 
     const int xs_len = (int)align_up((size_t)ceil_div(n, 32 * kR) * 32 * kR + G12 + 24, 4);
     const size_t sm = (size_t)(xs_len + G12) * sizeof(float);
     if (sm > 48 * 1024) return GOLF_ERR_UNSUPPORTED;
+    if (n <= 128) {
+      const int tl = 768, g12 = 768;  // two half-warp spans of 384 = 32 * 12 samples
+      const int xl = (int)align_up((size_t)128 + g12 + 24, 4);
+      const size_t sm2 = ((size_t)kDkWarps * (xl + g12) + kDkWarps * 128) * sizeof(float);
+      const int n_tiles = ceil_div(T, tl);
+      int sms = 148;
+      {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+      }
+      const int grid = std::min(sms, ceil_div(n_tiles * B, kDkWarps));
+      room_fir_dk2_kernel<<<grid, 32 * kDkWarps, sm2, st>>>(gy, x, d_k, B, T, n, tl, g12, xl, n_tiles);
+      GOLF_CHECK_LAUNCH();
+      return GOLF_OK;
+    }
     room_fir_dk_kernel<<<dim3(ceil_div(T, tile_len), B), 32, sm, st>>>(gy, x, d_k, T, n, tile_len, G12, xs_len);
     GOLF_CHECK_LAUNCH();
   }
+  return GOLF_OK;
+}
+
+GOLF_API int golf_exp_to_complex(const float* x, float* out_interleaved, int64_t n, void* stream) {
+  if (!x || !out_interleaved || n <= 0) return GOLF_ERR_INVALID;
+  exp_to_complex_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<float2*>(out_interleaved), n);
+  GOLF_CHECK_LAUNCH();
   return GOLF_OK;
 }
 

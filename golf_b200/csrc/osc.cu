@@ -623,6 +623,136 @@ __global__ void __launch_bounds__(128) osc_dw_kernel(OscBwdParams q) {
     if (dws[i] != 0.f) atomicAdd(q.d_w + (size_t)b * p.Fw + i, dws[i] * (float)(q.n_tab - 1));
 }
 
+// v2 of the weight adjoint (exact-phase mode, compile-time oversampling, power-of-two tables): the same
+// restructuring as osc_flow_v2_kernel.  The slope rows T[lo+1] - T[lo] of the (at most three) control frames a
+// tile can touch are staged in shared memory, so the four bilinear taps are LDS instead of eight dependent
+// L2 gathers per sample; table coordinates come from the integers (column = top bits of the Q0.64 phase,
+// row = t / hop_tab by one compare); the knot setup is done once per output index and the phase advances by
+// integer increments over its `os` samples; the three per-row sums are reduced by shuffles, one shared-memory
+// atomic per warp and row, one global atomic per CTA and row.
+template <int OS>
+__global__ void __launch_bounds__(128) osc_dw_v2_kernel(OscBwdParams q) {
+  const OscParams& p = q.f;
+  extern __shared__ __align__(16) float smem[];
+  float* gs = smem;                       // gout[m0 - Z + i]
+  float* hr = smem + p.plen;              // [OS][kp12] reversed polyphase taps
+  float* slope = hr + OS * p.kp12;        // [kOscRows][P] T[lo+1] - T[lo] of control frames ybase .. ybase+2
+  __shared__ unsigned long long soff_s[kPrefSplit];
+  __shared__ float dws[kOscRows];
+  if (threadIdx.x < 32) span_offsets(p.totals + (size_t)blockIdx.y * kPrefSplit, soff_s);
+  const int b = blockIdx.y, tid = threadIdx.x, P = p.P;
+  const int m0 = blockIdx.x * kOscTile;
+  const float* __restrict__ ph = p.phase + (size_t)b * p.Np;
+  const int Z = p.zeros;
+  const float os_f = (float)OS, inv_os_f = 1.f / os_f;
+  constexpr bool pow2 = (OS & (OS - 1)) == 0;
+  const int ybase = (m0 * OS) / p.hop_tab;
+  const int trow0 = ybase * p.hop_tab;
+  const float* __restrict__ gb = q.gout + (size_t)b * p.n_out;
+  for (int i = tid; i < p.plen; i += blockDim.x) {
+    const int m = m0 - Z + i;
+    gs[i] = (m >= 0 && m < p.n_out) ? __ldg(gb + m) : 0.f;
+  }
+  for (int i = tid; i < OS * p.kp12; i += blockDim.x) {
+    const int phs = i / p.kp12, qr = i % p.kp12;
+    const int n = (2 * Z - qr) * OS + phs;  // reversed: hr[phs][q'] = h[(2Z - q')*os + phs]
+    hr[i] = (qr <= 2 * Z && n >= 0 && n <= 2 * Z * OS) ? (p.dec ? p.dec[n] : 1.f) : 0.f;
+  }
+  for (int i = 0; i < kOscRows; ++i) {
+    const int f = min(ybase + i, p.Fw - 1);
+    const float raw = __fmul_rn(__ldg(q.w + (size_t)b * p.Fw + f), (float)(q.n_tab - 1));
+    const int lo = min(max((int)raw, 0), q.n_tab - 2);
+    const float4* t0 = reinterpret_cast<const float4*>(q.table + (size_t)lo * P);
+    const float4* t1 = reinterpret_cast<const float4*>(q.table + (size_t)(lo + 1) * P);
+    float4* dst = reinterpret_cast<float4*>(slope + i * P);
+    for (int c = tid; c < P / 4; c += blockDim.x) {
+      const float4 a = __ldg(t0 + c), d = __ldg(t1 + c);
+      dst[c] = make_float4(d.x - a.x, d.y - a.y, d.z - a.z, d.w - a.w);
+    }
+  }
+  if (tid < kOscRows) dws[tid] = 0.f;
+  __syncthreads();
+  const int r0 = tid * kR;
+  // gv[phs][i] = gradient w.r.t. the oversampled sample (m0+r0+i)*OS + phs: transposed decimation
+  float gv[OS][kR];
+#pragma unroll
+  for (int phs = 0; phs < OS; ++phs) {
+#pragma unroll
+    for (int i = 0; i < kR; ++i) gv[phs][i] = 0.f;
+    fir_tile8(gs + r0, hr + phs * p.kp12, p.kp12, gv[phs]);
+  }
+  const int phase_hop = p.hp / OS;
+  const bool ph1 = phase_hop == 1;
+  const int lgP = 31 - __clz(P), lg2hp = 31 - __clz(2 * p.hp);
+  const bool hp_pow2 = (p.hp & (p.hp - 1)) == 0;
+  const float inv_hop_tab = 1.f / (float)p.hop_tab, inv_hp = 1.f / (float)p.hp, inv_span = 1.f / (float)p.span;
+  const unsigned long long* __restrict__ prefb = reinterpret_cast<const unsigned long long*>(p.pref) + (size_t)b * p.Np;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;  // sums for staged rows 0, 1, 2
+#pragma unroll
+  for (int i = 0; i < kR; ++i) {
+    const int mj = m0 + r0 + i;
+    if (mj >= p.n_out || (int64_t)mj * OS >= p.N) continue;
+    const int k = min(ph1 ? mj : mj / phase_hop, p.Np - 1);
+    const int rr0 = ph1 ? 0 : (mj - k * phase_hop) * OS;
+    const float xk = div_os(__ldg(ph + k), os_f, inv_os_f, pow2), xn = div_os(__ldg(ph + min(k + 1, p.Np - 1)), os_f, inv_os_f, pow2);
+    const uint64_t qx = q64_from_float(xk), qn = q64_from_float(xn);
+    const int64_t dq = (int64_t)(qn - qx);
+    const int64_t qq = hp_pow2 ? (dq >> lg2hp) : __float2ll_rn(__ll2float_rn(dq) * p.inv_2hp);
+    int sp = (int)((float)k * inv_span);
+    sp -= (sp * p.span > k) ? 1 : 0;
+    sp += ((sp + 1) * p.span <= k) ? 1 : 0;
+    const uint64_t qp = __ldg(prefb + k) + soff_s[sp];
+    const uint64_t dd = (uint64_t)(2 * qq);
+    uint64_t phi = qp + (uint64_t)(rr0 + 1) * qx + (uint64_t)(qq * (int64_t)(rr0 * (rr0 + 1)));
+    uint64_t d = qx + (uint64_t)(2 * qq * (int64_t)(rr0 + 1));
+    const int t0 = mj * OS;
+#pragma unroll
+    for (int phs = 0; phs < OS; ++phs) {
+      if (t0 + phs < p.N) {
+        const uint32_t hi = (uint32_t)(phi >> 32), lo = (uint32_t)phi;
+        const int c0 = (int)(hi >> (32 - lgP));
+        const int c1 = (c0 + 1) & (P - 1);
+        const float fx = __fmul_rn(__uint2float_rn(__funnelshift_l(lo, hi, lgP)), 2.3283064365386963e-10f);
+        const int tr = t0 + phs - trow0;
+        const bool up = tr >= p.hop_tab;
+        const float fy = __fmul_rn((float)(up ? tr - p.hop_tab : tr), inv_hop_tab);
+        const float* s0p = slope + (up ? P : 0);
+        const float* s1p = s0p + P;
+        float g = gv[phs][i];
+        if (p.equal_energy) {
+          const float l1 = __fmul_rn((float)(rr0 + phs), inv_hp);
+          const float inc = __fmaf_rn(__fsub_rn(1.f, l1), xk, __fmul_rn(l1, xn));
+          float rs;
+          asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(inc));
+          g = __fmul_rn(g, rs);
+        }
+        const float gx1 = 1.f - fx;
+        const float lo_part = g * (1.f - fy) * __fmaf_rn(fx, s0p[c1], gx1 * s0p[c0]);
+        const float hi_part = g * fy * __fmaf_rn(fx, s1p[c1], gx1 * s1p[c0]);
+        a0 += up ? 0.f : lo_part;
+        a1 += up ? lo_part : hi_part;
+        a2 += up ? hi_part : 0.f;
+      }
+      phi += d;
+      d += dd;
+    }
+  }
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, sh);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, sh);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, sh);
+  }
+  if ((tid & 31) == 0) {
+    atomicAdd(dws + 0, a0);
+    atomicAdd(dws + 1, a1);
+    atomicAdd(dws + 2, a2);
+  }
+  __syncthreads();
+  if (tid < kOscRows && dws[tid] != 0.f)
+    atomicAdd(q.d_w + (size_t)b * p.Fw + min(ybase + tid, p.Fw - 1), dws[tid] * (float)(q.n_tab - 1));
+}
+
 struct OscLayout {
   int hp, N, n_out, hop_tab, blocks;
   size_t off_tables, off_pref, bytes;
@@ -763,9 +893,27 @@ GOLF_API int golf_glottal_osc_bwd_w(const float* gout, const float* phase, const
   OscBwdParams q{};
   q.f = osc_params(phase, nullptr, pref, totals, span, dec_kernel, nullptr, B, Np, Fw, w_hop, P, os, zeros, accumulate, flags, L);
   q.gout = gout, q.w = w, q.table = table, q.d_w = d_w, q.n_tab = n_tab;
+  dim3 grid(ceil_div(L.n_out, kOscTile), B);
+  const size_t smv2 = ((size_t)q.f.plen + (size_t)os * q.f.kp12 + (size_t)kOscRows * P) * sizeof(float);
+  if (g_osc_v2 && accumulate == 0 && (os == 1 || os == 2 || os == 4) && P >= 4 && (P & (P - 1)) == 0 && smv2 <= 200 * 1024 &&
+      (int64_t)kOscTile * os < (int64_t)q.f.hop_tab) {
+    static bool attr = false;
+    if (!attr) {
+      GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    switch (os) {
+      case 1: osc_dw_v2_kernel<1><<<grid, 128, smv2, st>>>(q); break;
+      case 2: osc_dw_v2_kernel<2><<<grid, 128, smv2, st>>>(q); break;
+      default: osc_dw_v2_kernel<4><<<grid, 128, smv2, st>>>(q); break;
+    }
+    GOLF_CHECK_LAUNCH();
+    return GOLF_OK;
+  }
   const size_t sm = (size_t)(q.f.plen + os * q.f.kp12 + Fw) * sizeof(float);
   if (sm > 48 * 1024) return GOLF_ERR_UNSUPPORTED;
-  dim3 grid(ceil_div(L.n_out, kOscTile), B);
   osc_dw_kernel<<<grid, 128, sm, st>>>(q);
   GOLF_CHECK_LAUNCH();
   return GOLF_OK;

@@ -153,16 +153,18 @@ class LTVZeroPhaseFIRFilter(LTVFilterInterface):
         return kernel * self.window_fn(kernel.shape[-1], device=kernel.device, dtype=kernel.dtype)
 
     def _window(self, K: int, like_t: torch.Tensor) -> torch.Tensor:
+        """window / K: raw_kernels() leaves the inverse FFT unnormalised, the 1/K rides on the window"""
         key = (K, like_t.device)
         if getattr(self, "_win_key", None) != key:
-            self._win_cache = self.window_fn(K, device=like_t.device, dtype=torch.float32)
+            self._win_cache = self.window_fn(K, device=like_t.device, dtype=torch.float32) / K
             self._win_key = key
         return self._win_cache
 
     def raw_kernels(self, log_mag) -> torch.Tensor:
-        """frame-rate half of the inference path: irfft(exp(log_mag)) (cuFFT); shift + window are
-        applied by the FIR kernel while it stages the taps"""
-        return torch.fft.irfft(torch.exp(plain(log_mag)).to(torch.complex64), dim=-1)
+        """frame-rate half of the inference path: K * irfft(exp(log_mag)) -- one kernel for exp + complex
+        packing, cuFFT without its scaling pass; 1/K, fftshift and the window are applied by the FIR kernel
+        while it stages the taps (apply_raw)"""
+        return torch.fft.irfft(G.exp_complex(plain(log_mag)), dim=-1, norm="forward")
 
     def apply_raw(self, ex, raw, hop: int, add=None):
         y = G.ltv_fir_blocks(plain(ex), raw, hop // hop_of(ex), None if add is None else plain(add),
@@ -182,7 +184,7 @@ class LTVZeroPhaseFIRFilter(LTVFilterInterface):
             kernel = self.windowing(self.get_zero_phase_fir(lm))
             y = G.ltv_fir_blocks(x, kernel, hop, add)
         else:  # inference: cuFFT gives the raw impulse responses, shift + window ride along in the FIR kernel
-            raw = torch.fft.irfft(torch.exp(lm).to(torch.complex64), dim=-1)
+            raw = self.raw_kernels(lm)
             y = G.ltv_fir_blocks(x, raw, hop, add, window=self._window(raw.shape[-1], raw))
         return like(ex, y, hop_of(ex))
 

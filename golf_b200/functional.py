@@ -461,3 +461,13 @@ def rc2lpc(logits, max_abs: float = 1.0) -> torch.Tensor:
         rc = _lib.lib().golf_rc2lpc_fwd(_ptr(logits), _ptr(a), logits.numel() // M, M, float(max_abs), _stream())
     check(rc, "golf_rc2lpc_fwd")
     return a
+
+
+def exp_complex(x) -> torch.Tensor:
+    """exp(x) + 0j as complex64 in one pass (first step of the zero-phase FIR design, inference path)."""
+    x = _cuda_f32(x, "x")
+    out = torch.empty(x.shape, dtype=torch.complex64, device=x.device)
+    with _on(x.device):
+        rc = _lib.lib().golf_exp_to_complex(_ptr(x), out.data_ptr(), x.numel(), _stream())
+    check(rc, "golf_exp_to_complex")
+    return out

@@ -20,7 +20,7 @@ from .synth import IndexedGlottalFlowTable
 # independent, so the batch is cut into SPLIT groups that run the whole decoder on their own CUDA
 # streams (forked from and joined back into the caller's stream; a CUDA graph captures them as
 # parallel branches): one group's serial stitch/solve overlaps another group's throughput kernels.
-# Within a group the noise draw + FIR design run beside the oscillator.  "off" = one stream.
+# Within a group the noise draw and the FIR design run beside the oscillator, each on its own stream.  "off" = one stream.
 CONCURRENT = "auto"
 SPLIT = 1
 _SIDE_STREAMS = {}
@@ -80,38 +80,43 @@ class SourceFilterSynth(Synth):
         B = plain(phase).shape[0]
         n = max(1, min(int(SPLIT), B))
         main = torch.cuda.current_stream(dev)
-        streams = _side_streams(dev, 2 * n)
+        streams = _side_streams(dev, 3 * n)
         bounds = [(B * i) // n for i in range(n + 1)]
         cut = lambda x, lo, hi: like(x, plain(x)[lo:hi], hop_of(x))
         outs = []
         for i in range(n):
             lo, hi = bounds[i], bounds[i + 1]
-            s_run, s_fir = streams[2 * i], streams[2 * i + 1]
+            s_run, s_fir, s_rng = streams[3 * i], streams[3 * i + 1], streams[3 * i + 2]
             s_run.wait_stream(main)
             with torch.cuda.stream(s_run):
-                y = self._forward_group(s_run, s_fir, cut(phase, lo, hi), tuple(cut(x, lo, hi) for x in harm_oscillator_params),
+                y = self._forward_group(s_run, s_fir, s_rng, cut(phase, lo, hi), tuple(cut(x, lo, hi) for x in harm_oscillator_params),
                                         cut(noise_filter_params[0], lo, hi), tuple(cut(x, lo, hi) for x in end_filter_params))
                 plain(y).record_stream(main)
             outs.append(y)
         for i in range(n):
-            main.wait_stream(streams[2 * i])
+            main.wait_stream(streams[3 * i])
         if n == 1:
             return outs[0]
         return like(outs[0], torch.cat([plain(o) for o in outs], 0), hop_of(outs[0]))
 
-    def _forward_group(self, s_run, s_fir, phase, harm_oscillator_params, log_mag, end_filter_params):
-        """one group on its own stream:  s_run: oscillator --+-> noise FIR (+harm) -> end filter -> room
-                                         s_fir: randn, exp, irfft (FIR design) ---+"""
+    def _forward_group(self, s_run, s_fir, s_rng, phase, harm_oscillator_params, log_mag, end_filter_params):
+        """one group:  s_run: oscillator ------------------------+-> noise FIR (+harm) -> end filter -> room
+                       s_fir: exp+pack, irfft (FIR design) -------+
+                       s_rng: randn ------------------------------+
+        The two side branches are independent of each other and each shorter than the oscillator."""
         dev = plain(phase).device
         hop = hop_of(log_mag)
         t_osc = self.harm_oscillator.out_length(phase)
         s_fir.wait_stream(s_run)
-        with torch.cuda.stream(s_fir):
+        s_rng.wait_stream(s_run)
+        with torch.cuda.stream(s_rng):
             noise = torch.randn(plain(phase).shape[0], t_osc, dtype=torch.float32, device=dev)
-            raw = self.noise_filter.raw_kernels(log_mag)
             noise.record_stream(s_run)
+        with torch.cuda.stream(s_fir):
+            raw = self.noise_filter.raw_kernels(log_mag)
             raw.record_stream(s_run)
         harm = self.harm_oscillator(phase, *harm_oscillator_params)
         s_run.wait_stream(s_fir)
+        s_run.wait_stream(s_rng)
         src = self.noise_filter.apply_raw(like(harm, noise, 1), raw, hop, add=harm)
         return self.room_filter(self.end_filter(src, *end_filter_params))
