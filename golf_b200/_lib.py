@@ -33,6 +33,7 @@ _SIGS = {
     "golf_lpc_ff_bwd": (c_int, [P, P, c_int64, P, P, P, P, c_int64, P, P] + [c_int] * 6 + [P, c_size_t, P]),
     "golf_biquad_ff_fwd": (c_int, [P, c_int64, P, P, P, P] + [c_int] * 6 + [P]),
     "golf_lpc_inverse_fwd": (c_int, [P, c_int64, P, P] + [c_int] * 5 + [P]),
+    "golf_lpc_inverse_bwd": (c_int, [P, P, c_int64, P, P, P] + [c_int] * 5 + [P]),
     "golf_noise_fir_fwd": (c_int, [P, c_int64, P, P, P, c_int64, P] + [c_int] * 5 + [P]),
     "golf_fir_set_variant": (None, [c_int]),
     "golf_noise_fir_bwd": (c_int, [P, P, c_int64, P, P, P] + [c_int] * 5 + [P]),

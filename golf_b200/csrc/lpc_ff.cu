@@ -410,6 +410,25 @@ __global__ void lpc_inverse_kernel(const float* __restrict__ y, int64_t y_stride
   r[(size_t)b * L + t] = acc + yb[t];
 }
 
+// adjoint w.r.t. the filtered signal: d_y[s] = g[s] + sum_i c(s+1+i, i) g[s+1+i], c(t, .) the coefficient row
+// the forward interpolated at time t (same arithmetic)
+__global__ void lpc_inverse_dy_kernel(const float* __restrict__ g, const float* __restrict__ a, float* __restrict__ d_y, int B,
+                                      int L, int F, int M, float scale) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (s >= L) return;
+  const float* gb = g + (size_t)b * L;
+  const float* ab = a + (size_t)b * F * M;
+  float acc = gb[s];
+  for (int i = 0; i < M; ++i) {
+    const int t = s + 1 + i;
+    if (t >= L) break;
+    const Lerp w = lerp_at(t, scale, F);
+    acc = __fmaf_rn(lerp_apply(w, ab[(size_t)w.i0 * M + i], ab[(size_t)w.i1 * M + i]), gb[t], acc);
+  }
+  d_y[(size_t)b * L + s] = acc;
+}
+
 // ---- host side ------------------------------------------------------------------------
 static size_t ff_smem_bytes(const FfParams& p, int vt_floats) {
   const int NS = 33 - p.NQ, NSTRIP = 32 + p.NQ - 1;
@@ -574,5 +593,18 @@ GOLF_API int golf_lpc_inverse_fwd(const float* y, int64_t y_stride, const float*
   dim3 grid(ceil_div(L, 256), B);
   lpc_inverse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, y_stride, a, r, B, L, F, M, lerp_scale(F, hop));
   GOLF_CHECK_LAUNCH();
+  return GOLF_OK;
+}
+
+GOLF_API int golf_lpc_inverse_bwd(const float* g, const float* y, int64_t y_stride, const float* a, float* d_y, float* d_a,
+                                  int B, int L, int F, int M, int hop, void* stream) {
+  if (!g || !y || !a || B <= 0 || L <= 0 || F <= 0 || M <= 0 || hop <= 0) return GOLF_ERR_INVALID;
+  if ((int64_t)L > (int64_t)(F - 1) * hop + 1 || y_stride < L || B > 65535) return GOLF_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d_y) {
+    lpc_inverse_dy_kernel<<<dim3(ceil_div(L, 256), B), 256, 0, st>>>(g, a, d_y, B, L, F, M, lerp_scale(F, hop));
+    GOLF_CHECK_LAUNCH();
+  }
+  if (d_a) return launch_frame_reduction(g, y, y_stride, d_a, B, L, F, M, hop, st);
   return GOLF_OK;
 }

@@ -58,15 +58,15 @@ __global__ void __launch_bounds__(32) ss_grad2_kernel(const float* __restrict__ 
                                                       const float* __restrict__ ex, int64_t ex_stride,
                                                       const float* __restrict__ zi, float* __restrict__ d_gain,
                                                       float* __restrict__ d_a, int B, int L, int F, int M, int hop,
-                                                      float scale, int n_max) {
+                                                      float scale, int n_max, int64_t y_stride, float sign) {
   extern __shared__ __align__(16) float smem[];
-  float* wu = smem;           // [n_max]  -w_k(t) u[t], zero padded to a multiple of 4
+  float* wu = smem;           // [n_max]  sign * w_k(t) u[t] (sign = -1 here), zero padded to a multiple of 4
   float* ys = smem + n_max;   // [n_max + M] y[t_lo - M + j]
   const int lane = threadIdx.x;
   const int b = blockIdx.x / F, k = blockIdx.x % F;
   const float* __restrict__ ub = u + (size_t)b * L;
-  const float* __restrict__ yb = y + (size_t)b * L;
-  const float* __restrict__ xb = ex + (size_t)b * ex_stride;
+  const float* __restrict__ yb = y + (size_t)b * y_stride;
+  const float* __restrict__ xb = d_gain ? ex + (size_t)b * ex_stride : nullptr;
   const float* __restrict__ zb = zi ? zi + (size_t)b * M : nullptr;
   const int t_lo = max(0, (k - 1) * hop), t_hi = min(L - 1, (k + 1) * hop);
   const int n = t_hi - t_lo + 1;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(32) ss_grad2_kernel(const float* __restrict__ 
           if (w.i0 == k) wk += w.l0;
           if (w.i1 == k) wk += w.l1;  // i0 == i1 == F-1 at the clamped end: both weights count
         }
-        wu[j] = wk != 0.f ? -(wk * uv[q]) : 0.f;  // samples outside the support never enter (as above)
+        wu[j] = wk != 0.f ? sign * (wk * uv[q]) : 0.f;  // samples outside the support never enter (as above)
         if (wk != 0.f) gsum = __fmaf_rn(wk, uv[q] * xv[q], gsum);
       }
     }
@@ -227,6 +227,19 @@ static int launch_form(const SsParams& p, int MP, bool generic, int passes, cuda
   return GOLF_ERR_UNSUPPORTED;
 }
 
+// d_a[b,k,i] = sum_t w_k(t) g[t] y[t-1-i]: the frame-rate reduction of the inverse filter's adjoint
+// (lpc_ff.cu) is the same kernel with the opposite sign and no gain / initial-state terms
+int launch_frame_reduction(const float* g, const float* y, int64_t y_stride, float* d_a, int B, int L, int F, int M, int hop,
+                           cudaStream_t st) {
+  const int n_max = (int)align_up((size_t)2 * hop + 1, 4);
+  const size_t sm_g = ((size_t)2 * n_max + M + 4) * sizeof(float);
+  if (sm_g > 48 * 1024 || (int64_t)B * F >= INT32_MAX) return GOLF_ERR_UNSUPPORTED;
+  ss_grad2_kernel<<<B * F, 32, sm_g, st>>>(g, y, nullptr, 0, nullptr, nullptr, d_a, B, L, F, M, hop, lerp_scale(F, hop), n_max,
+                                          y_stride, 1.f);
+  GOLF_CHECK_LAUNCH();
+  return GOLF_OK;
+}
+
 }  // namespace golf
 
 using namespace golf;
@@ -299,7 +312,7 @@ GOLF_API int golf_lpc_ss_bwd(const float* gy, const float* y, const float* ex, i
     const size_t sm_g = ((size_t)2 * n_max + M + 4) * sizeof(float);
     if (sm_g <= 48 * 1024 && (int64_t)B * F < INT32_MAX) {
       ss_grad2_kernel<<<B * F, 32, sm_g, st>>>(u, y, ex, ex_stride, zi, gain ? d_gain : nullptr, d_a, B, L, F, M, hop,
-                                              p.scale, n_max);
+                                              p.scale, n_max, (int64_t)L, -1.f);
     } else {
       const int warps = 4;
       ss_grad_kernel<<<ceil_div(B * F, warps), warps * 32, 0, st>>>(u, y, ex, ex_stride, zi, gain ? d_gain : nullptr, d_a,

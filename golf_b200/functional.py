@@ -267,7 +267,7 @@ def biquad_ff(ex, gain, biquads, window, hop: int) -> torch.Tensor:
     return y
 
 
-def lpc_inverse(y, a, hop: int) -> torch.Tensor:
+def _lpc_inverse_fwd(y, a, hop: int) -> torch.Tensor:
     y = _rows(y, "y")
     a = _cuda_f32(a, "a")
     B, T = y.shape
@@ -278,6 +278,40 @@ def lpc_inverse(y, a, hop: int) -> torch.Tensor:
         rc = _lib.lib().golf_lpc_inverse_fwd(_ptr(y), y.stride(0), _ptr(a), _ptr(r), B, L, Fr, M, hop, _stream())
     check(rc, "golf_lpc_inverse_fwd")
     return r
+
+
+class _LpcInverse(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, a, hop):
+        r = _lpc_inverse_fwd(y, a, hop)
+        ctx.save_for_backward(y, a)
+        ctx.hop = hop
+        return r
+
+    @staticmethod
+    def backward(ctx, g):
+        y, a = ctx.saved_tensors
+        g = _cuda_f32(g, "g")
+        yr, ac = _rows(y, "y"), _cuda_f32(a, "a")
+        B, T = yr.shape
+        Fr, M = ac.shape[1], ac.shape[2]
+        L = g.shape[1]
+        d_yl = torch.empty(B, L, dtype=torch.float32, device=g.device) if ctx.needs_input_grad[0] else None
+        d_a = torch.empty_like(ac) if ctx.needs_input_grad[1] else None
+        with _on(g.device):
+            rc = _lib.lib().golf_lpc_inverse_bwd(_ptr(g), _ptr(yr), yr.stride(0), _ptr(ac), _ptr(d_yl), _ptr(d_a), B, L, Fr, M,
+                                                 ctx.hop, _stream())
+        check(rc, "golf_lpc_inverse_bwd")
+        d_y = None
+        if d_yl is not None:  # samples of y beyond the output length never reach it
+            d_y = torch.nn.functional.pad(d_yl, (0, T - L)) if T > L else d_yl
+        return d_y, d_a, None
+
+
+def lpc_inverse(y, a, hop: int) -> torch.Tensor:
+    """Inverse (analysis) filter r[t] = y[t] + sum_i a_up[t,i] y[t-1-i] (models/filters.py:186-195 +
+    fir_filt, models/utils.py:433-441) on frame-rate coefficients; differentiable in y and a."""
+    return _LpcInverse.apply(y, a, int(hop))
 
 
 # ---------------------------------------------------------------------- FIR stages

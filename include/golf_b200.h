@@ -125,6 +125,11 @@ int golf_biquad_ff_fwd(const float *ex, int64_t ex_stride, const float *gain,
 /* Inverse (analysis) filter: r[t] = y[t] + sum_i up(a)[t,i] y[t-1-i], [B,L]. */
 int golf_lpc_inverse_fwd(const float *y, int64_t y_stride, const float *a, float *r, int B,
                          int L, int F, int M, int hop, void *stream);
+/* Adjoint of the inverse filter for an upstream gradient g [B,L]: d_y [B,L] (w.r.t. the first L samples of
+ * y; later samples do not reach r) and d_a [B,F,M]; either may be NULL.  Used when the reference trains with
+ * an inverse-filtered target (ltng/vocoder.py:192-198). */
+int golf_lpc_inverse_bwd(const float *g, const float *y, int64_t y_stride, const float *a, float *d_y,
+                         float *d_a, int B, int L, int F, int M, int hop, void *stream);
 
 /* -------------------------------------------------------------- FIR stages ---- */
 /* Block-wise time-varying FIR: output block k (hop samples) is the valid

@@ -249,8 +249,10 @@ def biquad_ff(ex, gain, biquads, hop: int, window_length: Optional[int] = None, 
 # ------------------------------------------------------ inverse / analysis filter (a17)
 def lpc_inverse(y: torch.Tensor, a: torch.Tensor, hop: int) -> torch.Tensor:
     """LTVMinimumPhaseFilter.reverse + fir_filt, models/filters.py:186-195,
-    models/utils.py:433-441: r[t] = y[t] + sum_i a_up[t,i] y[t-1-i]."""
-    y, a = _f32(y), _f32(a)
+    models/utils.py:433-441: r[t] = y[t] + sum_i a_up[t,i] y[t-1-i].  Differentiable when the inputs
+    require grad (torch ops only)."""
+    if not (y.requires_grad or a.requires_grad):
+        y, a = _f32(y), _f32(a)
     a_up = upsample_time(a, hop)
     n = min(y.shape[1], a_up.shape[1])
     y, a_up = y[:, :n], a_up[:, :n]

@@ -237,6 +237,25 @@ def test_inverse_filter_reference_golden(G, M):
     assert rel_rms(r, T(g[f"inverse_{M}"])) < 1e-5
 
 
+def test_inverse_filter_gradients_match_autograd_of_the_oracle(G, oracle):
+    """adjoint of the analysis filter (inverse-target training, ltng/vocoder.py:192-198): d_y, d_a vs torch
+    autograd through the CPU restatement; ragged length (y longer than the control range)"""
+    g = golden("filters_rand")
+    H, M = int(g["hop"]), 22
+    a = T(g[f"a_{M}"])
+    y = torch.cat([T(g[f"target_{M}"]), torch.randn(a.shape[0], 37, generator=torch.Generator().manual_seed(5))], 1)[:, : (a.shape[1] - 1) * H + 30]
+    yr, ar = y.clone().requires_grad_(), a.clone().requires_grad_()
+    ref = oracle.lpc_inverse(yr, ar, H)
+    up = torch.randn(ref.shape, generator=torch.Generator().manual_seed(6))
+    gy, ga = torch.autograd.grad(ref, (yr, ar), up)
+    yg, ag = y.to(DEV).requires_grad_(), a.to(DEV).requires_grad_()
+    r = G.lpc_inverse(yg, ag, H)
+    assert r.shape == ref.shape and rel_rms(r, ref.detach()) < 1e-5
+    d_y, d_a = torch.autograd.grad(r, (yg, ag), up.to(DEV))
+    assert d_y.shape == y.shape and rel_rms(d_y, gy) < 1e-5
+    assert rel_rms(d_a.flatten(1), ga.flatten(1)) < 1e-5
+
+
 # ----------------------------------------------------------------------- FIR stages
 @pytest.mark.parametrize("variant", ["ss", "ff"])
 def test_fir_stages_reference_golden(G, oracle, variant):
