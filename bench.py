@@ -164,16 +164,18 @@ def workload_config(n):
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def build_decoder(dev):
+def build_decoder(dev, variant: str = "ss"):
     from golf_b200 import filters, noise, sf, synth
+
+    end = (filters.LTVMinimumPhaseFilterPrecise(lpc_order=ORDER, lpc_parameterisation="rc2lpc") if variant == "ss"
+           else filters.LTVMinimumPhaseFilter(window="hanning", window_length=4 * HOP, lpc_order=ORDER, lpc_parameterisation="rc2lpc"))
 
     dec = sf.SourceFilterSynth(
         synth.DownsampledIndexedGlottalFlowTable(hop_rate=10, in_channels=64, oversampling=OS, equal_energy=True,
                                                  table_type="derivative", normalize_method="constant_power", align_peak=True,
                                                  trainable=False, min_R_d=0.3, max_R_d=2.7, lf_v2=True, points=2048),
         noise.StandardNormalNoise(), filters.LTVZeroPhaseFIRFilter("hanning", conv_method="direct", n_mag=N_MAG),
-        filters.LTVMinimumPhaseFilterPrecise(lpc_order=ORDER, lpc_parameterisation="rc2lpc"),
-        filters.LTIAcousticFilter(128, "fft"), subtract_harmonics=False)
+        end, filters.LTIAcousticFilter(128, "fft"), subtract_harmonics=False)
     dec.room_filter.kernel.data = room_kernel()
     return dec.to(dev).eval()
 

@@ -13,6 +13,8 @@ namespace golf {
 void note_launch(int n = 1);
 int launch_frame_reduction(const float* g, const float* y, int64_t y_stride, float* d_a, int B, int L, int F, int M, int hop,
                            cudaStream_t st);  // lpc_ss.cu
+int launch_gain_reduction(const float* u, const float* ex, int64_t ex_stride, float* d_gain, int B, int L, int F, int hop,
+                          cudaStream_t st);  // lpc_ss.cu
 int note_cuda(cudaError_t e);  // records e, returns GOLF_ERR_CUDA if e != cudaSuccess else 0
 
 #define GOLF_CHECK_LAUNCH()                              \

@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kFfThreads) ff_backward_kernel(FfParams p) {
   float* __restrict__ strip = smem;                           // [NSTRIP][hop+1] gy / norm in padded coordinates
   float* __restrict__ acc = strip + g.NSTRIP * g.seg_stride;  // [NS][hop+1]     d_e accumulators
   float* __restrict__ wsm = acc + g.NS * g.seg_stride;        // [win]
-  float* __restrict__ vt = wsm + p.win;                       // [32][2*MP+1]    v tile: column c <-> v[nhi - 2*MP + c]
+  float* __restrict__ vt = wsm + p.win;                       // [2][32][2*MP+1] v tiles (double buffered): column c <-> v[nhi - 2*MP + c]
   const int k = g.k0 + lane;
   const bool frame_ok = (k >= 0) && (k < p.n_frames);
   // a frame's d_a is produced by the CTA that owns it (not by the neighbour that recomputes it)
@@ -293,24 +293,35 @@ __global__ void __launch_bounds__(kFfThreads) ff_backward_kernel(FfParams p) {
 #pragma unroll
     for (int i = 0; i < MP; ++i) da[i] = 0.f, vh[i] = 0.f;
     constexpr int VT = 2 * MP + 1;
+    // v tiles stream through two shared-memory buffers filled by cp.async (LDGSTS, zero-fill where a frame
+    // or a sample does not exist): the copy of the NEXT tile runs while this one is consumed.  (Staging each
+    // tile with load -> store pairs cost one L2 latency per 32 elements, 49 times per tile: 383 us.)
+    auto stage = [&](float* dst, int nhi_) {
+      for (int i = lane; i < 32 * VT; i += 32) {
+        const int rr = i / VT, c = i - rr * VT;
+        const int kk = g.k0 + rr, m = nhi_ - 2 * MP + c;
+        const bool ok = kk >= 0 && kk < p.n_frames && m >= 0;
+        cp_async4(dst + i, p.vws + ((size_t)b * p.n_frames + (ok ? kk : 0)) * p.win + (ok ? m : 0), ok);
+      }
+    };
+    stage(vt, p.win - 1);
     // reversed time: tau = 0..win-1 <-> n = win-1-tau.  Tile tau0..tau0+MP-1 covers n in [nhi-MP+1, nhi].
     int q0 = p.NQ - 1, r0 = p.hop - 1;  // (n / hop, n % hop) at the tile's first step
+    int buf = 0;
 #pragma unroll 1
     for (int tau0 = 0; tau0 < p.win; tau0 += MP) {
       const int nhi = p.win - 1 - tau0;
-      // ---- stage v[nhi-2*MP .. nhi] of all 32 frames (rows coalesced)
+      // ---- v[nhi-2*MP .. nhi] of all 32 frames: wait for this tile, start the next one
+      cp_async_wait_all();
       __syncwarp();
-      for (int i = lane; i < 32 * VT; i += 32) {
-        const int rr = i / VT, c = i - rr * VT;
-        const int kk = g.k0 + rr, m = nhi - 2 * MP + c;
-        vt[rr * VT + c] = (kk >= 0 && kk < p.n_frames && m >= 0) ? __ldg(p.vws + ((size_t)b * p.n_frames + kk) * p.win + m) : 0.f;
-      }
-      __syncwarp();
+      float* __restrict__ vcur = vt + buf * (32 * VT);
+      if (tau0 + MP < p.win) stage(vt + (buf ^ 1) * (32 * VT), nhi - MP);
+      buf ^= 1;
       if (tau0 == 0) {  // history for the first step: v[win-2 .. win-1-MP]
 #pragma unroll
         for (int i = 0; i < MP; ++i) {
           const int c = 2 * MP - 1 - i;  // m = nhi - 1 - i
-          vh[((MP - 2 - i) % MP + MP) % MP] = vt[lane * VT + c];
+          vh[((MP - 2 - i) % MP + MP) % MP] = vcur[lane * VT + c];
         }
       }
       // hop % MP == 0 (checked on the host): the tile stays inside hop-segment q0, offsets r0-s
@@ -322,7 +333,7 @@ __global__ void __launch_bounds__(kFfThreads) ff_backward_kernel(FfParams p) {
         for (int s = 0; s < MP; ++s) xs[s] = __fmul_rn(xrow[-s], wrow[-s]);
       }
       TileSteps<AllPole<MP>, 0, MP>::run(f, xs, us);
-      const float* __restrict__ vrow_t = vt + lane * VT;
+      const float* __restrict__ vrow_t = vcur + lane * VT;
 #pragma unroll
       for (int s = 0; s < MP; ++s) {
         // n = nhi - s; n mod MP = (MP-1-s) since win % MP == 0 and tau0 % MP == 0
@@ -458,7 +469,7 @@ template <int MP>
 static int launch_ff_bwd(const FfParams& pf, const FfParams& pb, cudaStream_t st) {
   int rc = launch_ff_fwd<AllPole<MP>, true>(pf, st);
   if (rc) return rc;
-  const size_t sm = ff_smem_bytes(pb, 32 * (2 * MP + 1));
+  const size_t sm = ff_smem_bytes(pb, 2 * 32 * (2 * MP + 1));
   if (sm > 220 * 1024) return GOLF_ERR_UNSUPPORTED;
   static size_t sm_allowed = 48 * 1024;
   if (sm > sm_allowed) {
@@ -562,8 +573,11 @@ GOLF_API int golf_lpc_ff_bwd(const float* gy, const float* ex, int64_t ex_stride
   if (rc) return rc;
   // d_ex covers the caller's full excitation row (zeros beyond the filtered span)
   const int span = T_ex > F ? T_ex : F;
-  ff_finish_kernel<<<dim3(ceil_div(span, 256), B), 256, 0, st>>>(d_e, ex, ex_stride, gain, d_ex, dex_stride, d_gain, d_a, B, T_ex,
-                                                                pf.Le, F, M, hop, pf.n_frames, 0, pf.scale);
+  // the gain gradient is a per-frame reduction over 2*hop samples: one warp per (utterance, frame) instead of
+  // one THREAD per frame walking its 481 samples (131 us for the whole launch)
+  const bool fast_gain = d_gain && launch_gain_reduction(d_e, ex, ex_stride, d_gain, B, pf.Le, F, hop, st) == GOLF_OK;
+  ff_finish_kernel<<<dim3(ceil_div(span, 256), B), 256, 0, st>>>(d_e, ex, ex_stride, gain, d_ex, dex_stride, fast_gain ? nullptr : d_gain,
+                                                                d_a, B, T_ex, pf.Le, F, M, hop, pf.n_frames, 0, pf.scale);
   GOLF_CHECK_LAUNCH();
   return GOLF_OK;
 }

@@ -240,6 +240,19 @@ int launch_frame_reduction(const float* g, const float* y, int64_t y_stride, flo
   return GOLF_OK;
 }
 
+// d_gain[b,k] = sum_t w_k(t) u[t] ex[t] alone (the frame-wise filter's adjoint, lpc_ff.cu): the gain half of the
+// same kernel, one warp per (utterance, frame)
+int launch_gain_reduction(const float* u, const float* ex, int64_t ex_stride, float* d_gain, int B, int L, int F, int hop,
+                          cudaStream_t st) {
+  const int n_max = (int)align_up((size_t)2 * hop + 1, 4);
+  const size_t sm_g = ((size_t)2 * n_max + 4) * sizeof(float);
+  if (sm_g > 48 * 1024 || (int64_t)B * F >= INT32_MAX) return GOLF_ERR_UNSUPPORTED;
+  ss_grad2_kernel<<<B * F, 32, sm_g, st>>>(u, u, ex, ex_stride, nullptr, d_gain, nullptr, B, L, F, 0, hop, lerp_scale(F, hop), n_max,
+                                          (int64_t)L, -1.f);
+  GOLF_CHECK_LAUNCH();
+  return GOLF_OK;
+}
+
 }  // namespace golf
 
 using namespace golf;

@@ -6,7 +6,7 @@ the decoder's own parameters (room kernel), then -- with more than one rank -- t
 DDP would do (NCCL), for the decoder's parameters plus a 6.08 M-parameter stand-in for the encoder's
 (autoencode.py:9-16; the encoder itself is the reference's torch U-Net and stays out of scope).
 
-    python tools/fit_step.py [steps]                       # one GPU
+    python tools/fit_step.py [steps] [ss|ff]               # one GPU
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/fit_step.py
 
 Prints one JSON line: samples/s over all ranks, ms per step (max over ranks), and the split.
@@ -26,7 +26,8 @@ dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-dec = bench.build_decoder(dev).train()
+variant = sys.argv[2] if len(sys.argv) > 2 else "ss"  # "ff": GOLF-ff (frame-wise filter), cfg/ae/decoder/golf.yaml
+dec = bench.build_decoder(dev, variant).train()
 gsynth.CHECK_INPUTS = "off"
 s = {k: v.to(dev) for k, v in bench.make_inputs(1, bench.BATCH, seed=2434 + rank)[0].items()}
 leaves = {k: s[k].clone().requires_grad_() for k in ("w", "log_mag", "gain", "a")}
@@ -80,7 +81,7 @@ if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     assert all(torch.isfinite(p.grad).all() for p in leaves.values())
-    print(json.dumps({"workload": "GOLF-ss decoder fit step (fwd + MSS loss + bwd" + (" + NCCL grad all-reduce" if world > 1 else "") + "), 32 x 2 s per GPU, eager",
+    print(json.dumps({"workload": f"GOLF-{variant} decoder fit step (fwd + MSS loss + bwd" + (" + NCCL grad all-reduce" if world > 1 else "") + "), 32 x 2 s per GPU, eager",
                       "n_gpus": world, "ms_per_step": float(t), "samples_per_s": world * bench.BATCH * bench.T / (float(t) * 1e-3),
                       "split_ms": {"decoder_fwd": tot[0] / steps, "mss_loss_fwd": tot[1] / steps, "backward": tot[2] / steps, "allreduce": tot[3] / steps},
                       "loss": float(loss)}))
