@@ -46,6 +46,7 @@ _SIGS = {
     "golf_wavetable_read_fwd": (c_int, [P, P, P] + [c_int] * 5 + [P]),
     "golf_linear_upsample": (c_int, [P, P, c_int, c_int, c_int, P]),
     "golf_rc2lpc_fwd": (c_int, [P, P, c_int, c_int, c_float, P]),
+    "golf_rc2lpc_bwd": (c_int, [P, P, P, c_int, c_int, c_float, P]),
     "golf_exp_to_complex": (c_int, [P, P, c_int64, P]),
 }
 EXPORTS = tuple(_SIGS)

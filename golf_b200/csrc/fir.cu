@@ -447,6 +447,52 @@ __global__ void rc2lpc_kernel(const float* __restrict__ logits, float* __restric
   for (int i = 0; i < M; ++i) a[(size_t)idx * M + i] = cur[i + 1];
 }
 
+// adjoint of the step-up recursion: one thread per frame recomputes the polynomial of every level (kept in
+// local memory, triangular: level n has n+2 coefficients) and walks the levels backwards,
+//   d_k_n = sum_j dpoly[j] ext[n+1-j],   d_ext[j] = dpoly[j] + k_n dpoly[n+1-j],
+// then d_logit = d_k * max_abs * (1 - tanh^2).
+constexpr int kMaxOrderBwd = 40;
+__global__ void rc2lpc_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ d_a, float* __restrict__ d_logits,
+                                  int N, int M, float max_abs) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N) return;
+  float lev[(kMaxOrderBwd + 1) * (kMaxOrderBwd + 2) / 2 + kMaxOrderBwd + 2];  // level n starts at n*(n+3)/2... offsets below
+  float kk[kMaxOrderBwd], th[kMaxOrderBwd], dp[kMaxOrderBwd + 2], dn[kMaxOrderBwd + 2];
+  const float* lg = logits + (size_t)idx * M;
+  auto off = [](int n) { return n * (n + 3) / 2; };  // level n holds n+2 coefficients: 2, 3, 4, ... -> offsets 0, 2, 5, 9
+  // level 0: [1, k0]
+  th[0] = tanhf(lg[0]);
+  kk[0] = __fmul_rn(th[0], max_abs);
+  lev[0] = 1.f, lev[1] = kk[0];
+  for (int n = 1; n < M; ++n) {
+    th[n] = tanhf(lg[n]);
+    kk[n] = __fmul_rn(th[n], max_abs);
+    const float* cur = lev + off(n - 1);  // n+1 coefficients
+    float* nxt = lev + off(n);            // n+2 coefficients
+    for (int i = 0; i <= n + 1; ++i) {
+      const float pi_ = i <= n ? cur[i] : 0.f;
+      const float pr = (n + 1 - i) <= n ? cur[n + 1 - i] : 0.f;
+      nxt[i] = __fadd_rn(pi_, __fmul_rn(kk[n], pr));
+    }
+  }
+  const float* g = d_a + (size_t)idx * M;
+  dp[0] = 0.f;
+  for (int i = 0; i < M; ++i) dp[i + 1] = g[i];
+  float* dl = d_logits + (size_t)idx * M;
+  for (int n = M - 1; n >= 1; --n) {
+    const float* ext = lev + off(n - 1);  // ext[j] = poly^{(n-1)}[j] for j <= n, 0 at j = n+1
+    float dk = 0.f;
+    for (int j = 0; j <= n + 1; ++j) {
+      const int r = n + 1 - j;
+      if (r <= n) dk = __fmaf_rn(dp[j], ext[r], dk);
+    }
+    for (int j = 0; j <= n; ++j) dn[j] = __fmaf_rn(kk[n], dp[n + 1 - j], dp[j]);
+    for (int j = 0; j <= n; ++j) dp[j] = dn[j];
+    dl[n] = dk * max_abs * (1.f - th[n] * th[n]);
+  }
+  dl[0] = dp[1] * max_abs * (1.f - th[0] * th[0]);
+}
+
 }  // namespace golf
 
 using namespace golf;
@@ -603,6 +649,14 @@ GOLF_API int golf_rc2lpc_fwd(const float* logits, float* a, int N, int M, float 
   if (!logits || !a || N <= 0 || M <= 0) return GOLF_ERR_INVALID;
   if (M > kMaxOrder) return GOLF_ERR_UNSUPPORTED;
   rc2lpc_kernel<<<ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(logits, a, N, M, max_abs);
+  GOLF_CHECK_LAUNCH();
+  return GOLF_OK;
+}
+
+GOLF_API int golf_rc2lpc_bwd(const float* logits, const float* d_a, float* d_logits, int N, int M, float max_abs, void* stream) {
+  if (!logits || !d_a || !d_logits || N <= 0 || M <= 0) return GOLF_ERR_INVALID;
+  if (M > kMaxOrderBwd) return GOLF_ERR_UNSUPPORTED;
+  rc2lpc_bwd_kernel<<<ceil_div(N, 64), 64, 0, (cudaStream_t)stream>>>(logits, d_a, d_logits, N, M, max_abs);
   GOLF_CHECK_LAUNCH();
   return GOLF_OK;
 }

@@ -51,7 +51,13 @@ def _logits2lpc(kind: str, max_abs: float):
         to_bq = get_logits2biquads(kind, max_abs)
         return lambda lg: biquads2lpc(to_bq(lg.view(lg.shape[0], lg.shape[1], -1, 2))), 0
     if kind == "rc2lpc":
-        return lambda lg: rc2lpc(lg.tanh() * max_abs), 0
+
+        def fn(lg):  # one CUDA launch (golf_rc2lpc_fwd / _bwd) where it applies, else the torch recursion
+            if lg.is_cuda and lg.dtype == torch.float32 and lg.shape[-1] <= 40:
+                return G.rc2lpc(lg, max_abs)
+            return rc2lpc(lg.tanh() * max_abs)
+
+        return fn, 0
     if kind == "lsp2lpc":
 
         def fn(lg):

@@ -486,15 +486,35 @@ def linear_upsample(x, hop: int) -> torch.Tensor:
     return out
 
 
+class _Rc2Lpc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, max_abs):
+        lg = _cuda_f32(logits, "logits")
+        M = lg.shape[-1]
+        a = torch.empty_like(lg)
+        with _on(lg.device):
+            rc = _lib.lib().golf_rc2lpc_fwd(_ptr(lg), _ptr(a), lg.numel() // M, M, float(max_abs), _stream())
+        check(rc, "golf_rc2lpc_fwd")
+        ctx.save_for_backward(lg)
+        ctx.max_abs = float(max_abs)
+        return a
+
+    @staticmethod
+    def backward(ctx, g):
+        (lg,) = ctx.saved_tensors
+        g = _cuda_f32(g, "d_a")
+        M = lg.shape[-1]
+        d = torch.empty_like(lg)
+        with _on(lg.device):
+            rc = _lib.lib().golf_rc2lpc_bwd(_ptr(lg), _ptr(g), _ptr(d), lg.numel() // M, M, ctx.max_abs, _stream())
+        check(rc, "golf_rc2lpc_bwd")
+        return d, None
+
+
 def rc2lpc(logits, max_abs: float = 1.0) -> torch.Tensor:
-    """a = step_up(tanh(logits)*max_abs), last dim = order (inference path, no autograd)."""
-    logits = _cuda_f32(logits, "logits")
-    M = logits.shape[-1]
-    a = torch.empty_like(logits)
-    with _on(logits.device):
-        rc = _lib.lib().golf_rc2lpc_fwd(_ptr(logits), _ptr(a), logits.numel() // M, M, float(max_abs), _stream())
-    check(rc, "golf_rc2lpc_fwd")
-    return a
+    """a = step_up(tanh(logits)*max_abs), last dim = order (models/utils.py:581-593 with the tanh * max_abs of
+    models/filters.py:80): one launch instead of ~3M tiny torch ops; differentiable for M <= 40."""
+    return _Rc2Lpc.apply(logits, float(max_abs))
 
 
 def exp_complex(x) -> torch.Tensor:

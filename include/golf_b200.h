@@ -194,6 +194,9 @@ int golf_wavetable_read_fwd(const float *wrapped, const float *tables, float *ou
 int golf_linear_upsample(const float *x, float *out, int R, int n, int hop, void *stream);
 /* a = step_up(tanh(logits) * max_abs); logits, a: [N, M] */
 int golf_rc2lpc_fwd(const float *logits, float *a, int N, int M, float max_abs, void *stream);
+/* Adjoint: d_logits [N,M] from d_a [N,M] (M <= 40); the recursion is recomputed per frame. */
+int golf_rc2lpc_bwd(const float *logits, const float *d_a, float *d_logits, int N, int M,
+                    float max_abs, void *stream);
 /* out[i] = (exp(x[i]), 0) as interleaved complex64: the spectrum handed to the inverse real FFT of the
  * zero-phase FIR design (models/filters.py:295-297), in one pass. */
 int golf_exp_to_complex(const float *x, float *out_interleaved, int64_t n, void *stream);

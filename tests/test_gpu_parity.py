@@ -413,3 +413,19 @@ def test_rc2lpc_kernel(G, oracle):
     a = G.rc2lpc(lg.to(DEV)).cpu()
     ref = oracle.rc2lpc(torch.tanh(lg))
     assert (a - ref).abs().max() < 5e-6 * ref.abs().max()
+
+
+@pytest.mark.parametrize("M", [1, 2, 22, 40])
+def test_rc2lpc_gradient_matches_torch_autograd(G, oracle, M):
+    """adjoint of the step-up recursion vs autograd through the torch restatement (models/utils.py:581-593)"""
+    from golf_b200.utils import rc2lpc as rc2lpc_torch
+
+    g = torch.Generator().manual_seed(M)
+    lg = (0.5 * torch.randn(3, 50, M, generator=g)).to(DEV)
+    up = torch.randn(3, 50, M, generator=g).to(DEV)
+    l1, l2 = lg.clone().requires_grad_(), lg.clone().requires_grad_()
+    a1 = G.rc2lpc(l1, 0.99)
+    a2 = rc2lpc_torch(torch.tanh(l2) * 0.99)
+    assert rel_rms(a1.flatten(1), a2.flatten(1)) < 1e-6
+    (d1,), (d2,) = torch.autograd.grad(a1, l1, up), torch.autograd.grad(a2, l2, up)
+    assert rel_rms(d1.flatten(1), d2.flatten(1)) < 1e-5
