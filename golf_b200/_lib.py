@@ -42,6 +42,7 @@ _SIGS = {
     "golf_glottal_osc_workspace_bytes": (c_size_t, [c_int] * 6),
     "golf_glottal_osc_set_variant": (None, [c_int]),
     "golf_glottal_osc_fwd": (c_int, [P, P, P, P, P] + [c_int] * 11 + [P, c_size_t, P]),
+    "golf_glottal_osc_fwd_from": (c_int, [P, P, P, P, P, P] + [c_int] * 11 + [P, c_size_t, P]),
     "golf_glottal_osc_bwd_w": (c_int, [P, P, P, P, P, P] + [c_int] * 11 + [P, c_size_t, P]),
     "golf_wavetable_read_fwd": (c_int, [P, P, P] + [c_int] * 5 + [P]),
     "golf_linear_upsample": (c_int, [P, P, c_int, c_int, c_int, P]),

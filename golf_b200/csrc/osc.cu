@@ -165,8 +165,18 @@ __global__ void __launch_bounds__(32 * kPrefWarps) osc_knot_prefix_q64_kernel(co
 }
 
 // reader prologue (first warp of the CTA): exclusive scan of the utterance's span totals into shared memory
-__device__ __forceinline__ void span_offsets(const unsigned long long* __restrict__ tot_b, unsigned long long* soff_s) {
+__device__ __forceinline__ void span_offsets(const unsigned long long* __restrict__ tot_b, unsigned long long* soff_s,
+                                             const double* __restrict__ phase0 = nullptr, int b = 0) {
   const int lane = threadIdx.x & 31;
+  // phase0[b]: running phase (cycles) the utterance starts from -- a stream continuing a previous call.  float64
+  // so that the hand-over is good to 2^-53 of a cycle (a float32 offset would move the table read by 1e-4 of a
+  // column); converted to Q0.64 in two 32-bit halves
+  unsigned long long start = 0ull;
+  if (phase0) {
+    const double fr = (phase0[b] - floor(phase0[b])) * 4294967296.0;
+    const double hi = floor(fr);
+    start = ((unsigned long long)(unsigned int)hi << 32) | (unsigned long long)(unsigned int)((fr - hi) * 4294967296.0);
+  }
   const unsigned long long w = tot_b[lane];
   unsigned long long winc = w;
 #pragma unroll
@@ -174,7 +184,7 @@ __device__ __forceinline__ void span_offsets(const unsigned long long* __restric
     const unsigned long long u = __shfl_up_sync(0xffffffffu, winc, d);
     if (lane >= d) winc += u;
   }
-  soff_s[lane] = winc - w;
+  soff_s[lane] = winc - w + start;
 }
 
 // upsampled increment at oversampled time t, ATen arithmetic on phase/os
@@ -246,6 +256,7 @@ struct OscParams {
   int aten_cpu;           // 1: round the running sum to float32 before mod 1 (ATen CPU cumsum semantics)
   const unsigned long long* totals;  // [B][kPrefSplit] span totals of the Q0.64 prefix (readers: span_offsets)
   int span;               // knots per span
+  const double* phase0;   // [B] initial running phase in cycles, or null (exact-phase mode only)
   const float* dec;       // [2*zeros*os+1]
   float* out;             // [B,n_out]
   int B, Np, hp, N, n_out, Fw, P, hop_tab, blocks, os, zeros, equal_energy;
@@ -301,7 +312,7 @@ __global__ void __launch_bounds__(128) osc_flow_decimate_kernel(OscParams p) {
   float* vp = smem;                      // [os][plen] polyphase oversampled flow
   float* hp_ = smem + p.os * p.plen;     // [os][kp12] polyphase taps
   __shared__ unsigned long long soff_s[kPrefSplit];
-  if (threadIdx.x < 32 && !p.aten_cpu) span_offsets(p.totals + (size_t)blockIdx.y * kPrefSplit, soff_s);
+  if (threadIdx.x < 32 && !p.aten_cpu) span_offsets(p.totals + (size_t)blockIdx.y * kPrefSplit, soff_s, p.phase0, blockIdx.y);
   const int b = blockIdx.y, tid = threadIdx.x;
   const int m0 = blockIdx.x * kOscTile;
   const float* ph = p.phase + (size_t)b * p.Np;
@@ -419,7 +430,7 @@ __global__ void __launch_bounds__(128) osc_flow_v2_kernel(OscParams p, const flo
     }
   }
   pdl_wait();  // everything above read launch inputs only; the knot prefix comes from the previous kernel
-  if (threadIdx.x < 32) span_offsets(p.totals + (size_t)blockIdx.y * kPrefSplit, soff_s);
+  if (threadIdx.x < 32) span_offsets(p.totals + (size_t)blockIdx.y * kPrefSplit, soff_s, p.phase0, blockIdx.y);
   __syncthreads();
   // ---- flow: strip index j <-> output-rate index mj = m0 - Z + j, samples t = mj*OS + phs
   const int phase_hop = p.hp / OS;
@@ -551,7 +562,7 @@ __global__ void __launch_bounds__(128) osc_dw_kernel(OscBwdParams q) {
   float* hr = smem + p.plen;              // [os][kp12] reversed polyphase taps
   float* dws = hr + p.os * p.kp12;        // [Fw] partial sums
   __shared__ unsigned long long soff_s[kPrefSplit];
-  if (threadIdx.x < 32 && !p.aten_cpu) span_offsets(p.totals + (size_t)blockIdx.y * kPrefSplit, soff_s);
+  if (threadIdx.x < 32 && !p.aten_cpu) span_offsets(p.totals + (size_t)blockIdx.y * kPrefSplit, soff_s, p.phase0, blockIdx.y);
   const int b = blockIdx.y, tid = threadIdx.x;
   const int m0 = blockIdx.x * kOscTile;
   const float* ph = p.phase + (size_t)b * p.Np;
@@ -639,7 +650,7 @@ __global__ void __launch_bounds__(128) osc_dw_v2_kernel(OscBwdParams q) {
   float* slope = hr + OS * p.kp12;        // [kOscRows][P] T[lo+1] - T[lo] of control frames ybase .. ybase+2
   __shared__ unsigned long long soff_s[kPrefSplit];
   __shared__ float dws[kOscRows];
-  if (threadIdx.x < 32) span_offsets(p.totals + (size_t)blockIdx.y * kPrefSplit, soff_s);
+  if (threadIdx.x < 32) span_offsets(p.totals + (size_t)blockIdx.y * kPrefSplit, soff_s, p.phase0, blockIdx.y);
   const int b = blockIdx.y, tid = threadIdx.x, P = p.P;
   const int m0 = blockIdx.x * kOscTile;
   const float* __restrict__ ph = p.phase + (size_t)b * p.Np;
@@ -801,10 +812,10 @@ GOLF_API size_t golf_glottal_osc_workspace_bytes(int B, int Np, int phase_hop, i
   return osc_layout(B, Np, phase_hop, Fw, P, os, &L) ? L.bytes : 0;
 }
 
-GOLF_API int golf_glottal_osc_fwd(const float* phase, const float* w, const float* table, const float* dec_kernel,
-                                  float* out, int B, int Np, int phase_hop, int Fw, int w_hop, int n_tab, int P, int os,
-                                  int zeros, int accumulate, int flags, void* workspace, size_t workspace_bytes,
-                                  void* stream) {
+static int glottal_osc_fwd(const float* phase, const float* w, const float* table, const float* dec_kernel, float* out, int B,
+                           int Np, int phase_hop, int Fw, int w_hop, int n_tab, int P, int os, int zeros, int accumulate,
+                           int flags, void* workspace, size_t workspace_bytes, void* stream, const double* phase0) {
+  if (phase0 && accumulate != 0) return GOLF_ERR_UNSUPPORTED;  // the initial phase rides on the fixed-point prefix
   if (!phase || !w || !table || !out || n_tab < 2 || w_hop <= 0 || zeros < 0) return GOLF_ERR_INVALID;
   if (os > 1 && !dec_kernel) return GOLF_ERR_INVALID;
   OscLayout L;
@@ -820,6 +831,7 @@ GOLF_API int golf_glottal_osc_fwd(const float* phase, const float* w, const floa
   unsigned long long* totals = reinterpret_cast<unsigned long long*>(ws + L.off_pref + align_up((size_t)B * Np * 8, 256));
   const int span = ceil_div(Np, kPrefSplit);
   OscParams p = osc_params(phase, tables, pref, totals, span, dec_kernel, out, B, Np, Fw, w_hop, P, os, zeros, accumulate, flags, L);
+  p.phase0 = phase0;
   dim3 grid(ceil_div(L.n_out, kOscTile), B);
   // v2: exact-phase mode, compile-time oversampling, table rows built in shared memory.  Needs a tile
   // (plus FIR halo) shorter than one table-row interval so three staged rows always suffice.
@@ -865,6 +877,22 @@ GOLF_API int golf_glottal_osc_fwd(const float* phase, const float* w, const floa
   return GOLF_OK;
 }
 
+
+GOLF_API int golf_glottal_osc_fwd(const float* phase, const float* w, const float* table, const float* dec_kernel,
+                                  float* out, int B, int Np, int phase_hop, int Fw, int w_hop, int n_tab, int P, int os,
+                                  int zeros, int accumulate, int flags, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  return glottal_osc_fwd(phase, w, table, dec_kernel, out, B, Np, phase_hop, Fw, w_hop, n_tab, P, os, zeros, accumulate, flags,
+                         workspace, workspace_bytes, stream, nullptr);
+}
+
+GOLF_API int golf_glottal_osc_fwd_from(const float* phase, const float* w, const float* table, const float* dec_kernel,
+                                       float* out, const double* phase0, int B, int Np, int phase_hop, int Fw, int w_hop,
+                                       int n_tab, int P, int os, int zeros, int accumulate, int flags, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  return glottal_osc_fwd(phase, w, table, dec_kernel, out, B, Np, phase_hop, Fw, w_hop, n_tab, P, os, zeros, accumulate, flags,
+                         workspace, workspace_bytes, stream, phase0);
+}
 
 GOLF_API int golf_glottal_osc_bwd_w(const float* gout, const float* phase, const float* w, const float* table,
                                     const float* dec_kernel, float* d_w, int B, int Np, int phase_hop, int Fw, int w_hop,

@@ -413,8 +413,15 @@ _OSC_MODES = {"exact": 0, "fp64": 0, "aten_cpu": 1}
 
 class _GlottalOsc(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, phase, w, table, dec_kernel, phase_hop, w_hop, os_, equal_energy, mode):
+    def forward(ctx, phase, w, table, dec_kernel, phase_hop, w_hop, os_, equal_energy, mode, phase0=None):
         phase_c, w_c, table_c = _cuda_f32(phase, "phase"), _cuda_f32(w, "w"), _cuda_f32(table, "table")
+        p0 = None
+        if phase0 is not None:
+            if not phase0.is_cuda:
+                raise GolfError("glottal_osc: phase0 must be a CUDA tensor")
+            p0 = phase0.detach().to(torch.float64).reshape(-1).contiguous()
+        if p0 is not None and p0.numel() != phase_c.shape[0]:
+            raise GolfError("glottal_osc: phase0 must hold one value per utterance")
         dk = None if dec_kernel is None else _cuda_f32(dec_kernel, "dec_kernel")
         B, Np = phase_c.shape
         Fw = w_c.shape[1]
@@ -425,9 +432,16 @@ class _GlottalOsc(torch.autograd.Function):
         lib = _lib.lib()
         ws = _workspace(lib.golf_glottal_osc_workspace_bytes(B, Np, phase_hop, Fw, P, os_), phase_c.device)
         with _on(phase_c.device):
-            rc = lib.golf_glottal_osc_fwd(_ptr(phase_c), _ptr(w_c), _ptr(table_c), _ptr(dk), _ptr(out), B, Np, phase_hop, Fw,
-                                          w_hop, n_tab, P, os_, zeros, mode, 1 if equal_energy else 0, _ptr(ws), ws.numel(), _stream())
+            if p0 is None:
+                rc = lib.golf_glottal_osc_fwd(_ptr(phase_c), _ptr(w_c), _ptr(table_c), _ptr(dk), _ptr(out), B, Np, phase_hop, Fw,
+                                              w_hop, n_tab, P, os_, zeros, mode, 1 if equal_energy else 0, _ptr(ws), ws.numel(), _stream())
+            else:
+                rc = lib.golf_glottal_osc_fwd_from(_ptr(phase_c), _ptr(w_c), _ptr(table_c), _ptr(dk), _ptr(out), _ptr(p0), B, Np,
+                                                   phase_hop, Fw, w_hop, n_tab, P, os_, zeros, mode, 1 if equal_energy else 0,
+                                                   _ptr(ws), ws.numel(), _stream())
         check(rc, "golf_glottal_osc_fwd")
+        if p0 is not None and any(ctx.needs_input_grad[:3]):
+            raise GolfError("glottal_osc: the adjoint does not take an initial phase (streaming is an inference path)")
         ctx.save_for_backward(phase_c, w_c, table_c, dk)
         ctx.geom = (phase_hop, w_hop, os_, zeros, equal_energy, mode)
         return out
@@ -437,7 +451,7 @@ class _GlottalOsc(torch.autograd.Function):
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[2]:
             raise GolfError("glottal_osc: gradients w.r.t. phase / table are not implemented (detach f0; trainable=False)")
         if not ctx.needs_input_grad[1]:
-            return (None,) * 9
+            return (None,) * 10
         phase_c, w_c, table_c, dk = ctx.saved_tensors
         phase_hop, w_hop, os_, zeros, equal_energy, mode = ctx.geom
         gout = _cuda_f32(gout, "gout")
@@ -452,14 +466,15 @@ class _GlottalOsc(torch.autograd.Function):
                                             phase_hop, Fw, w_hop, n_tab, P, os_, zeros, mode, 1 if equal_energy else 0,
                                             _ptr(ws), ws.numel(), _stream())
         check(rc, "golf_glottal_osc_bwd_w")
-        return None, d_w, None, None, None, None, None, None, None
+        return None, d_w, None, None, None, None, None, None, None, None
 
 
 def glottal_osc(phase, phase_hop: int, w, w_hop: int, table, dec_kernel=None, oversampling: int = 1,
-                equal_energy: bool = False, accumulate: str = "exact") -> torch.Tensor:
-    """IndexedGlottalFlowTable.forward; differentiable in the table-selection weight `w`."""
+                equal_energy: bool = False, accumulate: str = "exact", phase0=None) -> torch.Tensor:
+    """IndexedGlottalFlowTable.forward; differentiable in the table-selection weight `w`.  phase0 [B]: running
+    phase (cycles) each utterance starts from (a per-utterance constant `phase_offset`, exact-phase mode)."""
     return _GlottalOsc.apply(phase, w, table, dec_kernel, int(phase_hop), int(w_hop), int(oversampling), bool(equal_energy),
-                             _OSC_MODES[accumulate])
+                             _OSC_MODES[accumulate], phase0)
 
 
 def wavetable_read(wrapped, tables, hop_tab: int) -> torch.Tensor:

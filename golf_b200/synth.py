@@ -127,13 +127,18 @@ class IndexedGlottalFlowTable(GlottalFlowTable):
     def forward(self, phase, table_select_weight, phase_offset=None):
         w = plain(table_select_weight)
         assert w.dim() == 2
-        if phase_offset is not None:
-            raise NotImplementedError("phase_offset is not used by the GOLF configs and is not fused")
+        p0 = None
+        if phase_offset is not None:  # models/synth.py:251-252; a constant per utterance rides on the phase prefix
+            p0 = plain(phase_offset).reshape(w.shape[0], -1)
+            if p0.shape[1] != 1:
+                raise NotImplementedError("phase_offset: only one value per utterance ([B] or [B,1]) is fused")
+            if self.phase_accumulation != "exact":
+                raise NotImplementedError("phase_offset needs phase_accumulation = 'exact'")
         if CHECK_INPUTS == "sync":
             assert bool(((w >= 0) & (w <= 1)).all()), "table_select_weight must lie in [0, 1]"
         dk = self.decimater.kernel if self.oversampling > 1 else None
         y = G.glottal_osc(plain(phase), hop_of(phase), w, hop_of(table_select_weight), self.table, dk,
-                          self.oversampling, self.equal_energy, self.phase_accumulation)
+                          self.oversampling, self.equal_energy, self.phase_accumulation, p0)
         return like(phase, y, 1)
 
 

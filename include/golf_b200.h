@@ -177,6 +177,13 @@ int golf_glottal_osc_fwd(const float *phase, const float *w, const float *table,
                          int Fw, int w_hop, int n_tab, int P, int os, int zeros,
                          int accumulate, int flags, void *workspace, size_t workspace_bytes,
                          void *stream);
+/* Same with an initial running phase phase0 [B] (cycles, float64; `phase_offset` of models/synth.py:195-218,251-252
+ * for a per-utterance constant): the stream continues where a previous call stopped.  Exact-phase mode only. */
+int golf_glottal_osc_fwd_from(const float *phase, const float *w, const float *table,
+                              const float *dec_kernel, float *out, const double *phase0, int B, int Np,
+                              int phase_hop, int Fw, int w_hop, int n_tab, int P, int os, int zeros,
+                              int accumulate, int flags, void *workspace, size_t workspace_bytes,
+                              void *stream);
 /* Adjoint w.r.t. the selection weight: gout [B, n_out] -> d_w [B,Fw] (same geometry arguments
  * and workspace size as the forward; the gradient w.r.t. phase is not provided -- the shipped
  * configs detach f0).  Accumulated with float atomics (last bit not reproducible). */
