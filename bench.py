@@ -306,6 +306,22 @@ def run_gpu(args):
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
                 "note": "FP32-issue/latency bound by design (M(M+1) FMA per sample for the time-parallel split), see DESIGN.md"}
 
+    # ---- BASELINE.json configs[1]: the GOLF-ff decoder (frame-wise filter) on the same controls, device-resident,
+    # reported beside the headline (never instead of it); a failure here must not cost the main line
+    ff = None
+    try:
+        if world > 1:
+            raise RuntimeError("N = 1 only (no collective inside an optional measurement)")
+        with torch.no_grad():
+            dec_ff = build_decoder(dev, "ff")
+            graphed_ff = [GraphedSynth(dec_ff, params_of(s)) for s in dev_sets]
+        ms_ff, _, out_ff = timed(lambda i: graphed_ff[i % N_SETS](**params_of(dev_sets[i % N_SETS])), args.steps, args.warmup)
+        ff = {"workload": "GOLF-ff decoder forward (cfg/ae/decoder/golf.yaml: LTVMinimumPhaseFilter, hanning 960), same controls",
+              "value": total * args.steps / (ms_ff * 1e-3), "unit": "samples/s", "ms_per_step": ms_ff / args.steps,
+              "output_samples_per_utterance": int(out_ff.shape[1])}
+    except Exception as e:  # noqa: BLE001
+        ff = None if world > 1 else {"error": f"{type(e).__name__}: {e}"[:200]}
+
     if rank != 0:
         return None
     line = {
@@ -317,7 +333,7 @@ def run_gpu(args):
                 "ms_per_step": ms_e2e / args.steps, "pipeline": f"{DEPTH} slots, H2D / graph replay / D2H on three streams",
                 "serial_ms_per_step": ms_ser / args.steps},
         "gpu_launches": int(launches), "roofline": roof, "output_samples_per_utterance": int(n_out),
-        "rtf": (ms / args.steps * 1e-3) / (BATCH * SECONDS),
+        "rtf": (ms / args.steps * 1e-3) / (BATCH * SECONDS), "golf_ff": ff,
     }
     if world == 1 and not args.no_cpu:
         val, cores, dt = run_cpu(args.cpu_steps, 1, BATCH)
