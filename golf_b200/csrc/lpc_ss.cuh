@@ -86,13 +86,22 @@ __device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y
 // Per step a lane issues ceil(MT/4) LDS.128 for its chunk's coefficient row and NC*MT FFMA.
 // Coefficient rows are interpolated (ATen arithmetic, negated) tile by tile by lanes mapped to
 // (chunk, group of TPL taps) whose frame pair sits in registers.
+#ifndef GOLF_RESP_NC
+#define GOLF_RESP_NC 5  // tuning experiments: -DGOLF_RESP_NC=3|4|6 (tools/resp_nc_sweep.sh)
+#endif
+#ifndef GOLF_RESP_WPB
+#define GOLF_RESP_WPB 4  // warps per CTA: they meet at a barrier every tile, which keeps them in the same part of the 48 KB loop body (81 -> 77 us; 8 per CTA: the same)
+#endif
 template <int MP>
 struct RespCfg {
-  static constexpr int NC = (MP == 24) ? 5 : 4;  // columns per lane
+  static constexpr int NC = (MP == 24) ? GOLF_RESP_NC : 4;  // columns per lane
+  // resident one-warp CTAs per SM the register budget is set for: NC*MP state registers + ~80
+  static constexpr int RES = MP > 24 ? 4 : (NC <= 3 ? 16 : (NC == 4 ? 12 : 8));
 };
 
 template <int MP, int MT, int FORM>
-__global__ void __launch_bounds__(32, (MP <= 24 ? 8 : 4)) ss_response_kernel(SsParams p) {
+__global__ void __launch_bounds__(32 * GOLF_RESP_WPB, (GOLF_RESP_WPB > 1 ? 1 : RespCfg<MP>::RES)) ss_response_kernel(SsParams p) {
+  constexpr int WPB = GOLF_RESP_WPB;
   constexpr int NC = RespCfg<MP>::NC;
   constexpr int LPC = (MT + 1 + NC - 1) / NC;  // lanes per chunk
   constexpr int CPW = 32 / LPC;                // chunks per warp
@@ -104,17 +113,21 @@ __global__ void __launch_bounds__(32, (MP <= 24 ? 8 : 4)) ss_response_kernel(SsP
   constexpr int SQ = (MP + TPL - 1) / TPL;                // staging lanes used per chunk
   constexpr int NQ = (MT + 3) / 4;                        // coefficient quads read per step
   static_assert(LPC * CPW <= 32 && SQ * CPW <= 32 && MT <= MP && MT >= 1, "response kernel geometry");
-  extern __shared__ __align__(128) float smem[];
-  const int lane = threadIdx.x;
+  extern __shared__ __align__(128) float smem_all[];
+  constexpr int kWarpFloats = (CPW * TSTR + ROWS * 5 + 31) / 32 * 32;  // shared memory of one warp
+  float* smem = smem_all + (WPB > 1 ? (threadIdx.x >> 5) * kWarpFloats : 0);
+  const int lane = threadIdx.x & 31;
   const int nresp = p.C - 1;
   const int wps = (nresp + CPW - 1) / CPW;  // warps per sequence
-  const int wg = blockIdx.x;
-  if (wg >= p.B * wps) return;
+  const int wg_raw = blockIdx.x * WPB + (threadIdx.x >> 5);
+  const bool warp_on = wg_raw < p.B * wps;
+  if (WPB == 1 && !warp_on) return;
+  const int wg = warp_on ? wg_raw : p.B * wps - 1;  // WPB > 1: idle warps shadow the last task (they must reach the barriers)
   const int b = wg / wps, w0 = (wg % wps) * CPW;
   const int gi = min(lane / LPC, CPW - 1), li = lane % LPC;
   const bool lane_on = lane < LPC * CPW;
   const int pi = w0 + gi;
-  const bool chunk_on = lane_on && pi < nresp;
+  const bool chunk_on = warp_on && lane_on && pi < nresp;
 
   float* ctile = smem;                                       // [CPW][MP rows][MP taps] negated coefficients
   float* etile = ctile + CPW * TSTR;                         // [CPW][MP] chunk inputs
@@ -176,6 +189,7 @@ __global__ void __launch_bounds__(32, (MP <= 24 ? 8 : 4)) ss_response_kernel(SsP
 
 #pragma unroll 1
   for (int tile = 0; tile < p.Lc / MP; ++tile) {
+    if (WPB > 1) __syncthreads();  // keeps the CTA's warps in the same tile of the (large) loop body
     __syncwarp();
     // ---- stage A: interpolation weights of every row + the inputs prefetched for this tile
 #pragma unroll
@@ -855,13 +869,15 @@ int launch_response(const SsParams& p, cudaStream_t st) {
   constexpr int LPC = (MT + 1 + NC - 1) / NC, CPW = 32 / LPC;
   const int nresp = p.C - 1;
   const int wps = ceil_div(nresp, CPW);
-  const size_t sm = (size_t)(CPW * (MP * MP + 4) + CPW * MP * 5) * sizeof(float);
+  constexpr int WPB = GOLF_RESP_WPB;
+  const size_t sm = (size_t)((CPW * (MP * MP + 4) + CPW * MP * 5 + 31) / 32 * 32) * sizeof(float) * WPB;
+  if (sm > 220 * 1024) return GOLF_ERR_UNSUPPORTED;
   static bool attr = false;
   if (!attr && sm > 48 * 1024) {
     GOLF_CUDA(cudaFuncSetAttribute(ss_response_kernel<MP, MT, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     attr = true;
   }
-  ss_response_kernel<MP, MT, FORM><<<p.B * wps, 32, sm, st>>>(p);
+  ss_response_kernel<MP, MT, FORM><<<ceil_div(p.B * wps, WPB), 32 * WPB, sm, st>>>(p);
   GOLF_CHECK_LAUNCH();
   return GOLF_OK;
 }
