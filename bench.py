@@ -345,6 +345,12 @@ def run_gpu(args):
 
 
 def main():
+    # stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner with
+    # printf when NCCL_DEBUG is WARN/VERSION/INFO): keep a private handle on the real stdout for the result and
+    # point file descriptor 1 at stderr for everything else.
+    sys.stdout.flush()
+    result_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -358,11 +364,11 @@ def main():
         if int(os.environ.get("RANK", 0)) != 0:
             return
         args.steps = min(args.steps, 20)  # ~0.7 s per pass on 8 cores: keep the arm within minutes
-        print(json.dumps(cpu_line(args)))
+        print(json.dumps(cpu_line(args)), file=result_out, flush=True)
         return
     line = run_gpu(args)
     if line is not None:
-        print(json.dumps(line))
+        print(json.dumps(line), file=result_out, flush=True)
 
 
 if __name__ == "__main__":
