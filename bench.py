@@ -180,6 +180,25 @@ def build_decoder(dev, variant: str = "ss"):
     return dec.to(dev).eval()
 
 
+def _bind_to_gpu_numa_node(index: int) -> None:
+    """Pin this rank to the CPU cores next to its GPU before any pinned host buffer is allocated (first touch puts
+    the pages on that NUMA node): with one rank per GPU the H2D / D2H copies of the e2e measurement then stay on
+    the GPU's own socket instead of crossing the inter-socket link.  Best effort."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:  # noqa: BLE001  (no NVML, no permission, single-node box: nothing to do)
+        pass
+
+
 def run_gpu(args):
     import torch.distributed as dist
 
@@ -195,6 +214,8 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device -- golf_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1:  # N = 1 keeps every host core for the cpu_baseline leg
+        _bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(2434 + rank)
