@@ -94,13 +94,20 @@ class PipelinedSynth:
         pipe.wait(t)                                 # out_host ([B, pipe.out_len], pinned, contiguous) is valid
     """
 
-    def __init__(self, decoder: torch.nn.Module, example_params: Dict[str, Any], depth: int = 3):
+    def __init__(self, decoder: torch.nn.Module, example_params: Dict[str, Any], depth: int = 3, compute_streams: int = 1):
+        """compute_streams > 1: consecutive replays alternate between that many streams, so the latency-bound
+        tail of one decoder pass (serial stitch / solve, a few SMs busy) overlaps the throughput kernels of the
+        next; depth must be a multiple of it (a slot always replays on the same stream)."""
+        if depth % compute_streams:
+            raise ValueError("PipelinedSynth: depth must be a multiple of compute_streams")
         self.slots = [GraphedSynth(decoder, example_params) for _ in range(depth)]
         out = plain(self.slots[0]._out)
         self.device = out.device
         self.out_len = out.shape[1]
         self.kernels_captured = self.slots[0].kernels_captured
-        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(device=self.device) for _ in range(3))
+        self.s_in, self.s_out = (torch.cuda.Stream(device=self.device) for _ in range(2))
+        self.s_runs = [torch.cuda.Stream(device=self.device) for _ in range(compute_streams)]
+        self.s_run = self.s_runs[0]
         self._ran = [None] * depth    # replay of the slot's previous use finished
         self._read = [None] * depth   # copy-out of the slot's previous use finished
         self._n = 0
@@ -109,12 +116,12 @@ class PipelinedSynth:
     def fork_from(self, stream=None):
         """order the pipeline after everything already enqueued on `stream` (default: current)"""
         stream = stream or torch.cuda.current_stream(self.device)
-        for s in (self.s_in, self.s_run, self.s_out):
+        for s in (self.s_in, self.s_out, *self.s_runs):
             s.wait_stream(stream)
 
     def join_into(self, stream=None):
         stream = stream or torch.cuda.current_stream(self.device)
-        for s in (self.s_in, self.s_run, self.s_out):
+        for s in (self.s_in, self.s_out, *self.s_runs):
             stream.wait_stream(s)
 
     def submit(self, out_host: torch.Tensor, **host_params) -> int:
@@ -126,13 +133,14 @@ class PipelinedSynth:
             self.h2d_bytes = slot.load(**host_params)
             loaded = torch.cuda.Event()
             loaded.record(self.s_in)
-        with torch.cuda.stream(self.s_run):
-            self.s_run.wait_event(loaded)
+        s_run = self.s_runs[k % len(self.s_runs)]
+        with torch.cuda.stream(s_run):
+            s_run.wait_event(loaded)
             if self._read[k] is not None:
-                self.s_run.wait_event(self._read[k])
+                s_run.wait_event(self._read[k])
             y = plain(slot.replay())
             self._ran[k] = torch.cuda.Event()
-            self._ran[k].record(self.s_run)
+            self._ran[k].record(s_run)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self._ran[k])
             # out_host must be a CONTIGUOUS pinned [B, out_len] tensor: a strided host destination makes
@@ -145,3 +153,37 @@ class PipelinedSynth:
 
     def wait(self, ticket: int) -> None:
         self._read[ticket].synchronize()
+
+
+class ReplayRing:
+    """Device-resident throughput mode: a ring of GraphedSynth instances (one per resident input set) replayed
+    round-robin on `streams` CUDA streams, so that `streams` decoder passes are in flight at a time -- the serial,
+    latency-bound tail of one pass (stitch / solve: a few SMs) runs under the throughput kernels of the next.
+    A graph always replays on the same stream (len(graphs) must be a multiple of `streams`), so a graph never
+    overlaps itself and its static buffers are never in use twice.
+
+        ring = ReplayRing(graphs, streams=2)
+        ring.fork_from(); [ring.submit(i) for i in range(k)]; ring.join_into()
+    """
+
+    def __init__(self, graphs, streams: int = 2):
+        if len(graphs) % streams:
+            raise ValueError("ReplayRing: the number of graphs must be a multiple of the number of streams")
+        self.graphs = list(graphs)
+        self.device = plain(self.graphs[0]._out).device
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(streams)]
+
+    def fork_from(self, stream=None):
+        stream = stream or torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(stream)
+
+    def join_into(self, stream=None):
+        stream = stream or torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            stream.wait_stream(s)
+
+    def submit(self, i: int):
+        g = self.graphs[i % len(self.graphs)]
+        with torch.cuda.stream(self.streams[i % len(self.streams)]):
+            return g.replay()

@@ -303,3 +303,33 @@ def test_precise_zero_phase_fir_reference_golden():
     cfg = {"class_path": "golf_b200.filters.LTVZeroPhaseFIRFilter", "init_args": {"window": "hanning", "conv_method": "direct", "n_mag": 256}}
     assert filters.convert2samplewise({"noise_filter": cfg})["noise_filter"] == {
         "class_path": "golf_b200.filters.LTVZeroPhaseFIRFilterPrecise", "init_args": {"window": "hanning", "n_mag": 256}}
+
+
+def test_replay_ring_concurrent_passes_do_not_interfere():
+    """several decoder passes in flight on different streams (golf_b200.graphs.ReplayRing): every graph owns its
+    workspaces, so concurrent replays must give exactly what one-at-a-time replays give (deterministic noise)"""
+    from golf_b200.graphs import GraphedSynth, ReplayRing
+
+    g = golden("stages_ss")
+    dec = build_decoder("ss", g)
+    dec.noise_generator = fixed_noise(T(g["noise"]).to(DEV))
+    graphs = []
+    with torch.no_grad():
+        for s in range(4):
+            p = _ss_params(g)
+            gain = p["end_filter_params"][0]
+            p["end_filter_params"] = (type(gain)(gain.as_tensor() * (1 + 0.25 * s), hop_length=gain.hop_length), p["end_filter_params"][1])
+            graphs.append(GraphedSynth(dec, p))
+        ref = [gr.replay().as_tensor().clone() for gr in graphs]
+        torch.cuda.synchronize()
+        for gr in graphs:
+            gr._out.as_tensor().zero_()
+        ring = ReplayRing(graphs, streams=4)
+        ring.fork_from()
+        for i in range(12):
+            ring.submit(i)
+        ring.join_into()
+        torch.cuda.synchronize()
+    for gr, r in zip(graphs, ref):
+        assert torch.equal(gr._out.as_tensor(), r)
+    assert not torch.equal(ref[0], ref[1])
