@@ -333,3 +333,37 @@ def test_replay_ring_concurrent_passes_do_not_interfere():
     for gr, r in zip(graphs, ref):
         assert torch.equal(gr._out.as_tensor(), r)
     assert not torch.equal(ref[0], ref[1])
+
+
+def test_harmonic_plus_noise_synth_matches_oracle_composition(oracle):
+    """HarmonicPlusNoiseSynth (GOLF-v1, cfg/ae/decoder/golf-v1.yaml; models/hpn.py:31-57): the harmonic branch goes
+    through the frame-wise LPC filter alone, the FIR-filtered noise is added after it, then the room filter --
+    checked against the same composition of the CPU restatements, on the reference's controls"""
+    from golf_b200 import filters, hpn, synth
+    from golf_b200.audiotensor import AudioTensor
+
+    g = golden("stages_ff")
+    H, W = int(g["hop"]), int(g["window_length"])
+    dec = hpn.HarmonicPlusNoiseSynth(
+        synth.DownsampledIndexedGlottalFlowTable(hop_rate=10, in_channels=64, oversampling=4, equal_energy=True, lf_v2=True, points=2048),
+        fixed_noise(T(g["noise"]).to(DEV)), filters.LTVMinimumPhaseFilter(window="hanning", window_length=W, lpc_order=22),
+        filters.LTVZeroPhaseFIRFilter("hanning", n_mag=256), filters.LTIAcousticFilter(128, "fft")).to(DEV).eval()
+    dec.end_filter.kernel.data = T(g["room_kernel"]).to(DEV)
+    dec.harm_oscillator.phase_accumulation = "aten_cpu"
+    A = lambda k, hop: AudioTensor(T(g[k]).to(DEV), hop_length=hop)
+    with torch.no_grad():
+        out = dec(phase=A("phase", int(g["phase_hop"])), harm_oscillator_params=(A("w", int(g["w_hop"])),), noise_generator_params=(),
+                  harm_filter_params=(A("gain", H), A("a", H)), noise_filter_params=(A("log_mag", H),))
+    harm = T(g["harm"])  # the reference oscillator's own output (pinned by test_oscillator_reference_golden)
+    hf = oracle.lpc_ff(harm, T(g["gain"]), T(g["a"]), H, W)
+    nf = T(g["noise_filtered"])  # the reference noise branch (same module, same noise)
+    n = min(hf.shape[1], nf.shape[1])
+    ref = oracle.room_fir(hf[:, :n] + nf[:, :n], T(g["room_kernel"]))
+    assert out.hop_length == 1 and tuple(out.shape) == tuple(ref.shape)
+    assert rel_rms(out.as_tensor(), ref) < REL_TOL
+    # voicing scales the phase (models/hpn.py:43-46)
+    with torch.no_grad():
+        out0 = dec(phase=A("phase", int(g["phase_hop"])), harm_oscillator_params=(A("w", int(g["w_hop"])),), noise_generator_params=(),
+                   harm_filter_params=(A("gain", H), A("a", H)), noise_filter_params=(A("log_mag", H),),
+                   voicing=AudioTensor(torch.full_like(T(g["phase"]), 0.5).to(DEV), hop_length=int(g["phase_hop"])))
+    assert torch.isfinite(out0.as_tensor()).all() and not torch.equal(out0.as_tensor(), out.as_tensor())
