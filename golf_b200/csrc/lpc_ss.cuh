@@ -75,19 +75,20 @@ __device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y
 //    lane-FMAs per cycle, so every coefficient a lane reads must feed >= 4 of its FMAs: a lane owns
 //    NC columns of one chunk's [Phi | z] (LPC = ceil((MT+1)/NC) lanes per chunk, CPW = 32/LPC chunks
 //    side by side in a warp);
-//  * the register file: 4 schedulers x 16384 registers.  NC*MP state registers + a coefficient row
-//    need ~200 registers per lane, which fits exactly TWO warps per scheduler -- so the kernel is
-//    built to run well at 8 warps per SM: CTA = one warp (the block scheduler spreads 1-warp CTAs
-//    evenly), NC = 5 for the 24-slot ring (M = 22: 5 lanes x 5 columns, 6 chunks per warp, 30 lanes,
-//    1056 warps at B = 32 = 1.8 per scheduler), and each lane's NC FMA chains are independent so one
-//    warp alone can issue an FMA per cycle.
+//  * the register file: 4 schedulers x 16384 registers.  NC*MP state registers + a coefficient row per lane:
+//    NC = 5 (M = 22: 5 lanes x 5 columns, 6 chunks per warp) needs every register of the SM for 8 warps and is the
+//    fastest mapping for ONE decoder pass at a time by ~2 %; NC = 3 (8 lanes per chunk, 4 chunks per warp, all
+//    32 lanes busy, 168 registers, 12 resident warps) is as fast alone (76 vs 78 us) and leaves a third of the
+//    register file to the other kernels when several passes are in flight (bench.py `value`: 7.19e9 vs 6.77e9
+//    samples/s), so it is the default.  CTAs are 4 warps that meet at a barrier every tile, and each lane's NC FMA
+//    chains are independent so one warp alone can keep the pipe busy.
 // MT = taps actually summed (M <= MT <= MP): the ring keeps MP outputs so that Lc % MP == 0 tiles
 // work, but only MT products per column and step are issued (M = 22: 22 of 24, 8 % fewer FMAs).
 // Per step a lane issues ceil(MT/4) LDS.128 for its chunk's coefficient row and NC*MT FFMA.
 // Coefficient rows are interpolated (ATen arithmetic, negated) tile by tile by lanes mapped to
 // (chunk, group of TPL taps) whose frame pair sits in registers.
 #ifndef GOLF_RESP_NC
-#define GOLF_RESP_NC 5  // tuning experiments: -DGOLF_RESP_NC=3|4|6 (tools/resp_nc_sweep.sh)
+#define GOLF_RESP_NC 3  // columns per lane at padded order 24; -DGOLF_RESP_NC=4|5|6 for experiments (tools/resp_nc_sweep.sh)
 #endif
 #ifndef GOLF_RESP_WPB
 #define GOLF_RESP_WPB 4  // warps per CTA: they meet at a barrier every tile, which keeps them in the same part of the 48 KB loop body (81 -> 77 us; 8 per CTA: the same)
@@ -96,11 +97,15 @@ template <int MP>
 struct RespCfg {
   static constexpr int NC = (MP == 24) ? GOLF_RESP_NC : 4;  // columns per lane
   // resident one-warp CTAs per SM the register budget is set for: NC*MP state registers + ~80
-  static constexpr int RES = MP > 24 ? 4 : (NC <= 3 ? 16 : (NC == 4 ? 12 : 8));
+#ifdef GOLF_RESP_RES
+  static constexpr int RES = MP > 24 ? 4 : GOLF_RESP_RES;
+#else
+  static constexpr int RES = MP > 24 ? 4 : (NC <= 4 ? 12 : 8);
+#endif
 };
 
 template <int MP, int MT, int FORM>
-__global__ void __launch_bounds__(32 * GOLF_RESP_WPB, (GOLF_RESP_WPB > 1 ? 1 : RespCfg<MP>::RES)) ss_response_kernel(SsParams p) {
+__global__ void __launch_bounds__(32 * GOLF_RESP_WPB, (RespCfg<MP>::RES / GOLF_RESP_WPB > 0 ? RespCfg<MP>::RES / GOLF_RESP_WPB : 1)) ss_response_kernel(SsParams p) {
   constexpr int WPB = GOLF_RESP_WPB;
   constexpr int NC = RespCfg<MP>::NC;
   constexpr int LPC = (MT + 1 + NC - 1) / NC;  // lanes per chunk

@@ -11,14 +11,14 @@ for NC in "$@"; do
     if [ $n = lpc_ss_mp ]; then
       for mp in 4 8 12 16 20 24 32 40; do
         nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden --expt-relaxed-constexpr \
-          -DGOLF_MP=$mp -DGOLF_RESP_NC=${NC%%w*} -DGOLF_RESP_WPB=${WPB:-1} -I include -c $f -o $OBJ/${n}$mp.o &
+          -DGOLF_MP=$mp -DGOLF_RESP_NC=${NC%%w*} -DGOLF_RESP_WPB=${WPB:-1} ${RESDEF} -I include -c $f -o $OBJ/${n}$mp.o &
       done
     else
       nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden --expt-relaxed-constexpr \
-        -DGOLF_RESP_NC=${NC%%w*} -DGOLF_RESP_WPB=${WPB:-1} -I include -c $f -o $OBJ/$n.o &
+        -DGOLF_RESP_NC=${NC%%w*} -DGOLF_RESP_WPB=${WPB:-1} ${RESDEF} -I include -c $f -o $OBJ/$n.o &
     fi
   done
   wait
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o golf_b200/_lib/libgolf_b200_nc${NC}w${WPB:-1}.so $OBJ/*.o -Xlinker --no-undefined -lcudart_static -ldl -lrt -lpthread
-  echo built golf_b200/_lib/libgolf_b200_nc${NC}w${WPB:-1}.so
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o golf_b200/_lib/libgolf_b200_nc${NC}w${WPB:-1}${TAG}.so $OBJ/*.o -Xlinker --no-undefined -lcudart_static -ldl -lrt -lpthread
+  echo built golf_b200/_lib/libgolf_b200_nc${NC}w${WPB:-1}${TAG}.so
 done
