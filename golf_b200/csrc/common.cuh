@@ -54,6 +54,16 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: launch sites keep one bit per device ordinal in a
+// static mask (one process per GPU is the supported mode, but a process that drives several must not trip here)
+static inline bool first_use_on_device(unsigned long long& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+  if ((mask >> dev) & 1ull) return false;
+  mask |= 1ull << dev;
+  return true;
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

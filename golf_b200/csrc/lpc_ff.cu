@@ -450,8 +450,11 @@ template <class Filt, bool STORE_V, bool ALIGNED>
 static int launch_ff_fwd_a(const FfParams& p, cudaStream_t st) {
   const size_t sm = ff_smem_bytes(p, STORE_V ? 32 * (Filt::TILE + 1) : 0);
   if (sm > 220 * 1024) return GOLF_ERR_UNSUPPORTED;
-  static size_t sm_allowed = 48 * 1024;  // per instantiation
-  if (sm > sm_allowed) {
+  static size_t sm_allowed_dev[64];  // per instantiation and device (0: the 48 KB default)
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  size_t& sm_allowed = sm_allowed_dev[dev_ & 63];
+  if (sm > 48 * 1024 && sm > sm_allowed) {
     GOLF_CUDA(cudaFuncSetAttribute(ff_forward_kernel<Filt, STORE_V, ALIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     sm_allowed = sm;
   }
@@ -471,8 +474,11 @@ static int launch_ff_bwd(const FfParams& pf, const FfParams& pb, cudaStream_t st
   if (rc) return rc;
   const size_t sm = ff_smem_bytes(pb, 2 * 32 * (2 * MP + 1));
   if (sm > 220 * 1024) return GOLF_ERR_UNSUPPORTED;
-  static size_t sm_allowed = 48 * 1024;
-  if (sm > sm_allowed) {
+  static size_t sm_allowed_dev[64];
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  size_t& sm_allowed = sm_allowed_dev[dev_ & 63];
+  if (sm > 48 * 1024 && sm > sm_allowed) {
     GOLF_CUDA(cudaFuncSetAttribute(ff_backward_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     sm_allowed = sm;
   }

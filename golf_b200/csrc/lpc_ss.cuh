@@ -877,10 +877,9 @@ int launch_response(const SsParams& p, cudaStream_t st) {
   constexpr int WPB = GOLF_RESP_WPB;
   const size_t sm = (size_t)((CPW * (MP * MP + 4) + CPW * MP * 5 + 31) / 32 * 32) * sizeof(float) * WPB;
   if (sm > 220 * 1024) return GOLF_ERR_UNSUPPORTED;
-  static bool attr = false;
-  if (!attr && sm > 48 * 1024) {
+  static unsigned long long attr = 0;
+  if (sm > 48 * 1024 && first_use_on_device(attr)) {
     GOLF_CUDA(cudaFuncSetAttribute(ss_response_kernel<MP, MT, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    attr = true;
   }
   ss_response_kernel<MP, MT, FORM><<<ceil_div(p.B * wps, WPB), 32 * WPB, sm, st>>>(p);
   GOLF_CHECK_LAUNCH();
@@ -905,12 +904,11 @@ int launch_mp(const SsParams& p, bool generic, int passes, cudaStream_t st) {
       ((size_t)kStitchStages * kStitchGroup * ((MP + 1) * MP + 2 * MP) + 2 * MP) * sizeof(float) + kStitchStages * 8 + 128;
   constexpr int MCS = MP >= 8 ? MP - 2 : 0;  // compile-time column counts: M == MP - 2 and M == MP
   const int mc = p.M == MP ? MP : (MCS && p.M == MCS ? MCS : 0);
-  static bool attr2 = false;
-  if (!attr2) {
+  static unsigned long long attr2 = 0;
+  if (first_use_on_device(attr2)) {
     GOLF_CUDA(cudaFuncSetAttribute(ss_stitch_kernel<MP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stitch));
     GOLF_CUDA(cudaFuncSetAttribute(ss_stitch_kernel<MP, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stitch));
     if (MCS) GOLF_CUDA(cudaFuncSetAttribute(ss_stitch_kernel<MP, (MCS ? MCS : MP)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stitch));
-    attr2 = true;
   }
   const int G = ceil_div(p.C, 32);
   const size_t sm_solve = (FORM == 0 ? 1 : 2) * 32 * (MP + 1) * sizeof(float);

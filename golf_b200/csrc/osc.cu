@@ -842,12 +842,11 @@ static int glottal_osc_fwd(const float* phase, const float* w, const float* tabl
     osc_knot_prefix_q64_kernel<<<dim3(kPrefSplit / kPrefWarps, B), 32 * kPrefWarps, 0, st>>>(phase, reinterpret_cast<unsigned long long*>(pref), totals, Np,
                                                                                           L.hp, (float)os, span);
     GOLF_CHECK_LAUNCH();
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (first_use_on_device(attr)) {
       GOLF_CUDA(cudaFuncSetAttribute(osc_flow_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       GOLF_CUDA(cudaFuncSetAttribute(osc_flow_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       GOLF_CUDA(cudaFuncSetAttribute(osc_flow_v2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr = true;
     }
     switch (os) {
       case 1: GOLF_CUDA(launch_pdl(osc_flow_v2_kernel<1>, grid, dim3(128), sm2, st, p, w, table, n_tab)); break;
@@ -925,12 +924,11 @@ GOLF_API int golf_glottal_osc_bwd_w(const float* gout, const float* phase, const
   const size_t smv2 = ((size_t)q.f.plen + (size_t)os * q.f.kp12 + (size_t)kOscRows * P) * sizeof(float);
   if (g_osc_v2 && accumulate == 0 && (os == 1 || os == 2 || os == 4) && P >= 4 && (P & (P - 1)) == 0 && smv2 <= 200 * 1024 &&
       (int64_t)kOscTile * os < (int64_t)q.f.hop_tab) {
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (first_use_on_device(attr)) {
       GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr = true;
     }
     switch (os) {
       case 1: osc_dw_v2_kernel<1><<<grid, 128, smv2, st>>>(q); break;
