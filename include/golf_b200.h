@@ -17,13 +17,19 @@
  *   golf_lpc_ff_*            models/filters.py:131-184 LTVMinimumPhaseFilter.forward
  *                            (unfold, models/lpc.py:11-16 lpc_synthesis -> torchaudio lfilter, Hann OLA)
  *   golf_biquad_ff_fwd       models/lpc.py:94-131     BatchSecondOrderLPCSynth.forward
- *   golf_lpc_inverse_fwd     models/filters.py:186-195 reverse() + models/utils.py:433-441 fir_filt
+ *   golf_lpc_inverse_fwd/bwd models/filters.py:186-195 reverse() + models/utils.py:433-441 fir_filt, and its
+ *                            autograd (inverse-target training, ltng/vocoder.py:192-198)
  *   golf_noise_fir_*         models/filters.py:350-384 LTVZeroPhaseFIRFilter.forward (block FIR)
  *   golf_room_fir_*          models/filters.py:443-450 LTIAcousticFilter.forward
  *   golf_glottal_osc_fwd     models/synth.py:213-263   IndexedGlottalFlowTable.forward
+ *   golf_glottal_osc_fwd_from  the same with phase_offset (models/synth.py:195-218,251-252) as a per-utterance constant
+ *   golf_glottal_osc_bwd_w   autograd of the above w.r.t. table_select_weight
  *   golf_wavetable_read_fwd  models/synth.py:124-177   GlottalFlowTable.generate
  *   golf_linear_upsample     models/audiotensor/audiotensor.py:11-17 linear_upsample
- *   golf_rc2lpc_fwd          models/utils.py:581-593   rc2lpc (with the tanh*max_abs of filters.py:80)
+ *   golf_rc2lpc_fwd/bwd      models/utils.py:581-593   rc2lpc (with the tanh*max_abs of filters.py:80) and its autograd
+ *   golf_exp_to_complex      models/filters.py:295-296 `torch.exp(log_mag) + 0j` of get_zero_phase_fir
+ *   (golf_set_pdl, golf_fir_set_variant, golf_lpc_ss_set_*, golf_glottal_osc_set_variant: process-wide kernel
+ *    selection switches for A/B timing and tests; no reference counterpart)
  */
 #ifndef GOLF_B200_H_
 #define GOLF_B200_H_
@@ -35,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GOLF_B200_ABI_VERSION 2
+#define GOLF_B200_ABI_VERSION 3
 
 enum {
   GOLF_OK = 0,
