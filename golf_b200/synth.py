@@ -75,7 +75,9 @@ class GlottalFlowTable(OscillatorInterface):
         if lf_v2:
             table = lf_period_v2(self.R_d_values, **kwargs)
         else:
-            table = torch.stack([lf_period_v1(R_d=float(r), **kwargs) for r in self.R_d_values])
+            # the 0-dim float32 tensor goes through as it does in the reference (models/synth.py:83-84): its Newton
+            # iterations then run in float32 with the math.* calls evaluated on the float32-rounded arguments
+            table = torch.stack([lf_period_v1(R_d=r, **kwargs) for r in self.R_d_values])
         if table_type == "flow":
             table = table.cumsum(dim=1)
         elif table_type != "derivative":

@@ -119,8 +119,10 @@ def lf_period_v2(Rd: torch.Tensor, points: int = 1024) -> torch.Tensor:
     return torch.where(t < Te, rise, ret).squeeze()
 
 
-def lf_period_v1(R_d: float = 0.3, T_0: float = 5.0, n_iter_eps: int = 5, n_iter_a: int = 100, points: int = 1000) -> torch.Tensor:
-    """Iterative LF fit used by the ISMIR-23 checkpoints (models/utils.py:308-360)."""
+def lf_period_v1(R_d=0.3, T_0: float = 5.0, n_iter_eps: int = 5, n_iter_a: int = 100, points: int = 1000) -> torch.Tensor:
+    """Iterative LF fit used by the ISMIR-23 checkpoints (models/utils.py:308-360).  R_d may be a Python float or a
+    0-dim tensor; with a float32 tensor (what GlottalFlowTable passes, like the reference) every derived quantity
+    and both Newton loops are float32 tensors."""
     R_ap = 0.048 * R_d - 0.01
     R_kp = 0.118 * R_d + 0.224
     R_gp = 0.25 * R_kp * (0.5 + 1.2 * R_kp) / (0.11 * R_d - R_ap * (0.5 + 1.2 * R_kp))

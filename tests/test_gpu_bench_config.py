@@ -1,0 +1,136 @@
+"""GPU: element-wise parity at the sizes bench.py times (BASELINE.json configs[1], [2], [4]).
+
+The oracle finishes a 32 x 2 s decoder pass in ~0.1 s, so the benched configuration is checked
+sample by sample against it (float32 restatement AND float64 truth), on the same inputs bench.py
+uses (encoder-derived controls tiled to the batch + its synthetic f0 tracks), not only through
+size-independent properties.  Bar: 1e-4 relative RMS per utterance (north_star)."""
+import os
+import sys
+
+import pytest
+import torch
+
+from conftest import REL_TOL, ROOT, rel_rms, synthetic_controls
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def G():
+    from golf_b200 import functional
+
+    return functional
+
+
+@pytest.fixture(scope="module")
+def bench():
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import bench as b
+
+    return b
+
+
+@pytest.fixture(scope="module")
+def bench_set(bench):
+    return bench.make_inputs(1, bench.BATCH)[0]
+
+
+def test_ss_filter_at_bench_size(G, oracle, bench, bench_set):
+    """a10 at B = 32 x 2 s, M = 22, hop 240, encoder-derived controls, identical (excitation, coefficient) inputs"""
+    s = bench_set
+    ex = torch.randn(bench.BATCH, bench.T - bench.HOP, generator=torch.Generator().manual_seed(0))
+    ref32 = oracle.lpc_ss_fused(ex, s["gain"], s["a"], bench.HOP)
+    ref64 = oracle.lpc_ss_fused(ex, s["gain"], s["a"], bench.HOP, double=True)
+    y = G.lpc_ss(ex.to(DEV), s["gain"].to(DEV), s["a"].to(DEV), bench.HOP)
+    assert y.shape == ref32.shape == (bench.BATCH, (bench.FRAMES - 1) * bench.HOP + 1)
+    floor = rel_rms(ref32, ref64)
+    assert rel_rms(y, ref32) < REL_TOL and rel_rms(y, ref64) < REL_TOL
+    assert rel_rms(y, ref64) < 3 * floor  # as accurate as the reference's own float32 loop
+
+
+def test_ff_filter_at_bench_size(G, oracle, bench, bench_set):
+    """a11 at B = 32 x 2 s (6 400 frames of 960), hanning, centred"""
+    s = bench_set
+    ex = torch.randn(bench.BATCH, bench.T - bench.HOP, generator=torch.Generator().manual_seed(1))
+    ref = oracle.lpc_ff(ex, s["gain"], s["a"], bench.HOP, 4 * bench.HOP)
+    win = torch.hann_window(4 * bench.HOP).to(DEV)
+    y = G.lpc_ff(ex.to(DEV), s["gain"].to(DEV), s["a"].to(DEV), win, bench.HOP)
+    assert y.shape == ref.shape
+    assert rel_rms(y, ref) < 1e-5
+
+
+def _fixed_noise_decoder(bench, variant, noise_draw):
+    from golf_b200 import noise as gnoise
+    from golf_b200.audiotensor import AudioTensor
+
+    class Fixed(gnoise.NoiseInterface):
+        def forward(self, ref_, *args):
+            return AudioTensor(noise_draw[:, : ref_.shape[1]])
+
+    dec = bench.build_decoder(torch.device(DEV), variant)
+    dec.noise_generator = Fixed()
+    return dec
+
+
+@pytest.mark.parametrize("variant", ["ss", "ff"])
+def test_decoder_at_bench_size(oracle, bench, bench_set, variant):
+    """a1 at the benched configuration: the whole decoder, injected noise, sample-rate f0.  The oscillator
+    runs in its "aten_cpu" phase mode so both sides accumulate phase with the reference's arithmetic."""
+    from golf_b200.audiotensor import AudioTensor
+
+    s = bench_set
+    noise = torch.randn(bench.BATCH, bench.T, generator=torch.Generator().manual_seed(2))
+    dec = _fixed_noise_decoder(bench, variant, noise.to(DEV))
+    dec.harm_oscillator.phase_accumulation = "aten_cpu"
+    A = lambda t, hop: AudioTensor(t.to(DEV), hop_length=hop)
+    with torch.no_grad():
+        out = dec(phase=A(s["phase"], 1), harm_oscillator_params=(A(s["w"], 2400),), noise_generator_params=(),
+                  noise_filter_params=(A(s["log_mag"], bench.HOP),), end_filter_params=(A(s["gain"], bench.HOP), A(s["a"], bench.HOP)))
+    table, _ = oracle.glottal_table()
+    assert rel_rms(dec.harm_oscillator.table.cpu(), table) < 1e-5
+    ref = oracle.source_filter_synth(s["phase"], 1, s["w"], 2400, s["log_mag"], s["gain"], s["a"], bench.HOP, noise,
+                                     dec.harm_oscillator.table.cpu(), bench.room_kernel(), variant=variant, oversampling=bench.OS)
+    assert out.shape == ref.shape == (bench.BATCH, bench.T - bench.HOP)
+    assert rel_rms(out.as_tensor(), ref) < REL_TOL
+
+
+def test_decoder_exact_phase_is_closer_to_float64_phase(oracle, bench, bench_set):
+    """the default (Q0.64 exact running phase) against the oracle with a float64 phase sum: the product's
+    default must not be further from exact arithmetic than the reference's float32 cumsum is"""
+    from golf_b200.audiotensor import AudioTensor
+
+    s = {k: v[:4] for k, v in bench_set.items()}
+    noise = torch.randn(4, bench.T, generator=torch.Generator().manual_seed(3))
+    dec = _fixed_noise_decoder(bench, "ss", noise.to(DEV))
+    A = lambda t, hop: AudioTensor(t.to(DEV), hop_length=hop)
+    with torch.no_grad():
+        out = dec(phase=A(s["phase"], 1), harm_oscillator_params=(A(s["w"], 2400),), noise_generator_params=(),
+                  noise_filter_params=(A(s["log_mag"], bench.HOP),), end_filter_params=(A(s["gain"], bench.HOP), A(s["a"], bench.HOP)))
+    kw = dict(variant="ss", oversampling=bench.OS)
+    args = (s["phase"], 1, s["w"], 2400, s["log_mag"], s["gain"], s["a"], bench.HOP, noise, dec.harm_oscillator.table.cpu(), bench.room_kernel())
+    truth = oracle.source_filter_synth(*args, accumulate="fp64", **kw)
+    ref32 = oracle.source_filter_synth(*args, accumulate="fp32", **kw)
+    assert rel_rms(out.as_tensor(), truth) <= max(rel_rms(ref32, truth), REL_TOL)
+
+
+# BASELINE.json configs[4]: the RTF grid's largest batch, filter level (the decoders of the grid differ only in it)
+@pytest.mark.parametrize("hop", [120, 240])
+@pytest.mark.parametrize("M", [12, 20, 32])
+def test_rtf_grid_filters_at_B128(G, oracle, M, hop):
+    B, Tn = 128, 48000
+    Fr = Tn // hop + 1
+    gain, a = synthetic_controls(B, Fr, M, seed=100 + M + hop)
+    ex = torch.randn(B, Tn, generator=torch.Generator().manual_seed(M))
+    ref32 = oracle.lpc_ss_fused(ex, gain, a, hop)
+    ref64 = oracle.lpc_ss_fused(ex, gain, a, hop, double=True)
+    exd, gd, ad = ex.to(DEV), gain.to(DEV), a.to(DEV)
+    y = G.lpc_ss(exd, gd, ad, hop)
+    assert y.shape == ref32.shape
+    assert rel_rms(y, ref32) < REL_TOL and rel_rms(y, ref64) < REL_TOL
+    win = torch.hann_window(4 * hop).to(DEV)
+    yf = G.lpc_ff(exd, gd, ad, win, hop)
+    reff = oracle.lpc_ff(ex, gain, a, hop, 4 * hop)
+    assert yf.shape == reff.shape
+    assert rel_rms(yf, reff) < 1e-5

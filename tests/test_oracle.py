@@ -155,3 +155,58 @@ def test_precise_fir_oracle_matches_reference_golden(oracle):
         y = oracle.noise_fir_precise(T(g[f"ex_{tag}"]), T(g["log_mag"]), H)
         assert y.shape == g[f"y_{tag}"].shape
         assert rel_rms(y, T(g[f"y_{tag}"])) < 2e-6
+
+
+# ---------------------------------------------------------------- independent ss restatements
+def test_ss_three_independent_restatements_agree(oracle):
+    """The GOLF-ss recurrence is third-party code that cannot be installed here (PARITY UNPINNED at the
+    source).  Three implementations that share no code -- the C loop, a LAPACK banded solve of the
+    defining linear system, and the padded-buffer in-place shape of torchlpc's numba kernel -- must agree:
+    float64 to ~1e-12, float32 to the rounding floor, with and without an initial state."""
+    from oracle import ss_independent as S
+
+    g = golden("controls_gt")
+    H = int(g["hop"])
+    a_f, gain_f = T(g["a"])[:2, :21], T(g["gain"])[:2, :21]  # encoder-derived (pole radius up to 0.996)
+    Tn = 20 * H
+    A = oracle.upsample_time(a_f, H)[:, :Tn].contiguous()
+    x = torch.randn(2, Tn, generator=torch.Generator().manual_seed(0)) * oracle.upsample_time(gain_f, H)[:, :Tn]
+    zi = 1e-3 * torch.randn(2, A.shape[2], generator=torch.Generator().manual_seed(1))
+    for z in (None, zi):
+        zd = None if z is None else z.double()
+        c64 = oracle.sample_wise_lpc(x.double(), A.double(), zd)
+        banded = torch.from_numpy(S.sample_wise_lpc_banded(x.numpy(), A.numpy(), None if z is None else z.numpy()))
+        padded64 = torch.from_numpy(S.sample_wise_lpc_padded(x.double().numpy(), A.double().numpy(), None if zd is None else zd.numpy()))
+        assert rel_rms(c64, banded) < 1e-9  # the fp64 difference is the conditioning of the banded solve
+        assert rel_rms(padded64, banded) < 1e-9
+        c32 = oracle.sample_wise_lpc(x, A, z)
+        padded32 = torch.from_numpy(S.sample_wise_lpc_padded(x.numpy(), A.numpy(), None if z is None else z.numpy()))
+        floor = rel_rms(c32, banded)
+        assert floor < REL_TOL and rel_rms(padded32, banded) < REL_TOL
+        assert rel_rms(padded32, c32) < 4 * floor + 1e-7
+    # the numba and the plain-NumPy versions of the padded shape are the same arithmetic
+    small = slice(0, 600)
+    p_np = S.sample_wise_lpc_padded(x[:, small].numpy(), A[:, small].numpy(), zi.numpy(), use_numba=False)
+    p_nb = S.sample_wise_lpc_padded(x[:, small].numpy(), A[:, small].numpy(), zi.numpy(), use_numba=True)
+    assert np.abs(p_np - p_nb).max() <= 1e-6 * np.abs(p_np).max()
+
+
+def test_ss_zi_ordering_split_continuation(oracle):
+    """`zi[:, j] = y[-1-j]` (recalled from the package, unpinned): whatever the convention, filtering a
+    signal in two pieces -- the second started from the last M outputs of the first, newest first -- must
+    reproduce the one-shot result exactly; any other ordering of zi breaks this identity."""
+    from oracle import ss_independent as S
+
+    g = torch.Generator().manual_seed(5)
+    B, Tn, M, cut = 2, 700, 6, 333
+    A = oracle.rc2lpc(torch.tanh(0.3 * smooth(torch.randn(B, Tn, M, generator=g), 32))).double()
+    x = torch.randn(B, Tn, generator=g, dtype=torch.float64)
+    full = oracle.sample_wise_lpc(x, A)
+    zi = full[:, cut - M : cut].flip(1)  # newest first
+    tail = oracle.sample_wise_lpc(x[:, cut:].contiguous(), A[:, cut:].contiguous(), zi.contiguous())
+    assert torch.equal(tail, full[:, cut:])
+    wrong = oracle.sample_wise_lpc(x[:, cut:].contiguous(), A[:, cut:].contiguous(), zi.flip(1).contiguous())
+    assert not torch.allclose(wrong, full[:, cut:])
+    for fn in (S.sample_wise_lpc_banded, S.sample_wise_lpc_padded):
+        t2 = torch.from_numpy(fn(x[:, cut:].numpy(), A[:, cut:].numpy(), zi.numpy()))
+        assert rel_rms(t2, full[:, cut:]) < 1e-10
