@@ -10,7 +10,7 @@ from ctypes import c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("GOLF_B200_SO") or os.path.join(_HERE, "_lib", "libgolf_b200.so")  # env: A/B builds (tools/)
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 _lib = None
 
 P = c_void_p
@@ -26,6 +26,9 @@ _SIGS = {
     "golf_lpc_ss_set_solver": (None, [c_int]),
     "golf_lpc_ss_fwd": (c_int, [P, c_int64, P, P, P, P] + [c_int] * 6 + [P, c_size_t, P]),
     "golf_lpc_ss_fwd_passes": (c_int, [P, c_int64, P, P, P, P] + [c_int] * 6 + [P, c_size_t, c_int, P]),
+    "golf_lpc_ss_set_tail": (None, [c_int]),
+    "golf_lpc_ss_room_workspace_bytes": (c_size_t, [c_int] * 5),
+    "golf_lpc_ss_room_fwd": (c_int, [P, c_int64, P, P, P, P, c_int, P, P] + [c_int] * 7 + [P, c_size_t, P]),
     "golf_lpc_ss_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
     "golf_lpc_ss_bwd": (c_int, [P, P, P, c_int64, P, P, P, P, P, P, P] + [c_int] * 7 + [P, c_size_t, P]),
     "golf_lpc_ff_fwd": (c_int, [P, c_int64, P, P, P, P] + [c_int] * 6 + [P]),

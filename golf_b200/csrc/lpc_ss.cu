@@ -150,6 +150,7 @@ __global__ void ss_dzi_kernel(const float* __restrict__ u, const float* __restri
 // solve to a few float32 ulps (well-conditioned filters) -- see DESIGN.md 3.1.
 static float g_refine_tol = 1e-4f;
 int g_solve_systolic = 1;
+int g_ss_tail = 1;
 
 struct SsPlan {
   int B, MP, Lc, C, HB;
@@ -195,16 +196,30 @@ static bool make_plan(int B, int L, int M, int hop, int chunk, SsPlan* pl) {
   return true;
 }
 
-// workspace layout: W | S | E | flags
+// workspace layout: W | S | E | flags | Gw | Sg | Dg   (the last three: group blocks / states of the one-launch tail)
+static size_t plan_group_floats(const SsPlan& pl) { return (size_t)pl.B * kTailNW * ((size_t)(pl.MP + 1) * pl.MP); }
+static size_t plan_gstate_floats(const SsPlan& pl) { return (size_t)pl.B * kTailNW * pl.MP; }
 static size_t plan_bytes(const SsPlan& pl) {
-  return align_up(pl.w_floats * 4, 256) + 2 * align_up(pl.s_floats * 4, 256) + align_up((size_t)pl.B * 8, 256);
+  return align_up(pl.w_floats * 4, 256) + 2 * align_up(pl.s_floats * 4, 256) + align_up((size_t)pl.B * 8, 256) +
+         align_up(plan_group_floats(pl) * 4, 256) + 2 * align_up(plan_gstate_floats(pl) * 4, 256);
 }
 static void plan_pointers(const SsPlan& pl, void* workspace, SsParams* p) {
   char* ws = reinterpret_cast<char*>(workspace);
-  p->W = reinterpret_cast<float*>(ws);
-  p->S = reinterpret_cast<float*>(ws + align_up(pl.w_floats * 4, 256));
-  p->E = reinterpret_cast<float*>(ws + align_up(pl.w_floats * 4, 256) + align_up(pl.s_floats * 4, 256));
-  p->flags = reinterpret_cast<unsigned int*>(ws + align_up(pl.w_floats * 4, 256) + 2 * align_up(pl.s_floats * 4, 256));
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* q = ws + off;
+    off += align_up(bytes, 256);
+    return q;
+  };
+  p->W = reinterpret_cast<float*>(take(pl.w_floats * 4));
+  p->S = reinterpret_cast<float*>(take(pl.s_floats * 4));
+  p->E = reinterpret_cast<float*>(take(pl.s_floats * 4));
+  p->flags = reinterpret_cast<unsigned int*>(take((size_t)pl.B * 8));
+  p->Gw = reinterpret_cast<float*>(take(plan_group_floats(pl) * 4));
+  p->Sg = reinterpret_cast<float*>(take(plan_gstate_floats(pl) * 4));
+  p->Dg = reinterpret_cast<float*>(take(plan_gstate_floats(pl) * 4));
+  tail_groups(pl.C, &p->NG, &p->G);
+  p->room_k = nullptr, p->room_out = nullptr, p->room_n = 0;
   p->refine_tol = g_refine_tol;
 }
 
@@ -291,6 +306,40 @@ GOLF_API int golf_lpc_ss_fwd(const float* ex, int64_t ex_stride, const float* ga
                              float* y, int B, int L, int F, int M, int hop, int chunk, void* workspace,
                              size_t workspace_bytes, void* stream) {
   return golf_lpc_ss_fwd_passes(ex, ex_stride, gain, a, zi, y, B, L, F, M, hop, chunk, workspace, workspace_bytes, 15, stream);
+}
+
+GOLF_API void golf_lpc_ss_set_tail(int fused) { g_ss_tail = fused ? 1 : 0; }
+
+GOLF_API size_t golf_lpc_ss_room_workspace_bytes(int B, int L, int M, int hop, int chunk) {
+  SsPlan pl;
+  if (!make_plan(B, L, M, hop, chunk, &pl)) return 0;
+  return plan_bytes(pl) + align_up((size_t)B * L * 4, 256);  // + y when the caller does not keep it
+}
+
+GOLF_API int golf_lpc_ss_room_fwd(const float* ex, int64_t ex_stride, const float* gain, const float* a, const float* zi,
+                                  const float* room_k, int room_n, float* y, float* out, int B, int L, int F, int M, int hop,
+                                  int chunk, int refine, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!ex || !a || !room_k || !out || room_n < 1 || B <= 0 || L <= 0 || F <= 0 || M <= 0 || hop <= 0) return GOLF_ERR_INVALID;
+  if (ex_stride < L || (int64_t)L > (int64_t)(F - 1) * hop + 1) return GOLF_ERR_INVALID;
+  SsPlan pl;
+  if (!make_plan(B, L, M, hop, chunk, &pl)) return GOLF_ERR_UNSUPPORTED;
+  const size_t need = plan_bytes(pl) + (y ? 0 : align_up((size_t)B * L * 4, 256));
+  if (!workspace || workspace_bytes < need) return GOLF_ERR_WORKSPACE;
+  if (((uintptr_t)workspace & 15) != 0) return GOLF_ERR_INVALID;
+  float* yb = y ? y : reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + plan_bytes(pl));
+  SsParams p{};
+  p.in = ex, p.in_stride = ex_stride, p.gain = gain, p.a = a, p.out = yb, p.out2 = nullptr, p.zi = zi;
+  plan_pointers(pl, workspace, &p);
+  p.B = B, p.L = L, p.F = F, p.M = M, p.hop = hop, p.Lc = pl.Lc, p.C = pl.C, p.HB = pl.HB;
+  p.scale = lerp_scale(F, hop);
+  p.room_k = room_k, p.room_n = room_n, p.room_out = out;
+  const int passes = refine ? 15 : 7;
+  int rc = launch_form<0>(p, pl.MP, pl.generic, passes, (cudaStream_t)stream);
+  if (rc != GOLF_ERR_UNSUPPORTED) return rc;
+  // configurations the one-launch tail does not cover: the filter, then the stand-alone room FIR
+  rc = golf_lpc_ss_fwd_passes(ex, ex_stride, gain, a, zi, yb, B, L, F, M, hop, chunk, workspace, workspace_bytes, passes, stream);
+  if (rc) return rc;
+  return golf_room_fir_fwd(yb, room_k, out, B, L, room_n, stream);
 }
 
 GOLF_API size_t golf_lpc_ss_bwd_workspace_bytes(int B, int L, int M, int hop, int chunk) {

@@ -43,6 +43,7 @@
 namespace golf {
 
 extern int g_solve_systolic;  // 1 (default): 4-lanes-per-chunk solve where it applies; 0: lane-per-chunk
+extern int g_ss_tail;         // 1 (default): stitch + solve + refinement (+ room) in one cluster launch where it applies
 
 struct SsParams {
   const float* in;     // FORM0: ex [B, in_stride]; FORM1: gy [B, L]
@@ -59,6 +60,13 @@ struct SsParams {
   int B, L, F, M, hop, Lc, C, HB;
   float scale;
   float refine_tol;    // refine sequence b only if mismatch > refine_tol * max|S| (0: always)
+  // ---- one-launch tail (lpc_ss_tail.cuh): two-level stitch + solve + refinement (+ room FIR) per sequence
+  float* Gw;           // [B][NG][(MP+1)*MP]  composed transition [Phi_grp | z_grp] of each group of G chunks
+  float* Sg;           // [B][NG][MP]         state entering each group
+  float* Dg;           // [B][NG][MP]         refinement: mismatch accumulated over a group, then the correction entering it
+  const float* room_k; // [room_n] learned taps of the room FIR fused behind the filter, or null
+  float* room_out;     // [B][L] final output when room_k is given (p.out then holds the filter output y)
+  int NG, G, room_n;
 };
 
 // processing index p, step n within chunk -> absolute time
@@ -669,20 +677,17 @@ __global__ void __launch_bounds__(32) ss_solve_kernel(SsParams p, int round) {
 // Coefficient frames are (re)loaded when a lane's local time enters a new frame; the first sample
 // of a frame (where ATen's floor() may land one frame low) uses coefficients computed with the
 // exact reference arithmetic at load time.  FORM 0, frame-aligned chunks only.
-template <int MP>
-__global__ void __launch_bounds__(32) ss_solve_sys_kernel(SsParams p, int round) {
+// One warp solves the GPW = 8 chunks 8g .. 8g+7 of sequence b.  xin_all: [2][GPW*MP] floats, yout: [GPW*MP] floats of
+// shared memory private to the calling warp (16-byte aligned).  Warp-level synchronisation only, so several warps of a
+// CTA may run it side by side (ss_tail_kernel) or one warp per CTA (ss_solve_sys_kernel).  READ_CG: S was written by
+// another CTA of this kernel (read through L2).
+template <int MP, bool READ_CG>
+__device__ __forceinline__ void solve_sys_body(const SsParams& p, const int b, const int g, const int round, float* xin_all,
+                                               float* yout, const int lane) {
   constexpr int LB = 4, TB = MP / LB, D = 2, HOPD = TB - D, GPW = 32 / LB, PRE = D * (LB - 1);
   constexpr int NLD = (GPW * MP + 31) / 32;  // staged elements per lane per tile
   static_assert(MP % LB == 0 && HOPD >= 1 && TB % 2 == 0, "systolic solve geometry");
-  __shared__ __align__(16) float xin[2][GPW * MP];
-  __shared__ __align__(16) float yout[GPW * MP];
-  const int lane = threadIdx.x, grp = lane / LB, j = lane % LB;
-  const int G = (p.C + GPW - 1) / GPW;
-  const int b = blockIdx.x / G, g = blockIdx.x % G;
-  if (round == 1) {  // refinement round: only for the sequences that need it
-    const float mism = __uint_as_float(p.flags[2 * b]), smax = __uint_as_float(p.flags[2 * b + 1]);
-    if (!(mism > p.refine_tol * smax)) return;
-  }
+  const int grp = lane / LB, j = lane % LB;
   const int pi = g * GPW + grp;
   const bool active = pi < p.C;
   const int pic = active ? pi : p.C - 1;
@@ -698,9 +703,9 @@ __global__ void __launch_bounds__(32) ss_solve_sys_kernel(SsParams p, int round)
     const float* s0 = p.S + ((size_t)b * p.C + pic) * MP;
     const bool ld = active && round >= 0;
 #pragma unroll
-    for (int k = 0; k < TB; ++k) ring[k] = ld ? s0[PRE + HOPD * j + k] : 0.f;
+    for (int k = 0; k < TB; ++k) ring[k] = ld ? (READ_CG ? __ldcg(s0 + PRE + HOPD * j + k) : s0[PRE + HOPD * j + k]) : 0.f;
 #pragma unroll
-    for (int i = 0; i < PRE; ++i) pre[i] = ld ? s0[PRE - 1 - i] : 0.f;
+    for (int i = 0; i < PRE; ++i) pre[i] = ld ? (READ_CG ? __ldcg(s0 + PRE - 1 - i) : s0[PRE - 1 - i]) : 0.f;
   }
   // coefficient frames (negated) of this lane's taps, gain pair, and the exact set for the first
   // sample of the frame
@@ -793,7 +798,7 @@ __global__ void __launch_bounds__(32) ss_solve_sys_kernel(SsParams p, int round)
 #pragma unroll
     for (int i = 0; i < NLD; ++i) {
       const int idx = lane + 32 * i;
-      if (idx < GPW * MP) xin[buf][idx] = v[i];
+      if (idx < GPW * MP) xin_all[buf * (GPW * MP) + idx] = v[i];
     }
   };
   fetch(0);
@@ -809,7 +814,7 @@ __global__ void __launch_bounds__(32) ss_solve_sys_kernel(SsParams p, int round)
   for (int tile = 0; tile < ntiles; ++tile) {
     const int buf = tile & 1;
     if (tile + 1 < ntiles) fetch(tile + 1);
-    const float* xg = xin[buf] + grp * MP;
+    const float* xg = xin_all + buf * (GPW * MP) + grp * MP;
 #pragma unroll
     for (int sx = 0; sx < MP; ++sx) {
       // frame changes of lane j happen D*j iterations before lane 0's (which are tile aligned)
@@ -850,7 +855,7 @@ __global__ void __launch_bounds__(32) ss_solve_sys_kernel(SsParams p, int round)
         const float ev = yout[grp * MP + MP - 1 - comp];
         e0[comp] = ev;
         if (pi + 1 < p.C && comp < p.M) {
-          const float sv = s1[comp];
+          const float sv = READ_CG ? __ldcg(s1 + comp) : s1[comp];
           mism = fmaxf(mism, fabsf(ev - sv));
           smax = fmaxf(smax, fabsf(sv));
         }
@@ -867,6 +872,24 @@ __global__ void __launch_bounds__(32) ss_solve_sys_kernel(SsParams p, int round)
     }
   }
 }
+
+template <int MP>
+__global__ void __launch_bounds__(32) ss_solve_sys_kernel(SsParams p, int round) {
+  constexpr int GPW = 8;
+  __shared__ __align__(16) float xin[2 * GPW * MP];
+  __shared__ __align__(16) float yout[GPW * MP];
+  const int G = (p.C + GPW - 1) / GPW;
+  const int b = blockIdx.x / G, g = blockIdx.x % G;
+  if (round == 1) {  // refinement round: only for the sequences that need it
+    const float mism = __uint_as_float(p.flags[2 * b]), smax = __uint_as_float(p.flags[2 * b + 1]);
+    if (!(mism > p.refine_tol * smax)) return;
+  }
+  solve_sys_body<MP, false>(p, b, g, round, xin, yout, (int)threadIdx.x);
+}
+
+}  // namespace golf
+#include "lpc_ss_tail.cuh"
+namespace golf {
 
 template <int MP, int MT, int FORM>
 int launch_response(const SsParams& p, cudaStream_t st) {
@@ -891,6 +914,12 @@ int launch_response(const SsParams& p, cudaStream_t st) {
 template <int MP, int FORM>
 int launch_mp(const SsParams& p, bool generic, int passes, cudaStream_t st) {
   const int nresp = p.C - 1;
+  // one-launch tail: two-level stitch + solve + refinement (+ room FIR) by a cluster per sequence (lpc_ss_tail.cuh)
+  bool use_tail = false;
+  if constexpr (FORM == 0 && MP >= 16 && MP % 8 == 0 && MP <= 32) {
+    use_tail = !generic && g_solve_systolic && g_ss_tail && (passes & 6) == 6 && p.Gw != nullptr;
+  }
+  if (p.room_k && !use_tail) return GOLF_ERR_UNSUPPORTED;  // the fused room FIR exists only in the tail kernel
   if (nresp > 0 && (passes & 1)) {
     constexpr int MTS = MP >= 8 ? MP - 2 : MP;  // short-tap variant for M <= MP - 2
     int rc;
@@ -899,6 +928,9 @@ int launch_mp(const SsParams& p, bool generic, int passes, cudaStream_t st) {
     else
       rc = launch_response<MP, MP, FORM>(p, st);
     if (rc) return rc;
+  }
+  if constexpr (FORM == 0 && MP >= 16 && MP % 8 == 0 && MP <= 32) {
+    if (use_tail) return launch_tail<MP>(p, passes, st);
   }
   const size_t sm_stitch =
       ((size_t)kStitchStages * kStitchGroup * ((MP + 1) * MP + 2 * MP) + 2 * MP) * sizeof(float) + kStitchStages * 8 + 128;

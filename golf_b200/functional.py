@@ -186,6 +186,68 @@ def lpc_ss(ex, gain, a, hop: int, zi=None, chunk: int = 0, refine: bool = True) 
     return _LpcSS.apply(ex, gain, a, zi, int(hop), int(chunk), bool(refine))
 
 
+def _lpc_ss_room_fwd(ex, gain, a, zi, room_k, hop: int, chunk: int = 0, refine: bool = True, keep_y: bool = False):
+    ex = _rows(ex, "ex")
+    a = _cuda_f32(a, "a")
+    gain = None if gain is None else _cuda_f32(gain, "gain")
+    zi = None if zi is None else _cuda_f32(zi, "zi")
+    room_k = _cuda_f32(room_k, "room kernel")
+    B, Tex = ex.shape
+    Fr, M = a.shape[1], a.shape[2]
+    if a.shape[0] != B or (gain is not None and tuple(gain.shape) != (B, Fr)) or (zi is not None and tuple(zi.shape) != (B, M)):
+        raise GolfError(f"lpc_ss_room: inconsistent shapes ex{tuple(ex.shape)} gain{None if gain is None else tuple(gain.shape)} a{tuple(a.shape)}")
+    L = lpc_ss_length(Tex, Fr, hop)
+    out = torch.empty(B, L, dtype=torch.float32, device=ex.device)
+    y = torch.empty(B, L, dtype=torch.float32, device=ex.device) if keep_y else None
+    lib = _lib.lib()
+    nbytes = lib.golf_lpc_ss_room_workspace_bytes(B, L, M, hop, chunk)
+    if nbytes == 0:
+        raise GolfError(f"lpc_ss_room: unsupported configuration B={B} L={L} M={M} hop={hop} chunk={chunk}")
+    ws = _workspace(nbytes, ex.device)
+    with _on(ex.device):
+        rc = lib.golf_lpc_ss_room_fwd(_ptr(ex), ex.stride(0), _ptr(gain), _ptr(a), _ptr(zi), _ptr(room_k), room_k.numel(), _ptr(y),
+                                      _ptr(out), B, L, Fr, M, hop, chunk, 1 if refine else 0, _ptr(ws), ws.numel(), _stream())
+    check(rc, "golf_lpc_ss_room_fwd")
+    return out, y
+
+
+class _LpcSSRoom(torch.autograd.Function):
+    """room_fir(lpc_ss(ex, gain, a), k) in one pass; the adjoint chains the two stages' adjoints on the saved y"""
+
+    @staticmethod
+    def forward(ctx, ex, gain, a, room_k, hop, refine):
+        need = any(ctx.needs_input_grad[:4])
+        out, y = _lpc_ss_room_fwd(ex, gain, a, None, room_k, hop, 0, refine, keep_y=need)
+        if need:
+            ctx.save_for_backward(ex, gain, a, room_k, y)
+        ctx.hop, ctx.refine = hop, refine
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        ex, gain, a, room_k, y = ctx.saved_tensors
+        gout = _cuda_f32(gout, "gout")
+        kc = _cuda_f32(room_k, "room kernel")
+        B, L = y.shape
+        gy = torch.empty_like(y)
+        d_k = torch.empty_like(kc) if ctx.needs_input_grad[3] else None
+        with _on(gout.device):
+            rc = _lib.lib().golf_room_fir_bwd(_ptr(gout), _ptr(y), _ptr(kc), _ptr(gy), _ptr(d_k), B, L, kc.numel(), _stream())
+        check(rc, "golf_room_fir_bwd")
+        d_ex = d_gain = d_a = None
+        if any(ctx.needs_input_grad[:3]):
+            d_ex, d_gain, d_a, _ = _lpc_ss_bwd(gy, y, ex, gain, a, None, ctx.hop, tuple(ctx.needs_input_grad[:3]) + (False,), 0, ctx.refine)
+            if d_ex is not None and d_ex.shape[1] < ex.shape[1]:
+                d_ex = torch.nn.functional.pad(d_ex, (0, ex.shape[1] - d_ex.shape[1]))
+        return d_ex, d_gain, d_a, d_k, None, None
+
+
+def lpc_ss_room(ex, gain, a, room_k, hop: int, refine: bool = True) -> torch.Tensor:
+    """GOLF-ss end filter followed by the learned room FIR (models/sf.py:64) -- the filter's stitch / solve and the
+    128-tap FIR share one launch (golf_lpc_ss_room_fwd).  Differentiable in ex, gain, a and the room taps."""
+    return _LpcSSRoom.apply(ex, gain, a, room_k, int(hop), bool(refine))
+
+
 def sample_wise_lpc(x, a, zi=None) -> torch.Tensor:
     """torchlpc.sample_wise_lpc: x [B,T], a [B,T,M] sample-rate coefficients, zi [B,M]."""
     if x.ndim != 2 or a.ndim != 3 or a.shape[:2] != x.shape:

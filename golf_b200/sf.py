@@ -11,7 +11,8 @@ import torch.nn.functional as F
 
 from .audiotensor import AudioTensor, hop_of, like, plain
 from .ctrl import PassThrough, Synth
-from .filters import LTVMinimumPhaseFilterPrecise, LTVZeroPhaseFIRFilter
+from . import functional as G
+from .filters import LTIAcousticFilter, LTVMinimumPhaseFilter, LTVMinimumPhaseFilterPrecise, LTVZeroPhaseFIRFilter
 from .noise import StandardNormalNoise
 from .synth import IndexedGlottalFlowTable
 
@@ -23,6 +24,7 @@ from .synth import IndexedGlottalFlowTable
 # Within a group the noise draw and the FIR design run beside the oscillator, each on its own stream.  "off" = one stream.
 CONCURRENT = "auto"
 SPLIT = 1
+FUSE_ROOM = True  # GOLF-ss end filter + room FIR through golf_lpc_ss_room_fwd (False: two module calls)
 _SIDE_STREAMS = {}
 
 
@@ -62,6 +64,19 @@ class SourceFilterSynth(Synth):
             src = src - self.noise_filter(harm, *noise_filter_params)
         if target is not None:
             return self.end_filter.reverse(src, target, *end_filter_params)
+        return self._end_and_room(src, end_filter_params)
+
+    def _end_and_room(self, src, end_filter_params):
+        """room_filter(end_filter(src, gain, a)) (models/sf.py:64).  For the sample-wise filter followed by the learned
+        room FIR the two share one launch chain (golf_lpc_ss_room_fwd): the FIR runs as the last phase of the filter's
+        per-sequence cluster kernel, on y while it is still in L2."""
+        if (FUSE_ROOM and type(self.end_filter) is LTVMinimumPhaseFilterPrecise and type(self.room_filter) is LTIAcousticFilter
+                and len(end_filter_params) == 2 and plain(src).is_cuda and self.room_filter.kernel.numel() <= 252):
+            gain, a = end_filter_params
+            hop, ex_hop = hop_of(gain), hop_of(src)
+            if hop % ex_hop == 0 and hop_of(a, hop) == hop and plain(a).shape[1] == plain(gain).shape[1]:
+                y = G.lpc_ss_room(plain(src), plain(gain), plain(a), self.room_filter.kernel, hop // ex_hop)
+                return like(src, y, ex_hop)
         return self.room_filter(self.end_filter(src, *end_filter_params))
 
     # ------------------------------------------------------------- concurrent inference path
@@ -119,4 +134,4 @@ class SourceFilterSynth(Synth):
         s_run.wait_stream(s_fir)
         s_run.wait_stream(s_rng)
         src = self.noise_filter.apply_raw(like(harm, noise, 1), raw, hop, add=harm)
-        return self.room_filter(self.end_filter(src, *end_filter_params))
+        return self._end_and_room(src, end_filter_params)

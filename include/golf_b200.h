@@ -14,6 +14,7 @@
  *                            (ex*gain, upsample a, torchlpc.sample_wise_lpc) and its autograd
  *                            with hop == 1, gain == NULL: torchlpc.sample_wise_lpc(x, a, zi)
  *                            as called at models/filters.py:112,789 and models/lru/lru.py:15
+ *   golf_lpc_ss_room_fwd     models/sf.py:64 room_filter(end_filter(...)): filters.py:99-113 followed by :443-450
  *   golf_lpc_ff_*            models/filters.py:131-184 LTVMinimumPhaseFilter.forward
  *                            (unfold, models/lpc.py:11-16 lpc_synthesis -> torchaudio lfilter, Hann OLA)
  *   golf_biquad_ff_fwd       models/lpc.py:94-131     BatchSecondOrderLPCSynth.forward
@@ -41,7 +42,7 @@
 extern "C" {
 #endif
 
-#define GOLF_B200_ABI_VERSION 3
+#define GOLF_B200_ABI_VERSION 4
 
 enum {
   GOLF_OK = 0,
@@ -95,6 +96,18 @@ int golf_lpc_ss_fwd_passes(const float *ex, int64_t ex_stride, const float *gain
                            const float *a, const float *zi, float *y, int B, int L, int F,
                            int M, int hop, int chunk, void *workspace, size_t workspace_bytes,
                            int passes, void *stream);
+/* 1 (default): passes 2..4 (stitch, solve, refinement) run as ONE launch, a thread-block cluster per sequence with a
+ * two-level stitch; 0: the separate stitch / solve launches.  Same recurrences, different grouping of
+ * the state propagation (results agree to float32 rounding).  Process-wide; for A/B timing and tests. */
+void golf_lpc_ss_set_tail(int fused);
+/* GOLF-ss end filter + the room filter behind it (models/sf.py:64: room_filter(end_filter(src, gain, a)) with
+ * models/filters.py:99-113 and :443-450) in the same launches: out[t] = y[t] + sum_{j<room_n} room_k[j] y[t-room_n+j],
+ * y = golf_lpc_ss_fwd(ex, gain, a, zi).  y may be NULL (the filter output then lives in the workspace only; pass a
+ * buffer to keep it for the adjoint); refine != 0 allows the refinement round.  room_n <= 252 taps. */
+size_t golf_lpc_ss_room_workspace_bytes(int B, int L, int M, int hop, int chunk);
+int golf_lpc_ss_room_fwd(const float *ex, int64_t ex_stride, const float *gain, const float *a, const float *zi,
+                         const float *room_k, int room_n, float *y, float *out, int B, int L, int F, int M,
+                         int hop, int chunk, int refine, void *workspace, size_t workspace_bytes, void *stream);
 /* Adjoint.  Inputs: gy = dL/dy [B,L], saved y, ex, gain, a, zi.  Outputs (any may
  * be NULL): d_ex [B,L], d_gain [B,F], d_a [B,F,M], d_zi [B,M]. */
 size_t golf_lpc_ss_bwd_workspace_bytes(int B, int L, int M, int hop, int chunk);

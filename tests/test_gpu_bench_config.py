@@ -44,7 +44,7 @@ def test_ss_filter_at_bench_size(G, oracle, bench, bench_set):
     ref32 = oracle.lpc_ss_fused(ex, s["gain"], s["a"], bench.HOP)
     ref64 = oracle.lpc_ss_fused(ex, s["gain"], s["a"], bench.HOP, double=True)
     y = G.lpc_ss(ex.to(DEV), s["gain"].to(DEV), s["a"].to(DEV), bench.HOP)
-    assert y.shape == ref32.shape == (bench.BATCH, (bench.FRAMES - 1) * bench.HOP + 1)
+    assert y.shape == ref32.shape == (bench.BATCH, bench.T - bench.HOP)
     floor = rel_rms(ref32, ref64)
     assert rel_rms(y, ref32) < REL_TOL and rel_rms(y, ref64) < REL_TOL
     assert rel_rms(y, ref64) < 3 * floor  # as accurate as the reference's own float32 loop

@@ -74,6 +74,9 @@ stages += [
     ("lpc_ss stitch (2)", lambda: G._lpc_ss_fwd(srct, s["gain"], s["a"], None, 240, 0, 2, ws=ws)),
     ("lpc_ss solve (4)", lambda: G._lpc_ss_fwd(srct, s["gain"], s["a"], None, 240, 0, 4, ws=ws)),
     ("lpc_ss finish (30)", lambda: G._lpc_ss_fwd(srct, s["gain"], s["a"], None, 240, 0, 30, ws=ws)),
+    ("lpc_ss tail only (14)", lambda: G._lpc_ss_fwd(srct, s["gain"], s["a"], None, 240, 0, 14, ws=ws)),
+    ("lpc_ss tail no refine (6)", lambda: G._lpc_ss_fwd(srct, s["gain"], s["a"], None, 240, 0, 6, ws=ws)),
+    ("lpc_ss + room fused", lambda: G._lpc_ss_room_fwd(srct, s["gain"], s["a"], None, dec.room_filter.kernel, 240)),
 ]
 for name, fn in stages:
     print(f"{name:28s} {t(graphed(fn)):8.1f} us")
