@@ -178,7 +178,9 @@ static bool make_plan(int B, int L, int M, int hop, int chunk, SsPlan* pl) {
     if (Lc % pl->MP != 0) return false;
     if (!pl->generic && !(Lc % hop == 0 || hop % Lc == 0)) pl->generic = true;
   } else if (!pl->generic) {
-    Lc = hop >= target ? hop : hop * ((target + hop - 1) / hop);
+    // one control frame per chunk where the frames are long enough: the transposed solve (lpc_ss_solve_tr.cuh) needs a
+    // chunk to lie inside a frame; shorter frames are grouped up to ~240 samples
+    Lc = hop >= 96 ? hop : hop * ((target + hop - 1) / hop);
     if (hop > 2 * target) {  // long frames: subdivide, keeping Lc | hop and MP | Lc
       Lc = hop;
       for (int d = 2; d <= hop / pl->MP; ++d)

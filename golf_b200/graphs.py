@@ -24,11 +24,35 @@ from .audiotensor import hop_of, like, plain
 
 
 class GraphedSynth:
-    def __init__(self, decoder: torch.nn.Module, example_params: Dict[str, Any], warmup: int = 3):
+    def __init__(self, decoder: torch.nn.Module, example_params: Dict[str, Any], warmup: int = 3, packed: bool = False):
+        """packed: the static inputs are views into ONE flat float32 device buffer (each tensor starts on a 256-byte
+        boundary), so a step's controls arrive with a single host-to-device copy from a pinned staging buffer of the
+        same layout (`host_staging()` / `load_flat()`) instead of one copy per control tensor."""
         leaves, self._spec = tree_flatten(example_params)
         self._is_tensor = [isinstance(v, torch.Tensor) for v in leaves]
         dev = next(plain(v).device for v, t in zip(leaves, self._is_tensor) if t and plain(v).is_cuda)
-        self._static = [plain(v).detach().to(dev, copy=True) if t else v for v, t in zip(leaves, self._is_tensor)]
+        self._flat, self._offsets = None, None
+        if packed:
+            off, self._offsets = 0, []
+            for v, t in zip(leaves, self._is_tensor):
+                if t:
+                    if plain(v).dtype != torch.float32:
+                        raise ValueError("GraphedSynth(packed=True): every tensor input must be float32")
+                    self._offsets.append(off)
+                    off += (plain(v).numel() + 63) // 64 * 64
+                else:
+                    self._offsets.append(None)
+            self._flat = torch.zeros(max(off, 64), dtype=torch.float32, device=dev)
+            self._static = []
+            for v, t, o in zip(leaves, self._is_tensor, self._offsets):
+                if t:
+                    view = self._flat[o : o + plain(v).numel()].view(plain(v).shape)
+                    view.copy_(plain(v).detach())
+                    self._static.append(view)
+                else:
+                    self._static.append(v)
+        else:
+            self._static = [plain(v).detach().to(dev, copy=True) if t else v for v, t in zip(leaves, self._is_tensor)]
         self._hops = [hop_of(v, None) if t else None for v, t in zip(leaves, self._is_tensor)]
         self._refs = [v if t else None for v, t in zip(leaves, self._is_tensor)]
         self.decoder = decoder
@@ -68,6 +92,26 @@ class GraphedSynth:
                     n += dst.numel() * dst.element_size()
         return n
 
+    def host_staging(self):
+        """(flat, params): a pinned host buffer with the packed layout and a params pytree of views into it (same
+        structure and hop lengths as the example) -- fill the views, then `load_flat(flat)` is one H2D copy"""
+        if self._flat is None:
+            raise ValueError("host_staging() needs GraphedSynth(packed=True)")
+        flat = torch.zeros(self._flat.numel(), dtype=torch.float32).pin_memory()
+        leaves = []
+        for s_, t, h, r, o in zip(self._static, self._is_tensor, self._hops, self._refs, self._offsets):
+            if t:
+                view = flat[o : o + s_.numel()].view(s_.shape)
+                leaves.append(like(r, view, h) if h is not None else view)
+            else:
+                leaves.append(s_)
+        return flat, tree_unflatten(leaves, self._spec)
+
+    def load_flat(self, host_flat: torch.Tensor) -> int:
+        """one copy of the whole packed control block (pinned host or device) into the static inputs"""
+        self._flat.copy_(host_flat, non_blocking=True)
+        return self._flat.numel() * 4
+
     def replay(self):
         self.graph.replay()
         return self._out
@@ -94,13 +138,15 @@ class PipelinedSynth:
         pipe.wait(t)                                 # out_host ([B, pipe.out_len], pinned, contiguous) is valid
     """
 
-    def __init__(self, decoder: torch.nn.Module, example_params: Dict[str, Any], depth: int = 3, compute_streams: int = 1):
+    def __init__(self, decoder: torch.nn.Module, example_params: Dict[str, Any], depth: int = 3, compute_streams: int = 1,
+                 packed: bool = False):
         """compute_streams > 1: consecutive replays alternate between that many streams, so the latency-bound
         tail of one decoder pass (serial stitch / solve, a few SMs busy) overlaps the throughput kernels of the
-        next; depth must be a multiple of it (a slot always replays on the same stream)."""
+        next; depth must be a multiple of it (a slot always replays on the same stream).
+        packed: slots take their controls as ONE packed block (GraphedSynth(packed=True)); `submit_flat`."""
         if depth % compute_streams:
             raise ValueError("PipelinedSynth: depth must be a multiple of compute_streams")
-        self.slots = [GraphedSynth(decoder, example_params) for _ in range(depth)]
+        self.slots = [GraphedSynth(decoder, example_params, packed=packed) for _ in range(depth)]
         out = plain(self.slots[0]._out)
         self.device = out.device
         self.out_len = out.shape[1]
@@ -124,13 +170,24 @@ class PipelinedSynth:
         for s in (self.s_in, self.s_out, *self.s_runs):
             stream.wait_stream(s)
 
+    def host_staging(self):
+        """a pinned staging buffer + views for one step's controls (packed mode), see GraphedSynth.host_staging"""
+        return self.slots[0].host_staging()
+
+    def submit_flat(self, out_host: torch.Tensor, host_flat: torch.Tensor) -> int:
+        """packed mode: the step's controls are one pinned block -> one H2D copy"""
+        return self._submit(out_host, lambda slot: slot.load_flat(host_flat))
+
     def submit(self, out_host: torch.Tensor, **host_params) -> int:
+        return self._submit(out_host, lambda slot: slot.load(**host_params))
+
+    def _submit(self, out_host: torch.Tensor, load) -> int:
         k = self._n % len(self.slots)
         slot = self.slots[k]
         with torch.cuda.stream(self.s_in):
             if self._ran[k] is not None:
                 self.s_in.wait_event(self._ran[k])
-            self.h2d_bytes = slot.load(**host_params)
+            self.h2d_bytes = load(slot)
             loaded = torch.cuda.Event()
             loaded.record(self.s_in)
         s_run = self.s_runs[k % len(self.s_runs)]
