@@ -19,8 +19,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
-OBJDIR = os.path.join(LIBDIR, "obj")
-SO = os.path.join(LIBDIR, "libgolf_b200.so")
+# A/B and instrumented builds (tools/): GOLF_B200_VARIANT=name GOLF_NVCC_DEFS="-DX ..." builds libgolf_b200_name.so beside
+# the product library; select it at run time with GOLF_B200_SO=<path>
+VARIANT = os.environ.get("GOLF_B200_VARIANT", "")
+EXTRA_DEFS = os.environ.get("GOLF_NVCC_DEFS", "").split() if VARIANT else []
+OBJDIR = os.path.join(LIBDIR, "obj" + ("_" + VARIANT if VARIANT else ""))
+SO = os.path.join(LIBDIR, "libgolf_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 SS_MPS = (4, 8, 12, 16, 20, 24, 32, 40)
@@ -55,7 +59,7 @@ def _digest(src, extra) -> str:
     files += [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))]
     for p in files:
         h.update(open(p, "rb").read())
-    h.update(" ".join(ARCH + NVCC_FLAGS + list(extra)).encode())
+    h.update(" ".join(ARCH + NVCC_FLAGS + EXTRA_DEFS + list(extra)).encode())
     return h.hexdigest()[:16]
 
 
@@ -66,7 +70,7 @@ def _compile(unit, verbose):
     dig = _digest(src, defs + [name])
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
         return obj, False, ""
-    cmd = [nvcc()] + ARCH + NVCC_FLAGS + defs + ["-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [nvcc()] + ARCH + NVCC_FLAGS + EXTRA_DEFS + defs + ["-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -33,16 +33,19 @@ __device__ __forceinline__ void solve_tr_body(const SsParams& p, const int b, co
   constexpr int LB = 4, TB = MP / LB, D = 2, GPW = 32 / LB, KS = TB - D - 2;
   constexpr int NLD = (GPW * MP + 31) / 32;  // staged elements per lane per tile
   static_assert(MP % LB == 0 && KS >= 0, "transposed solve geometry");
+  // (the caller may be a non-inlined function holding `p` in local memory: read each field once)
+  const int C = p.C, L = p.L, Lc = p.Lc, F = p.F, M = p.M, hop = p.hop;
+  const float scale = p.scale;
   const int grp = lane / LB, j = lane % LB;
   const int pi = g * GPW + grp;
-  const bool active = pi < p.C;
-  const int pic = active ? pi : p.C - 1;
-  const float* __restrict__ ab = p.a + (size_t)b * p.F * p.M;
-  const float* __restrict__ gb = p.gain ? p.gain + (size_t)b * p.F : nullptr;
+  const bool active = pi < C;
+  const int pic = active ? pi : C - 1;
+  const float* __restrict__ ab = p.a + (size_t)b * F * M;
+  const float* __restrict__ gb = p.gain ? p.gain + (size_t)b * F : nullptr;
   const float* __restrict__ inb = p.in + (size_t)b * p.in_stride;
-  float* __restrict__ outb = p.out ? p.out + (size_t)b * p.L : nullptr;
+  float* __restrict__ outb = p.out ? p.out + (size_t)b * L : nullptr;
   const int tap0 = TB * j;
-  const int t0 = pic * p.Lc;
+  const int t0 = pic * Lc;
 
   // ---- entry states of the 8 chunks -> shared memory (zero: from rest)
   __syncwarp();
@@ -52,40 +55,35 @@ __device__ __forceinline__ void solve_tr_body(const SsParams& p, const int b, co
     const int prr = g * GPW + r;
     if (idx < GPW * MP) {
       float v = 0.f;
-      if (round >= 0 && prr < p.C) {
-        const float* sp = p.S + ((size_t)b * p.C + prr) * MP + c;
+      if (round >= 0 && prr < C) {
+        const float* sp = p.S + ((size_t)b * C + prr) * MP + c;
         v = READ_CG ? __ldcg(sp) : *sp;
       }
       ssm[idx] = v;
     }
   }
   // ---- this lane's taps of the chunk's frame pair (negated), the exact set for a frame's first sample, gain pair
-  const int kreg = min(t0 / p.hop, p.F - 1), k1 = min(kreg + 1, p.F - 1);
+  const int kreg = min(t0 / hop, F - 1), k1 = min(kreg + 1, F - 1);
   const float kregf = (float)kreg;
-  const bool first_exact = (t0 % p.hop) == 0;  // dest time t0 is the first sample of frame kreg
+  const bool first_exact = (t0 % hop) == 0;  // dest time t0 is the first sample of frame kreg
   float na0[TB], na1[TB], cg[TB];
-  float g0 = 1.f, g1 = 1.f, gg = 1.f;
   {
-    const Lerp w = lerp_at(min(t0, p.L - 1), p.scale, p.F);
-    const float* r0 = ab + (size_t)kreg * p.M + tap0;
-    const float* r1 = ab + (size_t)k1 * p.M + tap0;
-    const float* e0 = ab + (size_t)w.i0 * p.M + tap0;
-    const float* e1 = ab + (size_t)w.i1 * p.M + tap0;
+    const Lerp w = lerp_at(min(t0, L - 1), scale, F);
+    const float* r0 = ab + (size_t)kreg * M + tap0;
+    const float* r1 = ab + (size_t)k1 * M + tap0;
+    const float* e0 = ab + (size_t)w.i0 * M + tap0;
+    const float* e1 = ab + (size_t)w.i1 * M + tap0;
 #pragma unroll
     for (int i = 0; i < TB; ++i) {
-      const bool in = tap0 + i < p.M;
+      const bool in = tap0 + i < M;
       na0[i] = in ? -__ldg(r0 + i) : 0.f;
       na1[i] = in ? -__ldg(r1 + i) : 0.f;
       cg[i] = in ? -lerp_apply(w, __ldg(e0 + i), __ldg(e1 + i)) : 0.f;
     }
-    if (gb) {
-      g0 = __ldg(gb + kreg), g1 = __ldg(gb + k1);
-      gg = lerp_apply(w, __ldg(gb + w.i0), __ldg(gb + w.i1));
-    }
   }
   // interpolation weights of time tf (ATen: src = scale * t; l1 = clamp(src - i0); l0 = 1 - l1), frame kreg
   auto weights = [&](float tf, float& l0, float& l1) {
-    const float src = __fmul_rn(p.scale, tf);
+    const float src = __fmul_rn(scale, tf);
     float v = __fsub_rn(src, kregf);
     v = fminf(fmaxf(v, 0.f), 1.f);
     l1 = v;
@@ -105,38 +103,29 @@ __device__ __forceinline__ void solve_tr_body(const SsParams& p, const int b, co
     }
     tf_top = (float)(t0 + m0 + tap0 + TB);
   }
-  float tf_src = (float)(t0 - MP);  // float(t0 + i): source time of lane 0 (gain interpolation)
   float done_last = 0.f, pin_cur = 0.f, y_last = 0.f, yin_cur = 0.f, done_prev = 0.f;
 
   const float* smine = ssm + grp * MP;
 
-  // one tile of MP iterations starting at iteration i0.  EARLY: sources with m < 0 come from the entry state and the
-  // destination t0 may need the exact first-sample coefficients; xg: this tile's inputs (null while i < 0).
-  auto tile = [&](auto early_tag, const int i0, const float* __restrict__ xg) {
+  // TB iterations starting at iteration i0 (the slot rotation has period TB, so this is the smallest body with static
+  // register indices; a 24-iteration body is 19 KB of straight-line code and starves on instruction fetch).
+  // EARLY: sources with m < 0 come from the entry state and the destination t0 may need the exact first-sample
+  // coefficients; eg: this lane-group's excitation samples e[i0 ..] (null while i < 0); yo: where lane 0 stores y.
+  auto subtile = [&](auto early_tag, const int i0, const float* __restrict__ eg, float* __restrict__ yo) {
     constexpr bool EARLY = decltype(early_tag)::value;
 #pragma unroll
-    for (int s = 0; s < MP; ++s) {
-      const int i = i0 + s;
-      // ---- source sample of this lane
-      float gv;
-      {
-        float l0, l1;
-        weights(tf_src, l0, l1);
-        gv = __fmaf_rn(l0, g0, __fmul_rn(l1, g1));
-        if (EARLY && i == 0 && first_exact) gv = gg;
-        tf_src = __fadd_rn(tf_src, 1.f);
-      }
-      const float x = xg ? xg[s] : 0.f;
-      const float ycomp = (gb ? __fmul_rn(x, gv) : x) + done_prev;  // lane 0: y[i] = e[i] + (sum completed last iteration)
+    for (int s = 0; s < TB; ++s) {
+      // ---- source sample of this lane.  lane 0: y[i] = e[i] + (sum completed last iteration)
+      const float ycomp = (eg ? eg[s] : 0.f) + done_prev;
       float ysrc = (j == 0) ? ycomp : yin_cur;
       if (EARLY) {
-        const int m = i - D * j;
+        const int m = i0 + s - D * j;
         if (m < 0) {
           const int idx = -1 - m;
           ysrc = idx < MP ? smine[min(idx, MP - 1)] : 0.f;
         }
       }
-      if (j == 0 && xg) yout[grp * MP + s] = ycomp;
+      if (j == 0 && yo) yo[s] = ycomp;
       // ---- partial sum handed down by lane j+1 joins the pending sum of the same destination
       q[(KS + s) % TB] = __fadd_rn(q[(KS + s) % TB], pin_cur);
       // ---- the slot that enters at the top: weights of its destination time
@@ -149,7 +138,7 @@ __device__ __forceinline__ void solve_tr_body(const SsParams& p, const int b, co
         const int ph = (k + s) % TB;
         float c = __fmaf_rn(wl0[ph], na0[k], __fmul_rn(wl1[ph], na1[k]));
         if (EARLY && first_exact) {
-          const int dest = i - D * j + 1 + tap0 + k;
+          const int dest = i0 + s - D * j + 1 + tap0 + k;
           if (dest == 0) c = cg[k];
         }
         if (k == 0)
@@ -172,56 +161,74 @@ __device__ __forceinline__ void solve_tr_body(const SsParams& p, const int b, co
   using True = std::true_type;
   using False = std::false_type;
 
-  // ---- input staging (as in solve_sys_body): tile tl covers iterations tl*MP .. tl*MP+MP-1
-  const int ntiles = p.Lc / MP;
-  float v[NLD];
+  // ---- input staging: tile tl covers iterations tl*MP .. tl*MP+MP-1 of the 8 chunks; the excitation e = x * up(gain)
+  // is formed here, in parallel over the lanes, with the reference's interpolation arithmetic (lerp_at)
+  const int ntiles = Lc / MP;
+  // (raw loads only in fetch(): nothing waits on them until publish(), one tile later)
+  float vx[NLD], vg0[NLD], vg1[NLD];
   auto fetch = [&](int tl) {
 #pragma unroll
     for (int i = 0; i < NLD; ++i) {
       const int idx = lane + 32 * i, r = idx / MP, sx = idx - r * MP;
       const int prr = g * GPW + r;
-      const int t = prr * p.Lc + tl * MP + sx;
-      v[i] = (idx < GPW * MP && prr < p.C && t < p.L) ? __ldg(inb + t) : 0.f;
+      const int t = prr * Lc + tl * MP + sx;
+      const bool ok = idx < GPW * MP && prr < C && t < L;
+      vx[i] = ok ? __ldg(inb + t) : 0.f;
+      if (gb) {
+        const Lerp w = lerp_at(ok ? t : 0, scale, F);
+        vg0[i] = __ldg(gb + w.i0), vg1[i] = __ldg(gb + w.i1);
+      }
     }
   };
-  auto publish = [&](int buf) {
+  auto publish = [&](int buf, int tl) {
 #pragma unroll
     for (int i = 0; i < NLD; ++i) {
-      const int idx = lane + 32 * i;
-      if (idx < GPW * MP) xin_all[buf * (GPW * MP) + idx] = v[i];
+      const int idx = lane + 32 * i, r = idx / MP, sx = idx - r * MP;
+      float e = vx[i];
+      if (gb) {
+        const int t = (g * GPW + r) * Lc + tl * MP + sx;
+        const Lerp w = lerp_at(t < L ? t : 0, scale, F);
+        e = __fmul_rn(e, lerp_apply(w, vg0[i], vg1[i]));
+      }
+      if (idx < GPW * MP) xin_all[buf * (GPW * MP) + idx] = e;
     }
   };
   fetch(0);
   __syncwarp();  // ssm visible
-  tile(True{}, -MP, nullptr);  // replay the entry state
-  publish(0);
+#pragma unroll 1
+  for (int u = 0; u < MP / TB; ++u) subtile(True{}, -MP + u * TB, nullptr, nullptr);  // replay the entry state
+  publish(0, 0);
   __syncwarp();
 #pragma unroll 1
   for (int tl = 0; tl < ntiles; ++tl) {
     const int buf = tl & 1;
     if (tl + 1 < ntiles) fetch(tl + 1);
-    const float* xg = xin_all + buf * (GPW * MP) + grp * MP;
-    if (tl == 0)
-      tile(True{}, 0, xg);
-    else
-      tile(False{}, tl * MP, xg);
+    const float* eg = xin_all + buf * (GPW * MP) + grp * MP;
+    float* yo = yout + grp * MP;
+    if (tl == 0) {
+#pragma unroll 1
+      for (int u = 0; u < MP / TB; ++u) subtile(True{}, u * TB, eg + u * TB, yo + u * TB);
+    } else {
+#pragma unroll 1
+      for (int u = 0; u < MP / TB; ++u) subtile(False{}, tl * MP + u * TB, eg + u * TB, yo + u * TB);
+    }
     __syncwarp();
     if (round >= 0) {  // write the tile back: GPW segments of MP contiguous samples
 #pragma unroll
       for (int i = 0; i < NLD; ++i) {
         const int idx = lane + 32 * i, r = idx / MP, sx = idx - r * MP;
         const int prr = g * GPW + r;
-        const int t = prr * p.Lc + tl * MP + sx;
-        if (idx < GPW * MP && prr < p.C && t < p.L) outb[t] = yout[idx];
+        const int t = prr * Lc + tl * MP + sx;
+        if (idx < GPW * MP && prr < C && t < L) outb[t] = yout[idx];
       }
     }
-    if (tl + 1 < ntiles) publish(buf ^ 1);
+    if (tl + 1 < ntiles) publish(buf ^ 1, tl + 1);
     if (tl + 1 < ntiles) __syncwarp();
   }
   // ---- end state of each chunk = its last MP outputs (still in yout): component k = y[Lc-1-k]
   if (round < 0) {  // zero-state response -> W[b][pi][col M][:]
-    if (active && pi < p.C - 1) {
-      float* z = p.W + ((size_t)b * (p.C - 1) + pi) * ((MP + 1) * MP) + p.M * MP;
+    if (active && pi < C - 1) {
+      float* z = p.W + ((size_t)b * (C - 1) + pi) * ((MP + 1) * MP) + M * MP;
 #pragma unroll
       for (int k = 0; k < TB; ++k) z[TB * j + k] = yout[grp * MP + MP - 1 - (TB * j + k)];
     }
@@ -230,14 +237,14 @@ __device__ __forceinline__ void solve_tr_body(const SsParams& p, const int b, co
   if (round == 0 && p.E) {
     float mism = 0.f, smax = 0.f;
     if (active) {
-      float* e0 = p.E + ((size_t)b * p.C + pi) * MP;
-      const float* s1 = p.S + ((size_t)b * p.C + min(pi + 1, p.C - 1)) * MP;
+      float* e0 = p.E + ((size_t)b * C + pi) * MP;
+      const float* s1 = p.S + ((size_t)b * C + min(pi + 1, C - 1)) * MP;
 #pragma unroll
       for (int k = 0; k < TB; ++k) {
         const int comp = TB * j + k;
         const float ev = yout[grp * MP + MP - 1 - comp];
         e0[comp] = ev;
-        if (pi + 1 < p.C && comp < p.M) {
+        if (pi + 1 < C && comp < M) {
           const float sv = READ_CG ? __ldcg(s1 + comp) : s1[comp];
           mism = fmaxf(mism, fabsf(ev - sv));
           smax = fmaxf(smax, fabsf(sv));

@@ -47,7 +47,8 @@ def test_tail_matches_oracle_and_separate_launches(G, oracle, tail_switch, B, Tn
     y0 = G.lpc_ss(exd, gd, ad, H)
     assert y1.shape == ref.shape
     assert rel_rms(y1, ref) < REL_TOL and rel_rms(y1, ref64) < REL_TOL
-    assert rel_rms(y1, y0) < 2e-5
+    floor = rel_rms(ref, ref64)  # what float32 itself costs on this input
+    assert rel_rms(y1, y0) < max(2e-5, 4 * floor)
     assert rel_rms(y1, ref64) < 2 * rel_rms(y0, ref64) + 1e-6  # no less accurate than the path it replaces
 
 
