@@ -10,7 +10,7 @@ from ctypes import c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("GOLF_B200_SO") or os.path.join(_HERE, "_lib", "libgolf_b200.so")  # env: A/B builds (tools/)
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 _lib = None
 
 P = c_void_p
@@ -40,6 +40,13 @@ _SIGS = {
     "golf_noise_fir_fwd": (c_int, [P, c_int64, P, P, P, c_int64, P] + [c_int] * 5 + [P]),
     "golf_fir_set_variant": (None, [c_int]),
     "golf_noise_fir_bwd": (c_int, [P, P, c_int64, P, P, P] + [c_int] * 5 + [P]),
+    "golf_noise_fir_design_supported": (c_int, [c_int, c_int]),
+    "golf_noise_fir_design_fwd": (c_int, [P, c_int64, P, P, P, P, c_int64, P] + [c_int] * 5 + [P]),
+    "golf_philox_normal": (c_int, [P, c_int, c_int, P, P]),
+    "golf_rng_advance": (c_int, [P, P]),
+    "golf_synth_fused_workspace_bytes": (c_size_t, [c_int] * 10),
+    "golf_synth_fused_out_length": (c_int, [c_int] * 6),
+    "golf_synth_fused_fwd": (c_int, [P, P, P, P, P, c_int64, P, P, P, P, P, P, c_int, P] + [c_int] * 16 + [P, c_size_t, P]),
     "golf_room_fir_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P]),
     "golf_room_fir_bwd": (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     "golf_glottal_osc_workspace_bytes": (c_size_t, [c_int] * 6),

@@ -25,6 +25,8 @@ from .audiotensor import AudioTensor, hop_of, like, plain
 from .ctrl import Controllable, wrap_ctrl_fn
 from .utils import biquads2lpc, get_logits2biquads, get_window_fn, rc2lpc
 
+FUSED_DESIGN = True  # inference: FIR taps designed inside the FIR kernel where supported (False: cuFFT route)
+
 __all__ = [
     "FilterInterface",
     "LTVFilterInterface",
@@ -158,13 +160,20 @@ class LTVZeroPhaseFIRFilter(LTVFilterInterface):
     def windowing(self, kernel: torch.Tensor) -> torch.Tensor:
         return kernel * self.window_fn(kernel.shape[-1], device=kernel.device, dtype=kernel.dtype)
 
-    def _window(self, K: int, like_t: torch.Tensor) -> torch.Tensor:
-        """window / K: raw_kernels() leaves the inverse FFT unnormalised, the 1/K rides on the window"""
-        key = (K, like_t.device)
-        if getattr(self, "_win_key", None) != key:
-            self._win_cache = self.window_fn(K, device=like_t.device, dtype=torch.float32) / K
-            self._win_key = key
-        return self._win_cache
+    def _window(self, K: int, like_t: torch.Tensor, scaled: bool = True) -> torch.Tensor:
+        """the window on like_t's device; scaled: window / K (raw_kernels() leaves the inverse FFT unnormalised, the 1/K
+        rides on the window).  Entries are never evicted (a captured CUDA graph may hold their pointers) and a new
+        entry is complete before any stream can see it."""
+        cache = self.__dict__.setdefault("_win_cache", {})
+        key = (K, like_t.device, scaled)
+        if key not in cache:
+            if like_t.is_cuda and torch.cuda.is_current_stream_capturing():
+                raise GolfError("LTVZeroPhaseFIRFilter: first use inside a CUDA-graph capture; run the module once eagerly first")
+            w = self.window_fn(K, device=like_t.device, dtype=torch.float32)
+            cache[key] = w / K if scaled else w
+            if like_t.is_cuda:
+                torch.cuda.current_stream(like_t.device).synchronize()
+        return cache[key]
 
     def raw_kernels(self, log_mag) -> torch.Tensor:
         """frame-rate half of the inference path: K * irfft(exp(log_mag)) -- one kernel for exp + complex
@@ -189,6 +198,9 @@ class LTVZeroPhaseFIRFilter(LTVFilterInterface):
         if need_grad:  # differentiable path: final taps built by torch (frame rate), FIR + adjoint in CUDA
             kernel = self.windowing(self.get_zero_phase_fir(lm))
             y = G.ltv_fir_blocks(x, kernel, hop, add)
+        elif lm.is_cuda and FUSED_DESIGN and G.noise_fir_design_supported(lm.shape[-1], hop):
+            # inference, shipped geometry: the taps are designed inside the FIR kernel (no FFT library, no [B,F,K] tensor)
+            y = G.noise_fir_design(x, lm, self._window(2 * (lm.shape[-1] - 1), lm, scaled=False), hop, add)
         else:  # inference: cuFFT gives the raw impulse responses, shift + window ride along in the FIR kernel
             raw = self.raw_kernels(lm)
             y = G.ltv_fir_blocks(x, raw, hop, add, window=self._window(raw.shape[-1], raw))

@@ -439,6 +439,106 @@ def ltv_fir_blocks(ex, kernel, hop: int, add=None, window=None) -> torch.Tensor:
     return _LtvFir.apply(ex, kernel, add, int(hop))
 
 
+def noise_fir_design_supported(n_mag: int, hop: int) -> bool:
+    return bool(_lib.lib().golf_noise_fir_design_supported(int(n_mag), int(hop)))
+
+
+def new_rng_state(device, seed: Optional[int] = None) -> torch.Tensor:
+    """{seed, offset} for the in-kernel noise generator: an int64[2] device tensor.  seed=None draws it from torch's
+    (CPU) generator, so torch.manual_seed governs it."""
+    if seed is None:
+        seed = int(torch.randint(0, 2**62, (1,), dtype=torch.int64).item())
+    return torch.tensor([seed, 0], dtype=torch.int64, device=device)
+
+
+def philox_normal(B: int, T: int, rng_state: torch.Tensor) -> torch.Tensor:
+    """the N(0,1) draw the fused noise kernels make for (rng_state), written to memory (tests, debugging)"""
+    out = torch.empty(B, T, dtype=torch.float32, device=rng_state.device)
+    with _on(out.device):
+        rc = _lib.lib().golf_philox_normal(_ptr(out), B, T, _ptr(rng_state), _stream())
+    check(rc, "golf_philox_normal")
+    return out
+
+
+def rng_advance(rng_state: torch.Tensor) -> None:
+    with _on(rng_state.device):
+        rc = _lib.lib().golf_rng_advance(_ptr(rng_state), _stream())
+    check(rc, "golf_rng_advance")
+
+
+def noise_fir_design(ex, log_mag, window, hop: int, add=None, rng_state=None) -> torch.Tensor:
+    """LTVZeroPhaseFIRFilter.forward with the taps designed inside the FIR kernel (golf_noise_fir_design_fwd): ex [B,T]
+    white noise (or None + rng_state: drawn in the kernel; give T through `add` or log_mag), log_mag [B,F,256],
+    window [510] (unscaled), optional fused `add + result`.  Inference path (no autograd)."""
+    log_mag = _cuda_f32(log_mag, "log_mag")
+    window = _cuda_f32(window, "window")
+    B, Fr, n_mag = log_mag.shape
+    K = 2 * (n_mag - 1)
+    if window.numel() != K:
+        raise GolfError(f"noise_fir_design: window has {window.numel()} taps, expected {K}")
+    if add is not None:
+        add = _rows(add, "add")
+    if ex is not None:
+        ex = _rows(ex, "ex")
+        T = ex.shape[1]
+    elif rng_state is not None and add is not None:
+        T = add.shape[1]
+    else:
+        raise GolfError("noise_fir_design: pass the noise (ex) or rng_state together with `add` (which fixes the length)")
+    n_blocks = _fir_blocks_count(T, Fr, K, hop)
+    if add is not None and add.shape[1] < n_blocks * hop:
+        raise GolfError("noise_fir_design: `add` shorter than the output")
+    y = torch.empty(B, n_blocks * hop, dtype=torch.float32, device=log_mag.device)
+    with _on(log_mag.device):
+        rc = _lib.lib().golf_noise_fir_design_fwd(_ptr(ex), 0 if ex is None else ex.stride(0), 0 if ex is not None else _ptr(rng_state),
+                                                  _ptr(log_mag), _ptr(window), _ptr(add), 0 if add is None else add.stride(0), _ptr(y),
+                                                  B, T, Fr, n_mag, hop, _stream())
+    check(rc, "golf_noise_fir_design_fwd")
+    return y
+
+
+def synth_fused(phase, phase_hop: int, w, w_hop: int, table, dec_kernel, oversampling: int, equal_energy: bool, accumulate: str,
+                log_mag, fir_window, gain, a, hop: int, room_k=None, noise=None, rng_state=None, refine: bool = True,
+                workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The whole GOLF-ss decoder pass through golf_synth_fused_fwd (five launches, no library kernel): oscillator ->
+    + FIR-filtered noise (taps designed in-kernel) -> sample-wise LPC filter -> room FIR.  noise [B,>=T_osc] is the
+    white-noise draw; noise=None uses the in-kernel generator with rng_state (advanced by the call).  Inference only."""
+    phase, w, table = _cuda_f32(phase, "phase"), _cuda_f32(w, "w"), _cuda_f32(table, "table")
+    log_mag, fir_window = _cuda_f32(log_mag, "log_mag"), _cuda_f32(fir_window, "window")
+    gain, a = _cuda_f32(gain, "gain"), _cuda_f32(a, "a")
+    dk = None if dec_kernel is None else _cuda_f32(dec_kernel, "dec_kernel")
+    rk = None if room_k is None else _cuda_f32(room_k, "room kernel")
+    B, Np = phase.shape
+    Fw = w.shape[1]
+    n_tab, P = table.shape
+    Fr, M = a.shape[1], a.shape[2]
+    n_mag = log_mag.shape[2]
+    if log_mag.shape[:2] != (B, Fr) or tuple(gain.shape) != (B, Fr) or a.shape[0] != B or w.shape[0] != B:
+        raise GolfError("synth_fused: inconsistent control shapes")
+    if noise is None and rng_state is None:
+        raise GolfError("synth_fused: pass the white-noise draw or an rng_state")
+    if noise is not None:
+        noise = _rows(noise, "noise")
+    zeros = 0 if dk is None else (dk.numel() - 1) // (2 * oversampling)
+    lib = _lib.lib()
+    L = lib.golf_synth_fused_out_length(Np, phase_hop, oversampling, Fr, hop, n_mag)
+    nbytes = lib.golf_synth_fused_workspace_bytes(B, Np, phase_hop, Fw, P, oversampling, Fr, M, hop, n_mag)
+    if L <= 0 or nbytes == 0:
+        raise GolfError("synth_fused: unsupported configuration")
+    ws = workspace if workspace is not None else _workspace(nbytes, phase.device)
+    if ws.numel() < nbytes or ws.data_ptr() % 256:
+        raise GolfError("synth_fused: workspace too small or not 256-byte aligned")
+    out = torch.empty(B, L, dtype=torch.float32, device=phase.device)
+    with _on(phase.device):
+        rc = lib.golf_synth_fused_fwd(_ptr(phase), _ptr(w), _ptr(table), _ptr(dk), _ptr(noise), 0 if noise is None else noise.stride(0),
+                                      0 if noise is not None else _ptr(rng_state), _ptr(log_mag), _ptr(fir_window), _ptr(gain), _ptr(a),
+                                      _ptr(rk), 0 if rk is None else rk.numel(), _ptr(out), B, Np, phase_hop, Fw, w_hop, n_tab, P,
+                                      oversampling, zeros, _OSC_MODES[accumulate], 1 if equal_energy else 0, Fr, M, hop, n_mag,
+                                      1 if refine else 0, _ptr(ws), ws.numel(), _stream())
+    check(rc, "golf_synth_fused_fwd")
+    return out
+
+
 class _RoomFir(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, k):

@@ -13,6 +13,8 @@ from .audiotensor import AudioTensor, hop_of, like, plain
 from .ctrl import PassThrough, Synth
 from . import functional as G
 from .filters import LTIAcousticFilter, LTVMinimumPhaseFilter, LTVMinimumPhaseFilterPrecise, LTVZeroPhaseFIRFilter
+from . import filters as filters_mod
+from . import synth as synth_mod
 from .noise import StandardNormalNoise
 from .synth import IndexedGlottalFlowTable
 
@@ -25,6 +27,7 @@ from .synth import IndexedGlottalFlowTable
 CONCURRENT = "auto"
 SPLIT = 1
 FUSE_ROOM = True  # GOLF-ss end filter + room FIR through golf_lpc_ss_room_fwd (False: two module calls)
+FUSED = True      # inference on the shipped GOLF-ss configuration through golf_synth_fused_fwd (False: module by module)
 _SIDE_STREAMS = {}
 
 
@@ -50,6 +53,8 @@ class SourceFilterSynth(Synth):
                 end_filter_params: Tuple, voicing: Optional[AudioTensor] = None, target: Optional[AudioTensor] = None,
                 **other_params):
         if voicing is None and target is None and self._can_run_concurrent(phase, noise_filter_params, end_filter_params):
+            if FUSED and self._can_run_fused(phase, harm_oscillator_params, noise_filter_params, end_filter_params):
+                return self._forward_fused(phase, harm_oscillator_params, noise_filter_params, end_filter_params)
             return self._forward_concurrent(phase, harm_oscillator_params, noise_filter_params, end_filter_params)
         harm = self.harm_oscillator(phase, *harm_oscillator_params)
         if voicing is not None:
@@ -78,6 +83,39 @@ class SourceFilterSynth(Synth):
                 y = G.lpc_ss_room(plain(src), plain(gain), plain(a), self.room_filter.kernel, hop // ex_hop)
                 return like(src, y, ex_hop)
         return self.room_filter(self.end_filter(src, *end_filter_params))
+
+    # ------------------------------------------------------------- fused inference path
+    def _can_run_fused(self, phase, harm_oscillator_params, noise_filter_params, end_filter_params) -> bool:
+        """the shipped GOLF-ss inference configuration (cfg/ae/decoder/golf-precise.yaml), no phase offset"""
+        lm, (gain, a) = noise_filter_params[0], end_filter_params
+        hop = hop_of(lm)
+        return (len(harm_oscillator_params) == 1 and hop_of(phase) >= 1 and hop_of(a, hop) == hop
+                and plain(a).shape[1] == plain(gain).shape[1] == plain(lm).shape[1]
+                and G.noise_fir_design_supported(plain(lm).shape[-1], hop)
+                and (type(self.room_filter) is PassThrough or (type(self.room_filter) is LTIAcousticFilter and self.room_filter.kernel.numel() <= 252))
+                and plain(phase).dtype == torch.float32)
+
+    def _forward_fused(self, phase, harm_oscillator_params, noise_filter_params, end_filter_params):
+        """One C call for the whole pass (golf_synth_fused_fwd): five launches, no library kernel.  The noise draw is
+        torch.randn (one ATen launch, exact torch stream) unless the generator module opts into the in-kernel one."""
+        osc, (w,), lm, (gain, a) = self.harm_oscillator, harm_oscillator_params, noise_filter_params[0], end_filter_params
+        ph = plain(phase)
+        dev = ph.device
+        if synth_mod.CHECK_INPUTS == "sync":
+            assert bool(((ph >= 0) & (ph <= 0.5)).all()), "phase (cycles/sample) must lie in [0, 0.5]"
+            assert bool(((plain(w) >= 0) & (plain(w) <= 1)).all()), "table_select_weight must lie in [0, 1]"
+        n_mag = plain(lm).shape[-1]
+        noise = rng = None
+        if getattr(self.noise_generator, "fused", False):
+            rng = self.noise_generator.rng_state(dev)
+        else:
+            noise = torch.randn(ph.shape[0], osc.out_length(phase), dtype=torch.float32, device=dev)
+        room_k = self.room_filter.kernel if type(self.room_filter) is LTIAcousticFilter else None
+        dk = osc.decimater.kernel if osc.oversampling > 1 else None
+        y = G.synth_fused(ph, hop_of(phase), plain(w), hop_of(w), osc.table, dk, osc.oversampling, osc.equal_energy,
+                          osc.phase_accumulation, plain(lm), self.noise_filter._window(2 * (n_mag - 1), plain(lm), scaled=False),
+                          plain(gain), plain(a), hop_of(lm), room_k, noise, rng)
+        return like(phase, y, 1)
 
     # ------------------------------------------------------------- concurrent inference path
     def _can_run_concurrent(self, phase, noise_filter_params, end_filter_params) -> bool:
@@ -122,16 +160,21 @@ class SourceFilterSynth(Synth):
         dev = plain(phase).device
         hop = hop_of(log_mag)
         t_osc = self.harm_oscillator.out_length(phase)
-        s_fir.wait_stream(s_run)
+        in_kernel_design = filters_mod.FUSED_DESIGN and G.noise_fir_design_supported(plain(log_mag).shape[-1], hop)
         s_rng.wait_stream(s_run)
         with torch.cuda.stream(s_rng):
             noise = torch.randn(plain(phase).shape[0], t_osc, dtype=torch.float32, device=dev)
             noise.record_stream(s_run)
-        with torch.cuda.stream(s_fir):
-            raw = self.noise_filter.raw_kernels(log_mag)
-            raw.record_stream(s_run)
+        if not in_kernel_design:
+            s_fir.wait_stream(s_run)
+            with torch.cuda.stream(s_fir):
+                raw = self.noise_filter.raw_kernels(log_mag)
+                raw.record_stream(s_run)
         harm = self.harm_oscillator(phase, *harm_oscillator_params)
-        s_run.wait_stream(s_fir)
         s_run.wait_stream(s_rng)
-        src = self.noise_filter.apply_raw(like(harm, noise, 1), raw, hop, add=harm)
+        if in_kernel_design:
+            src = self.noise_filter(like(harm, noise, 1), log_mag, add=harm)
+        else:
+            s_run.wait_stream(s_fir)
+            src = self.noise_filter.apply_raw(like(harm, noise, 1), raw, hop, add=harm)
         return self._end_and_room(src, end_filter_params)

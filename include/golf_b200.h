@@ -21,7 +21,9 @@
  *   golf_lpc_inverse_fwd/bwd models/filters.py:186-195 reverse() + models/utils.py:433-441 fir_filt, and its
  *                            autograd (inverse-target training, ltng/vocoder.py:192-198)
  *   golf_noise_fir_*         models/filters.py:350-384 LTVZeroPhaseFIRFilter.forward (block FIR)
+ *   golf_noise_fir_design_fwd models/filters.py:294-306 + 360-384 (+ models/noise.py:34-35 when it draws the noise itself)
  *   golf_room_fir_*          models/filters.py:443-450 LTIAcousticFilter.forward
+ *   golf_synth_fused_fwd     models/sf.py:47-64 SourceFilterSynth.forward, GOLF-ss modules, inference
  *   golf_glottal_osc_fwd     models/synth.py:213-263   IndexedGlottalFlowTable.forward
  *   golf_glottal_osc_fwd_from  the same with phase_offset (models/synth.py:195-218,251-252) as a per-utterance constant
  *   golf_glottal_osc_bwd_w   autograd of the above w.r.t. table_select_weight
@@ -42,7 +44,7 @@
 extern "C" {
 #endif
 
-#define GOLF_B200_ABI_VERSION 4
+#define GOLF_B200_ABI_VERSION 5
 
 enum {
   GOLF_OK = 0,
@@ -169,6 +171,19 @@ void golf_fir_set_variant(int x2);
 int golf_noise_fir_bwd(const float *gy, const float *ex, int64_t ex_stride,
                        const float *kernel, float *d_ex, float *d_kernel, int B, int T, int F,
                        int K, int hop, void *stream);
+/* Noise branch in one kernel (n_mag == 256, 128 < hop <= 256, hop % 4 == 0: golf_noise_fir_design_supported):
+ * taps designed in-kernel from log_mag [B,F,n_mag] (models/filters.py:294-306: exp -> irfft -> fftshift -> window, as
+ * a cosine series -- no FFT library, no [B,F,K] kernel tensor), block FIR as golf_noise_fir_fwd, optional `add`.
+ * window: [2*(n_mag-1)] the module's window (NOT divided by K).  Noise: `ex` [B,T] (e.g. the torch.randn draw of
+ * models/noise.py:34-35), or ex == NULL and rng_state -> device {seed, offset} (two uint64): white N(0,1) noise from
+ * Philox4x32-10 + Box-Muller inside the kernel (same distribution as randn_like, not the same stream; the caller
+ * advances the offset between calls: golf_rng_advance).  golf_philox_normal writes that very draw to memory. */
+int golf_noise_fir_design_supported(int n_mag, int hop);
+int golf_noise_fir_design_fwd(const float *ex, int64_t ex_stride, const uint64_t *rng_state, const float *log_mag,
+                              const float *window, const float *add, int64_t add_stride, float *y, int B, int T,
+                              int F, int n_mag, int hop, void *stream);
+int golf_philox_normal(float *out, int B, int T, const uint64_t *rng_state, void *stream);
+int golf_rng_advance(uint64_t *rng_state, void *stream);
 /* out[t] = x[t] + sum_{j<n} k[j] x[t-n+j]   (n = length-1 learned taps) */
 int golf_room_fir_fwd(const float *x, const float *k, float *out, int B, int T, int n,
                       void *stream);
@@ -214,6 +229,23 @@ int golf_glottal_osc_bwd_w(const float *gout, const float *phase, const float *w
 /* GlottalFlowTable.generate: wrapped [B,N] in [0,1), tables [B,R,P] at hop hop_tab. */
 int golf_wavetable_read_fwd(const float *wrapped, const float *tables, float *out, int B,
                             int N, int R, int P, int hop_tab, void *stream);
+
+/* ------------------------------------------------------------ whole decoder ---- */
+/* SourceFilterSynth.forward (models/sf.py:47-64) for the GOLF-ss decoder of cfg/ae/decoder/golf-precise.yaml in one
+ * call: oscillator -> (+ FIR-filtered noise, golf_noise_fir_design_fwd) -> sample-wise LPC filter -> room FIR.  Five
+ * launches (six with the in-kernel generator's offset bump), no library kernel, no allocation; harm / src / y live in
+ * the workspace.  Arguments as in golf_glottal_osc_fwd, golf_noise_fir_design_fwd and golf_lpc_ss_room_fwd;
+ * noise == NULL selects the in-kernel generator (rng_state is advanced); room_k == NULL skips the room filter.
+ * out [B, golf_synth_fused_out_length(...)].  The workspace must be 256-byte aligned. */
+size_t golf_synth_fused_workspace_bytes(int B, int Np, int phase_hop, int Fw, int P, int os, int F, int M, int hop,
+                                        int n_mag);
+int golf_synth_fused_out_length(int Np, int phase_hop, int os, int F, int hop, int n_mag);
+int golf_synth_fused_fwd(const float *phase, const float *w, const float *table, const float *dec_kernel,
+                         const float *noise, int64_t noise_stride, uint64_t *rng_state, const float *log_mag,
+                         const float *fir_window, const float *gain, const float *a, const float *room_k, int room_n,
+                         float *out, int B, int Np, int phase_hop, int Fw, int w_hop, int n_tab, int P, int os,
+                         int zeros, int osc_accumulate, int osc_flags, int F, int M, int hop, int n_mag, int refine,
+                         void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------- frame-rate helpers ---- */
 /* x [R,n] -> out [R,(n-1)*hop+1], F.interpolate(linear, align_corners=True) */
