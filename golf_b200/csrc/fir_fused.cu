@@ -267,9 +267,11 @@ GOLF_API int golf_noise_fir_design_fwd(const float* ex, int64_t ex_stride, const
   const size_t sm = ((size_t)2 * XS + (size_t)kDFB * 2 * kDK20 + (size_t)kDFB * kDN) * sizeof(float);
   const bool aligned = ((uintptr_t)y % 16 == 0) && (!add || ((uintptr_t)add % 16 == 0 && add_stride % 4 == 0));
   static unsigned long long attr = 0;
-  if (first_use_on_device(attr)) {
-    GOLF_CUDA(cudaFuncSetAttribute(noise_fir_design_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    GOLF_CUDA(cudaFuncSetAttribute(noise_fir_design_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  if (first_use_on_device(attr)) {  // sized for the largest supported hop (256), not for this call's
+    const int xs_max = (kDFB - 1) * 256 + 15 * kR2 + kDK20 + 24;
+    const size_t sm_max = ((size_t)2 * align_up((size_t)xs_max + 1, 32) + (size_t)kDFB * 2 * kDK20 + (size_t)kDFB * kDN) * sizeof(float);
+    GOLF_CUDA(cudaFuncSetAttribute(noise_fir_design_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_max));
+    GOLF_CUDA(cudaFuncSetAttribute(noise_fir_design_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_max));
   }
   const dim3 grid(ceil_div(n_blocks, kDFB), B);
   if (ex)

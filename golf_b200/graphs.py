@@ -19,7 +19,12 @@ from typing import Any, Dict
 import torch
 from torch.utils._pytree import tree_flatten, tree_unflatten
 
+import itertools
+
+from . import noise as _noise
 from . import synth as _synth
+
+_RNG_SLOTS = itertools.count(1)
 from .audiotensor import hop_of, like, plain
 
 
@@ -58,6 +63,7 @@ class GraphedSynth:
         self.decoder = decoder
         self.graph = torch.cuda.CUDAGraph()
         checks, _synth.CHECK_INPUTS = _synth.CHECK_INPUTS, "off"
+        slot, _noise.RNG_SLOT[0] = _noise.RNG_SLOT[0], next(_RNG_SLOTS)  # this capture's own in-kernel generator state
         try:
             with torch.no_grad():
                 side = torch.cuda.Stream(device=dev)
@@ -74,6 +80,7 @@ class GraphedSynth:
                 self.kernels_captured = launch_count() - n0  # golf_b200 kernels replayed per call
         finally:
             _synth.CHECK_INPUTS = checks
+            _noise.RNG_SLOT[0] = slot
 
     def _wrapped(self):
         leaves = [like(r, s, h) if (t and h is not None) else s for s, t, h, r in zip(self._static, self._is_tensor, self._hops, self._refs)]

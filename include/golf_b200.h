@@ -75,7 +75,7 @@ uint64_t golf_launch_count(void);
  * chunk = 0 lets the library pick the time-chunk length. */
 size_t golf_lpc_ss_workspace_bytes(int B, int L, int M, int hop, int chunk);
 /* The refinement round runs per sequence only when the states the chunks really
- * ended in differ from the stitched ones by more than tol * max|state| (default 1e-4; 0 = always).
+ * ended in differ from the stitched ones by more than tol * max|state| (default 1e-5; 0 = always).
  * Process-wide setting. */
 void golf_lpc_ss_set_refine_tolerance(float tol);
 float golf_lpc_ss_get_refine_tolerance(void);

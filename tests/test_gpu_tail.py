@@ -24,7 +24,7 @@ def tail_switch():
     L = _lib.lib()
     yield L.golf_lpc_ss_set_tail
     L.golf_lpc_ss_set_tail(1)
-    L.golf_lpc_ss_set_refine_tolerance(1e-4)
+    L.golf_lpc_ss_set_refine_tolerance(1e-5)
 
 
 def cu(*ts):

@@ -57,11 +57,15 @@ def graphed(fn):
     return lambda i: g.replay()
 
 srct, L = src.as_tensor(), y.shape[1]
+win510 = torch.hann_window(510, device=dev)
+rng = G.new_rng_state(dev, 1)
 stages = [
     ("oscillator", lambda: dec.harm_oscillator(A(s, "phase", 1), A(s, "w", 2400))),
     ("randn", lambda: dec.noise_generator(harm)),
     ("exp+irfft", lambda: dec.noise_filter.raw_kernels(A(s, "log_mag", 240))),
     ("noise FIR (+harm)", lambda: dec.noise_filter.apply_raw(noise, raw, 240, add=harm)),
+    ("noise FIR + in-kernel design", lambda: dec.noise_filter(noise, A(s, "log_mag", 240), add=harm)),
+    ("... + in-kernel noise", lambda: G.noise_fir_design(None, s["log_mag"], win510, 240, add=harm.as_tensor(), rng_state=rng)),
     ("lpc_ss all (15)", lambda: G._lpc_ss_fwd(srct, s["gain"], s["a"], None, 240, 0, 15)),
     ("lpc_ss no refine (7)", lambda: G._lpc_ss_fwd(srct, s["gain"], s["a"], None, 240, 0, 7)),
     ("lpc_ss responses+z (1)", lambda: G._lpc_ss_fwd(srct, s["gain"], s["a"], None, 240, 0, 1)),
