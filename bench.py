@@ -259,6 +259,8 @@ def run_gpu(args):
     torch.manual_seed(2434 + rank)
 
     fused_noise = NOISE_MODE == "fused"
+    if "GOLF_BENCH_TAIL" in os.environ:  # A/B: 0 = separate stitch / solve launches, 1 = cluster tail, 2 = by batch size (default)
+        golf_b200_lib().golf_lpc_ss_set_tail(int(os.environ["GOLF_BENCH_TAIL"]))
     dec = build_decoder(dev, fused_noise=fused_noise)
     raw_sets = make_inputs(N_SETS, BATCH, seed=2434 + rank)
     dev_sets = [{k: v.to(dev) for k, v in s.items()} for s in raw_sets]
@@ -547,7 +549,8 @@ def kernel_rooflines(dev, dec, dev_sets, G, AudioTensor):
     filt = add("GOLF-ss filter + room FIR (golf_lpc_ss_room_fwd: responses + tail)", ["ss_response_kernel", "ss_tail_kernel"],
                lambda i: lpc(i, 15, True), (8 + ctl) * n, flops=2.0 * (ORDER * (ORDER + 1) + ORDER + 128) * n)
     add("oscillator (knot prefix + flow / 4x decimation)", ["osc_knot_prefix_q64_kernel", "osc_flow_v2_kernel"],
-        lambda i: osc(AudioTensor(dev_sets[i % N_SETS]["phase"], hop_length=1), AudioTensor(dev_sets[i % N_SETS]["w"], hop_length=2400)),
+        lambda i: G.glottal_osc(dev_sets[i % N_SETS]["phase"], 1, dev_sets[i % N_SETS]["w"], 2400, osc.table, osc.decimater.kernel,
+                                osc.oversampling, osc.equal_energy, osc.phase_accumulation),
         8.0 * BATCH * T, note="reads phase (sample rate), writes harm")
     add("noise branch: FIR design + 510-tap block FIR + harm (noise tensor given)", ["noise_fir_design_kernel"],
         lambda i: G.noise_fir_design(noise, dev_sets[i % N_SETS]["log_mag"], win, HOP, add=harm), (12 + 4 * N_MAG / HOP) * n,

@@ -43,7 +43,8 @@
 namespace golf {
 
 extern int g_solve_systolic;  // 1 (default): 4-lanes-per-chunk solve where it applies; 0: lane-per-chunk
-extern int g_ss_tail;         // 1 (default): stitch + solve + refinement (+ room) in one cluster launch where it applies
+extern int g_ss_tail;         // stitch + solve + refinement (+ room) in one cluster launch: 0 never, 1 where it applies, 2 (default) small batches
+constexpr int kTailAutoMaxBatch = 8;
 
 struct SsParams {
   const float* in;     // FORM0: ex [B, in_stride]; FORM1: gy [B, L]
@@ -917,7 +918,12 @@ int launch_mp(const SsParams& p, bool generic, int passes, cudaStream_t st) {
   // one-launch tail: two-level stitch + solve + refinement (+ room FIR) by a cluster per sequence (lpc_ss_tail.cuh)
   bool use_tail = false;
   if constexpr (FORM == 0 && MP >= 16 && MP % 8 == 0 && MP <= 32) {
-    use_tail = !generic && g_solve_systolic && g_ss_tail && (passes & 6) == 6 && p.Gw != nullptr;
+    // g_ss_tail: 0 never, 1 always, 2 (default) for small batches only.  The cluster kernel shortens the serial part
+    // of a pass but holds whole SMs for it (166 registers x 256 threads, 100 KB of shared memory per CTA, 4 CTAs per
+    // sequence): with several passes in flight at B = 32 it costs throughput (bench.py `value` 6.05e9 vs 7.10e9 samples/s
+    // with the light stitch / solve launches), while one pass at a time is a wash there (316 vs 320 us).
+    const bool tail_wanted = g_ss_tail == 1 || (g_ss_tail == 2 && p.B <= kTailAutoMaxBatch);
+    use_tail = !generic && g_solve_systolic && tail_wanted && (passes & 6) == 6 && p.Gw != nullptr;
   }
   if (p.room_k && !use_tail) return GOLF_ERR_UNSUPPORTED;  // the fused room FIR exists only in the tail kernel
   if (nresp > 0 && (passes & 1)) {

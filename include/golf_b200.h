@@ -75,7 +75,7 @@ uint64_t golf_launch_count(void);
  * chunk = 0 lets the library pick the time-chunk length. */
 size_t golf_lpc_ss_workspace_bytes(int B, int L, int M, int hop, int chunk);
 /* The refinement round runs per sequence only when the states the chunks really
- * ended in differ from the stitched ones by more than tol * max|state| (default 1e-5; 0 = always).
+ * ended in differ from the stitched ones by more than tol * max|state| (default 1e-4; 0 = always).
  * Process-wide setting. */
 void golf_lpc_ss_set_refine_tolerance(float tol);
 float golf_lpc_ss_get_refine_tolerance(void);
@@ -98,10 +98,12 @@ int golf_lpc_ss_fwd_passes(const float *ex, int64_t ex_stride, const float *gain
                            const float *a, const float *zi, float *y, int B, int L, int F,
                            int M, int hop, int chunk, void *workspace, size_t workspace_bytes,
                            int passes, void *stream);
-/* 1 (default): passes 2..4 (stitch, solve, refinement) run as ONE launch, a thread-block cluster per sequence with a
- * two-level stitch; 0: the separate stitch / solve launches.  Same recurrences, different grouping of
- * the state propagation (results agree to float32 rounding).  Process-wide; for A/B timing and tests. */
-void golf_lpc_ss_set_tail(int fused);
+/* Passes 2..4 (stitch, solve, refinement -- and the room FIR of golf_lpc_ss_room_fwd) as ONE launch, a thread-block
+ * cluster per sequence with a two-level stitch: mode 0 never, 1 wherever the kernel applies, 2 (default)
+ * for batches of at most 8 sequences -- the cluster kernel shortens the serial part of a pass but occupies whole SMs, which
+ * costs throughput once several passes of a large batch are in flight.  Same recurrences, different grouping of the state
+ * propagation (results agree to float32 rounding).  Process-wide. */
+void golf_lpc_ss_set_tail(int mode);
 /* GOLF-ss end filter + the room filter behind it (models/sf.py:64: room_filter(end_filter(src, gain, a)) with
  * models/filters.py:99-113 and :443-450) in the same launches: out[t] = y[t] + sum_{j<room_n} room_k[j] y[t-room_n+j],
  * y = golf_lpc_ss_fwd(ex, gain, a, zi).  y may be NULL (the filter output then lives in the workspace only; pass a

@@ -23,8 +23,8 @@ def tail_switch():
 
     L = _lib.lib()
     yield L.golf_lpc_ss_set_tail
-    L.golf_lpc_ss_set_tail(1)
-    L.golf_lpc_ss_set_refine_tolerance(1e-5)
+    L.golf_lpc_ss_set_tail(2)  # library default: automatic (small batches)
+    L.golf_lpc_ss_set_refine_tolerance(1e-4)
 
 
 def cu(*ts):

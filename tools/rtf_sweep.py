@@ -20,6 +20,10 @@ dev = torch.device("cuda:0")
 SR, SEC = 24000, 2.0
 T = int(SR * SEC)
 with_cpu = "--cpu" in sys.argv
+quick = "--quick" in sys.argv  # hop 240, order 20 only
+if "GOLF_TAIL" in os.environ:  # A/B of the GOLF-ss schedules: 0 light stitch / solve launches, 1 cluster tail, 2 automatic
+    from golf_b200 import _lib
+    _lib.lib().golf_lpc_ss_set_tail(int(os.environ["GOLF_TAIL"]))
 
 
 def trimmed_mean(xs):
@@ -50,8 +54,8 @@ def decoder(variant, hop, M):
 
 rows = []
 gsynth.CHECK_INPUTS = "off"
-for hop in (120, 240):
-    for M in (12, 20, 32):
+for hop in ((240,) if quick else (120, 240)):
+    for M in ((20,) if quick else (12, 20, 32)):
         for B in (1, 8, 32, 128):
             Fr = T // hop + 1
             gain, a = synthetic_controls(B, Fr, M, seed=hop + M)
