@@ -152,7 +152,7 @@ __global__ void ss_dzi_kernel(const float* __restrict__ u, const float* __restri
 // floor, 2.4e-4 -- 1e-5 leaves none above 10x but also fires on realistic controls, +45 us per pass: tools/diag_accuracy.py.)
 static float g_refine_tol = 1e-4f;
 int g_solve_systolic = 1;
-int g_ss_tail = 2;
+int g_ss_tail = 0;
 
 struct SsPlan {
   int B, MP, Lc, C, HB;

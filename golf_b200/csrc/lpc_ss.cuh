@@ -43,7 +43,7 @@
 namespace golf {
 
 extern int g_solve_systolic;  // 1 (default): 4-lanes-per-chunk solve where it applies; 0: lane-per-chunk
-extern int g_ss_tail;         // stitch + solve + refinement (+ room) in one cluster launch: 0 never, 1 where it applies, 2 (default) small batches
+extern int g_ss_tail;         // stitch + solve + refinement (+ room) in one cluster launch: 0 (default) never, 1 where it applies, 2 small batches
 constexpr int kTailAutoMaxBatch = 8;
 
 struct SsParams {
@@ -918,10 +918,12 @@ int launch_mp(const SsParams& p, bool generic, int passes, cudaStream_t st) {
   // one-launch tail: two-level stitch + solve + refinement (+ room FIR) by a cluster per sequence (lpc_ss_tail.cuh)
   bool use_tail = false;
   if constexpr (FORM == 0 && MP >= 16 && MP % 8 == 0 && MP <= 32) {
-    // g_ss_tail: 0 never, 1 always, 2 (default) for small batches only.  The cluster kernel shortens the serial part
-    // of a pass but holds whole SMs for it (166 registers x 256 threads, 100 KB of shared memory per CTA, 4 CTAs per
-    // sequence): with several passes in flight at B = 32 it costs throughput (bench.py `value` 6.05e9 vs 7.10e9 samples/s
-    // with the light stitch / solve launches), while one pass at a time is a wash there (316 vs 320 us).
+    // g_ss_tail: 0 (default) never, 1 wherever it applies, 2 for batches of at most kTailAutoMaxBatch sequences.  The
+    // cluster kernel shortens the serial part of the FILTER (B = 1: 150 -> 142 us, B = 32: 178 -> 163 us) but holds whole
+    // SMs for it (166 registers x 256 threads, 100 KB of shared memory per CTA, 4 CTAs per sequence) and its fused room
+    // FIR runs on those 4 SMs only: with several passes in flight at B = 32 it costs throughput (bench.py `value`
+    // 6.05e9 vs 7.10e9 samples/s with the light stitch / solve launches) and the whole decoder is no faster even at
+    // B = 1 (250 vs 246 us).  It stays an opt-in schedule (profiles/README.md, round 2).
     const bool tail_wanted = g_ss_tail == 1 || (g_ss_tail == 2 && p.B <= kTailAutoMaxBatch);
     use_tail = !generic && g_solve_systolic && tail_wanted && (passes & 6) == 6 && p.Gw != nullptr;
   }

@@ -99,10 +99,11 @@ int golf_lpc_ss_fwd_passes(const float *ex, int64_t ex_stride, const float *gain
                            int M, int hop, int chunk, void *workspace, size_t workspace_bytes,
                            int passes, void *stream);
 /* Passes 2..4 (stitch, solve, refinement -- and the room FIR of golf_lpc_ss_room_fwd) as ONE launch, a thread-block
- * cluster per sequence with a two-level stitch: mode 0 never, 1 wherever the kernel applies, 2 (default)
- * for batches of at most 8 sequences -- the cluster kernel shortens the serial part of a pass but occupies whole SMs, which
- * costs throughput once several passes of a large batch are in flight.  Same recurrences, different grouping of the state
- * propagation (results agree to float32 rounding).  Process-wide. */
+ * cluster per sequence with a two-level stitch: mode 0 (default) never, 1 wherever the kernel applies,
+ * 2 for batches of at most 8 sequences.  An opt-in schedule: it shortens the filter's serial part and brings a decoder
+ * pass down to five launches, but it occupies whole SMs, which costs throughput once several passes are in flight
+ * (measured, profiles/README.md).  Same recurrences, different grouping of the state propagation (results agree to
+ * float32 rounding).  Process-wide. */
 void golf_lpc_ss_set_tail(int mode);
 /* GOLF-ss end filter + the room filter behind it (models/sf.py:64: room_filter(end_filter(src, gain, a)) with
  * models/filters.py:99-113 and :443-450) in the same launches: out[t] = y[t] + sum_{j<room_n} room_k[j] y[t-room_n+j],

@@ -23,7 +23,7 @@ def tail_switch():
 
     L = _lib.lib()
     yield L.golf_lpc_ss_set_tail
-    L.golf_lpc_ss_set_tail(2)  # library default: automatic (small batches)
+    L.golf_lpc_ss_set_tail(0)  # library default: the light stitch / solve launches
     L.golf_lpc_ss_set_refine_tolerance(1e-4)
 
 

@@ -29,4 +29,4 @@ for M, hop in ((22, 240), (32, 120), (32, 240)):
             e = rows(y, r64)
             worst = int(e.argmax())
             print(f"   tail={tail} {name:14s}: max {e.max():.2e} (row {worst}, floor there {floor[worst]:.2e})  rows > 1e-4: {int((e > 1e-4).sum())}  rows > 10x floor: {int((e > 10 * floor).sum())}")
-L.golf_lpc_ss_set_tail(2); L.golf_lpc_ss_set_refine_tolerance(1e-4)
+L.golf_lpc_ss_set_tail(0); L.golf_lpc_ss_set_refine_tolerance(1e-4)

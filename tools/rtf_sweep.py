@@ -20,7 +20,7 @@ dev = torch.device("cuda:0")
 SR, SEC = 24000, 2.0
 T = int(SR * SEC)
 with_cpu = "--cpu" in sys.argv
-quick = "--quick" in sys.argv  # hop 240, order 20 only
+quick = "--quick" in sys.argv  # hop 240, order 22 only
 if "GOLF_TAIL" in os.environ:  # A/B of the GOLF-ss schedules: 0 light stitch / solve launches, 1 cluster tail, 2 automatic
     from golf_b200 import _lib
     _lib.lib().golf_lpc_ss_set_tail(int(os.environ["GOLF_TAIL"]))
@@ -55,7 +55,7 @@ def decoder(variant, hop, M):
 rows = []
 gsynth.CHECK_INPUTS = "off"
 for hop in ((240,) if quick else (120, 240)):
-    for M in ((20,) if quick else (12, 20, 32)):
+    for M in ((22,) if quick else (12, 20, 32)):
         for B in (1, 8, 32, 128):
             Fr = T // hop + 1
             gain, a = synthetic_controls(B, Fr, M, seed=hop + M)
