@@ -28,120 +28,10 @@
 // STORE_V left in a workspace ([B*n_frames, win], L2 resident).
 //
 // Algorithmic HBM bytes per output sample: 4 (ex) + 4 (y) + 4(M+1)/hop = 8.383 B.
-#include "common.cuh"
+#include "lpc_ff.cuh"
 
 namespace golf {
 
-constexpr int kFfThreads = 128;
-
-struct FfParams {
-  const float* ex;       // fwd: excitation [B, ex_stride]; bwd: gy [B, out_len]
-  int64_t ex_stride;
-  const float* gain;     // [B,F]
-  const float* coef;     // all-pole: a [B,F,M]; biquad: [B,F,K,3]
-  const float* window;   // [win]
-  float* y;              // fwd: [B, out_len]; bwd: d_e [B, Le]
-  float* vws;            // [B*n_frames, win] frame outputs (fwd STORE_V writes, bwd reads)
-  float* d_a;            // bwd: [B,F,M]
-  int B, Le, F, M, hop, win, NQ, pad, n_frames, out_len, nseg0, nseg, ctas_per_seq;
-  int interp_gain;       // 1: strip holds ex*up(gain) (ff); 0: gain applied per frame (biquad synth)
-  float scale;
-};
-
-// ---- per-frame filters ------------------------------------------------------------
-template <int MP>
-struct AllPole {
-  static constexpr int TILE = MP;
-  float na[MP];  // na[j] = -a[MP-1-j]: index j pairs with the output MP-j steps back (oldest first)
-  float h[MP];   // h[s] = output of tile position s (static rotation)
-  __device__ __forceinline__ void load(const FfParams& p, int b, int k, bool ok) {
-    const float* a = p.coef + ((size_t)b * p.F + (ok ? k : 0)) * p.M;
-#pragma unroll
-    for (int j = 0; j < MP; ++j) {
-      const int i = MP - 1 - j;  // tap index (a[i] multiplies y[n-1-i])
-      na[j] = (ok && i < p.M) ? -__ldg(a + i) : 0.f;
-      h[j] = 0.f;
-    }
-  }
-  template <int S>
-  __device__ __forceinline__ float step(float x) {
-    float acc0 = x, acc1 = 0.f, acc2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < MP - 1; ++j) {  // y[n-MP+j] sits in slot (S+j)%MP
-      if (j % 3 == 0) acc0 = __fmaf_rn(na[j], h[(S + j) % MP], acc0);
-      if (j % 3 == 1) acc1 = __fmaf_rn(na[j], h[(S + j) % MP], acc1);
-      if (j % 3 == 2) acc2 = __fmaf_rn(na[j], h[(S + j) % MP], acc2);
-    }
-    const float y = __fmaf_rn(na[MP - 1], h[(S + MP - 1) % MP], (acc0 + acc1) + acc2);
-    h[S] = y;
-    return y;
-  }
-};
-
-template <int KP>
-struct BiquadCascade {
-  static constexpr int TILE = 16;
-  float b0[KP], na1[KP], na2[KP], y1[KP], y2[KP];
-  int K;
-  __device__ __forceinline__ void load(const FfParams& p, int b, int k, bool ok) {
-    K = p.M;
-    const float* q = p.coef + ((size_t)b * p.F + (ok ? k : 0)) * p.M * 3;
-#pragma unroll
-    for (int j = 0; j < KP; ++j) {
-      const bool on = ok && j < p.M;
-      const float a0 = on ? q[3 * j] : 1.f;
-      b0[j] = 1.f / a0;
-      na1[j] = on ? -(q[3 * j + 1] / a0) : 0.f;
-      na2[j] = on ? -(q[3 * j + 2] / a0) : 0.f;
-      y1[j] = y2[j] = 0.f;
-    }
-  }
-  template <int S>
-  __device__ __forceinline__ float step(float x) {
-#pragma unroll
-    for (int j = 0; j < KP; ++j) {
-      if (j < K) {
-        float acc = __fmul_rn(x, b0[j]);
-        acc = __fmaf_rn(na2[j], y2[j], acc);
-        acc = __fmaf_rn(na1[j], y1[j], acc);
-        y2[j] = y1[j];
-        y1[j] = acc;
-        x = acc;
-      }
-    }
-    return x;
-  }
-};
-
-template <class Filt, int S, int N>
-struct TileSteps {
-  __device__ __forceinline__ static void run(Filt& f, const float* xs, float* ys) {
-    ys[S] = f.template step<S>(xs[S]);
-    if constexpr (S + 1 < N) TileSteps<Filt, S + 1, N>::run(f, xs, ys);
-  }
-};
-
-struct FfGeom {
-  int NS, NSTRIP, seg_stride, P0, k0;
-};
-__device__ __forceinline__ FfGeom ff_geom(const FfParams& p, int w) {
-  FfGeom g;
-  g.NS = 33 - p.NQ;          // complete segments per CTA
-  g.NSTRIP = 32 + p.NQ - 1;  // segments the CTA's 32 frames touch
-  g.seg_stride = p.hop + 1;
-  g.P0 = p.nseg0 + w * g.NS;  // first padded segment owned by this CTA
-  g.k0 = g.P0 - (p.NQ - 1);   // frame handled by lane 0
-  return g;
-}
-// overlap-added window at padded segment P, offset r
-__device__ __forceinline__ float ff_norm(const FfParams& p, const float* wsm, int P, int r) {
-  float norm = 0.f;
-  for (int q = p.NQ - 1; q >= 0; --q) {  // frame P-q contributes its q-th hop of the window
-    const int kk = P - q;
-    if (kk >= 0 && kk < p.n_frames) norm += wsm[q * p.hop + r];
-  }
-  return norm;
-}
 
 // ---- forward ------------------------------------------------------------------------
 // ALIGNED: hop % TILE == 0 and win % TILE == 0 -> a tile never crosses a hop boundary, every
@@ -256,7 +146,10 @@ __global__ void __launch_bounds__(kFfThreads) ff_forward_kernel(FfParams p) {
 
 // ---- adjoint (all-pole only) ----------------------------------------------------------
 // ex := gy [B,out_len]; y := d_e [B,Le]; vws = forward frame outputs; d_a [B,F,M].
-template <int MP>
+// FRAME_GAIN (BatchLPCSynth, models/lpc.py:62-91): the gain is one value per frame instead of an interpolated
+// envelope -- the excitation strip is staged too, d_gain[k] = sum_n u[n] ex[n] is accumulated by the frame's lane
+// and the segment accumulators receive gain_k * u (= d_ex directly).
+template <int MP, bool FRAME_GAIN>
 __global__ void __launch_bounds__(kFfThreads) ff_backward_kernel(FfParams p) {
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -266,6 +159,7 @@ __global__ void __launch_bounds__(kFfThreads) ff_backward_kernel(FfParams p) {
   float* __restrict__ acc = strip + g.NSTRIP * g.seg_stride;  // [NS][hop+1]     d_e accumulators
   float* __restrict__ wsm = acc + g.NS * g.seg_stride;        // [win]
   float* __restrict__ vt = wsm + p.win;                       // [2][32][2*MP+1] v tiles (double buffered): column c <-> v[nhi - 2*MP + c]
+  float* __restrict__ xstrip = vt + 2 * 32 * (2 * MP + 1);    // [NSTRIP][hop+1] excitation in padded coordinates (FRAME_GAIN)
   const int k = g.k0 + lane;
   const bool frame_ok = (k >= 0) && (k < p.n_frames);
   // a frame's d_a is produced by the CTA that owns it (not by the neighbour that recomputes it)
@@ -282,12 +176,18 @@ __global__ void __launch_bounds__(kFfThreads) ff_backward_kernel(FfParams p) {
     float v = 0.f;
     if (o >= 0 && o < p.out_len) v = __ldg(gyb + o) / ff_norm(p, wsm, P, r);
     strip[sg * g.seg_stride + r] = v;
+    if (FRAME_GAIN) {
+      const int pos = P * p.hop + r - p.pad;
+      xstrip[sg * g.seg_stride + r] = (pos >= 0 && pos < p.Le) ? __ldg(p.vws_ex + (size_t)b * p.ex_stride2 + pos) : 0.f;
+    }
   }
   __syncthreads();
 
   if (warp == 0) {
     AllPole<MP> f;
     f.load(p, b, k, frame_ok);
+    const float gframe = (FRAME_GAIN && frame_ok) ? __ldg(p.gain + (size_t)b * p.F + k) : 0.f;
+    float dg = 0.f;
     float da[MP];  // da[i] accumulates -sum_n u[n] v[n-1-i]
     float vh[MP];  // vh[m mod MP] = v[m] for the M most recent m < n (win % MP == 0 keeps slots static)
 #pragma unroll
@@ -333,6 +233,11 @@ __global__ void __launch_bounds__(kFfThreads) ff_backward_kernel(FfParams p) {
         for (int s = 0; s < MP; ++s) xs[s] = __fmul_rn(xrow[-s], wrow[-s]);
       }
       TileSteps<AllPole<MP>, 0, MP>::run(f, xs, us);
+      if (FRAME_GAIN) {
+        const float* __restrict__ erow = xstrip + (lane + q0) * g.seg_stride + r0;
+#pragma unroll
+        for (int s = 0; s < MP; ++s) dg = __fmaf_rn(us[s], erow[-s], dg);
+      }
       const float* __restrict__ vrow_t = vcur + lane * VT;
 #pragma unroll
       for (int s = 0; s < MP; ++s) {
@@ -348,7 +253,7 @@ __global__ void __launch_bounds__(kFfThreads) ff_backward_kernel(FfParams p) {
         if (frame_ok && sj >= 0 && sj < g.NS) {
           float* __restrict__ arow = acc + sj * g.seg_stride + r0;
 #pragma unroll
-          for (int s = 0; s < MP; ++s) arow[-s] += us[s];
+          for (int s = 0; s < MP; ++s) arow[-s] += FRAME_GAIN ? us[s] * gframe : us[s];
         }
       }
       r0 -= MP;
@@ -358,6 +263,7 @@ __global__ void __launch_bounds__(kFfThreads) ff_backward_kernel(FfParams p) {
       float* dst = p.d_a + ((size_t)b * p.F + k) * p.M;
       for (int i = 0; i < p.M; ++i) dst[i] = -da[i];
     }
+    if (FRAME_GAIN && own && p.d_gain) p.d_gain[(size_t)b * p.F + k] = dg;
   }
   __syncthreads();
   float* __restrict__ deb = p.y + (size_t)b * p.Le;
@@ -441,10 +347,6 @@ __global__ void lpc_inverse_dy_kernel(const float* __restrict__ g, const float* 
 }
 
 // ---- host side ------------------------------------------------------------------------
-static size_t ff_smem_bytes(const FfParams& p, int vt_floats) {
-  const int NS = 33 - p.NQ, NSTRIP = 32 + p.NQ - 1;
-  return ((size_t)(NS + NSTRIP) * (p.hop + 1) + p.win + vt_floats) * sizeof(float);
-}
 
 template <class Filt, bool STORE_V, bool ALIGNED>
 static int launch_ff_fwd_a(const FfParams& p, cudaStream_t st) {
@@ -468,43 +370,54 @@ static int launch_ff_fwd(const FfParams& p, cudaStream_t st) {
   return launch_ff_fwd_a<Filt, STORE_V, false>(p, st);
 }
 
-template <int MP>
+template <int MP, bool FRAME_GAIN>
 static int launch_ff_bwd(const FfParams& pf, const FfParams& pb, cudaStream_t st) {
   int rc = launch_ff_fwd<AllPole<MP>, true>(pf, st);
   if (rc) return rc;
-  const size_t sm = ff_smem_bytes(pb, 2 * 32 * (2 * MP + 1));
+  const int NSTRIP = 32 + pb.NQ - 1;
+  const size_t sm = ff_smem_bytes(pb, 2 * 32 * (2 * MP + 1) + (FRAME_GAIN ? NSTRIP * (pb.hop + 1) : 0));
   if (sm > 220 * 1024) return GOLF_ERR_UNSUPPORTED;
   static size_t sm_allowed_dev[64];
   int dev_ = 0;
   cudaGetDevice(&dev_);
   size_t& sm_allowed = sm_allowed_dev[dev_ & 63];
   if (sm > 48 * 1024 && sm > sm_allowed) {
-    GOLF_CUDA(cudaFuncSetAttribute(ff_backward_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    GOLF_CUDA(cudaFuncSetAttribute(ff_backward_kernel<MP, FRAME_GAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     sm_allowed = sm;
   }
-  ff_backward_kernel<MP><<<pb.B * pb.ctas_per_seq, kFfThreads, sm, st>>>(pb);
+  ff_backward_kernel<MP, FRAME_GAIN><<<pb.B * pb.ctas_per_seq, kFfThreads, sm, st>>>(pb);
   GOLF_CHECK_LAUNCH();
   return GOLF_OK;
 }
 
-static int fill_geometry(FfParams* p, int T_ex, int pad) {
-  if (p->win % p->hop != 0) return GOLF_ERR_UNSUPPORTED;
-  p->NQ = p->win / p->hop;
-  if (p->NQ < 2 || p->NQ > 8) return GOLF_ERR_UNSUPPORTED;
-  p->pad = pad;
-  const int64_t up = (int64_t)(p->F - 1) * p->hop + 1;
-  p->Le = p->interp_gain ? (int)(T_ex < up ? T_ex : up) : T_ex;
-  if (p->Le + 2 * pad < p->win) return GOLF_ERR_INVALID;
-  p->n_frames = (p->Le + 2 * pad - p->win) / p->hop + 1;
-  if (p->n_frames > p->F) return GOLF_ERR_INVALID;  // the reference asserts the same
-  p->out_len = (p->n_frames - 1) * p->hop + p->win - 2 * pad;
-  if (p->out_len <= 0) return GOLF_ERR_INVALID;
-  p->nseg0 = pad / p->hop;
-  const int last = (pad + p->out_len - 1) / p->hop;
-  p->nseg = last - p->nseg0 + 1;
-  p->ctas_per_seq = ceil_div(p->nseg, 33 - p->NQ);
-  p->scale = lerp_scale(p->F, p->hop);
-  return GOLF_OK;
+static inline int ff_padded_order(int M) {
+  return M <= 4 ? 4 : M <= 8 ? 8 : M <= 12 ? 12 : M <= 16 ? 16 : M <= 20 ? 20 : M <= 24 ? 24 : M <= 32 ? 32 : 40;
+}
+
+template <bool FRAME_GAIN>
+static int dispatch_ff_bwd(int mp, const FfParams& pf, const FfParams& pb, cudaStream_t st) {
+  switch (mp) {
+    case 4: return launch_ff_bwd<4, FRAME_GAIN>(pf, pb, st);
+    case 8: return launch_ff_bwd<8, FRAME_GAIN>(pf, pb, st);
+    case 12: return launch_ff_bwd<12, FRAME_GAIN>(pf, pb, st);
+    case 16: return launch_ff_bwd<16, FRAME_GAIN>(pf, pb, st);
+    case 20: return launch_ff_bwd<20, FRAME_GAIN>(pf, pb, st);
+    case 24: return launch_ff_bwd<24, FRAME_GAIN>(pf, pb, st);
+    case 32: return launch_ff_bwd<32, FRAME_GAIN>(pf, pb, st);
+    default: return launch_ff_bwd<40, FRAME_GAIN>(pf, pb, st);
+  }
+}
+
+template <bool STORE_V>
+static int dispatch_ff_fwd(int M, const FfParams& p, cudaStream_t st) {
+  if (M <= 4) return launch_ff_fwd<AllPole<4>, STORE_V>(p, st);
+  if (M <= 8) return launch_ff_fwd<AllPole<8>, STORE_V>(p, st);
+  if (M <= 12) return launch_ff_fwd<AllPole<12>, STORE_V>(p, st);
+  if (M <= 16) return launch_ff_fwd<AllPole<16>, STORE_V>(p, st);
+  if (M <= 20) return launch_ff_fwd<AllPole<20>, STORE_V>(p, st);
+  if (M <= 24) return launch_ff_fwd<AllPole<24>, STORE_V>(p, st);
+  if (M <= 32) return launch_ff_fwd<AllPole<32>, STORE_V>(p, st);
+  return launch_ff_fwd<AllPole<40>, STORE_V>(p, st);
 }
 
 }  // namespace golf
@@ -522,14 +435,7 @@ GOLF_API int golf_lpc_ff_fwd(const float* ex, int64_t ex_stride, const float* ga
   int rc = fill_geometry(&p, T_ex, win / 2);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (M <= 4) return launch_ff_fwd<AllPole<4>, false>(p, st);
-  if (M <= 8) return launch_ff_fwd<AllPole<8>, false>(p, st);
-  if (M <= 12) return launch_ff_fwd<AllPole<12>, false>(p, st);
-  if (M <= 16) return launch_ff_fwd<AllPole<16>, false>(p, st);
-  if (M <= 20) return launch_ff_fwd<AllPole<20>, false>(p, st);
-  if (M <= 24) return launch_ff_fwd<AllPole<24>, false>(p, st);
-  if (M <= 32) return launch_ff_fwd<AllPole<32>, false>(p, st);
-  return launch_ff_fwd<AllPole<40>, false>(p, st);
+  return dispatch_ff_fwd<false>(M, p, st);
 }
 
 GOLF_API size_t golf_lpc_ff_bwd_workspace_bytes(int B, int T_ex, int F, int hop, int win) {
@@ -564,18 +470,9 @@ GOLF_API int golf_lpc_ff_bwd(const float* gy, const float* ex, int64_t ex_stride
   // the adjoint writes d_e over every input position [0, Le), which can reach past the last output
   pb.nseg = (pf.pad + pf.Le - 1) / hop - pf.nseg0 + 1;
   pb.ctas_per_seq = ceil_div(pb.nseg, 33 - pf.NQ);
-  const int mp = M <= 4 ? 4 : M <= 8 ? 8 : M <= 12 ? 12 : M <= 16 ? 16 : M <= 20 ? 20 : M <= 24 ? 24 : M <= 32 ? 32 : 40;
+  const int mp = ff_padded_order(M);
   if (win % mp != 0 || hop % mp != 0) return GOLF_ERR_UNSUPPORTED;  // the adjoint keeps static slots / offsets
-  switch (mp) {
-    case 4: rc = launch_ff_bwd<4>(pf, pb, st); break;
-    case 8: rc = launch_ff_bwd<8>(pf, pb, st); break;
-    case 12: rc = launch_ff_bwd<12>(pf, pb, st); break;
-    case 16: rc = launch_ff_bwd<16>(pf, pb, st); break;
-    case 20: rc = launch_ff_bwd<20>(pf, pb, st); break;
-    case 24: rc = launch_ff_bwd<24>(pf, pb, st); break;
-    case 32: rc = launch_ff_bwd<32>(pf, pb, st); break;
-    default: rc = launch_ff_bwd<40>(pf, pb, st); break;
-  }
+  rc = dispatch_ff_bwd<false>(mp, pf, pb, st);
   if (rc) return rc;
   // d_ex covers the caller's full excitation row (zeros beyond the filtered span)
   const int span = T_ex > F ? T_ex : F;
@@ -586,6 +483,68 @@ GOLF_API int golf_lpc_ff_bwd(const float* gy, const float* ex, int64_t ex_stride
                                                                 d_a, B, T_ex, pf.Le, F, M, hop, pf.n_frames, 0, pf.scale);
   GOLF_CHECK_LAUNCH();
   return GOLF_OK;
+}
+
+// ---- BatchLPCSynth / LPCSynth (models/lpc.py:19-91): one gain per frame, frames padded by (win - hop) / 2 ----
+static int frames_params(FfParams* p, const float* ex, int64_t ex_stride, const float* gain, const float* a, const float* window,
+                         int B, int T_ex, int F, int M, int hop, int win) {
+  if (!ex || !gain || !a || !window || B <= 0 || T_ex <= 0 || F <= 0 || M <= 0 || hop <= 0 || win < 2 * hop) return GOLF_ERR_INVALID;
+  if (M > 40 || hop < 40 || (win - hop) % 2 != 0) return GOLF_ERR_UNSUPPORTED;
+  p->ex = ex, p->ex_stride = ex_stride, p->gain = gain, p->coef = a, p->window = window;
+  p->B = B, p->F = F, p->M = M, p->hop = hop, p->win = win, p->interp_gain = 0;
+  return fill_geometry(p, T_ex, (win - hop) / 2);
+}
+
+GOLF_API int golf_lpc_frames_out_length(int T_ex, int F, int hop, int win) {
+  FfParams p{};
+  p.B = 1, p.F = F, p.hop = hop, p.win = win, p.interp_gain = 0;
+  if (T_ex <= 0 || F <= 0 || hop <= 0 || win < hop || (win - hop) % 2 != 0) return 0;
+  if (fill_geometry(&p, T_ex, (win - hop) / 2)) return 0;
+  return p.out_len;
+}
+
+GOLF_API int golf_lpc_frames_fwd(const float* ex, int64_t ex_stride, const float* gain, const float* a, const float* window,
+                                 float* y, int B, int T_ex, int F, int M, int hop, int win, void* stream) {
+  if (!y) return GOLF_ERR_INVALID;
+  FfParams p{};
+  int rc = frames_params(&p, ex, ex_stride, gain, a, window, B, T_ex, F, M, hop, win);
+  if (rc) return rc;
+  p.y = y;
+  return dispatch_ff_fwd<false>(M, p, (cudaStream_t)stream);
+}
+
+GOLF_API size_t golf_lpc_frames_bwd_workspace_bytes(int B, int T_ex, int F, int hop, int win) {
+  FfParams p{};
+  p.B = B, p.F = F, p.hop = hop, p.win = win, p.interp_gain = 0;
+  if (B <= 0 || T_ex <= 0 || F <= 0 || hop <= 0 || win < 2 * hop || (win - hop) % 2 != 0) return 0;
+  if (fill_geometry(&p, T_ex, (win - hop) / 2)) return 0;
+  return align_up((size_t)B * p.n_frames * win * 4, 256) + align_up((size_t)B * p.out_len * 4, 256);
+}
+
+GOLF_API int golf_lpc_frames_bwd(const float* gy, const float* ex, int64_t ex_stride, const float* gain, const float* a,
+                                 const float* window, float* d_ex, float* d_gain, float* d_a, int B, int T_ex, int F, int M,
+                                 int hop, int win, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!gy || !d_ex) return GOLF_ERR_INVALID;
+  FfParams pf{};
+  int rc = frames_params(&pf, ex, ex_stride, gain, a, window, B, T_ex, F, M, hop, win);
+  if (rc) return rc;
+  const size_t need = golf_lpc_frames_bwd_workspace_bytes(B, T_ex, F, hop, win);
+  if (!workspace || workspace_bytes < need) return GOLF_ERR_WORKSPACE;
+  const int mp = ff_padded_order(M);
+  if (win % mp != 0 || hop % mp != 0) return GOLF_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = reinterpret_cast<char*>(workspace);
+  pf.vws = reinterpret_cast<float*>(ws);
+  pf.y = reinterpret_cast<float*>(ws + align_up((size_t)B * pf.n_frames * win * 4, 256));
+  // frames beyond n_frames receive no gradient
+  if (d_gain) GOLF_CUDA(cudaMemsetAsync(d_gain, 0, (size_t)B * F * sizeof(float), st));
+  if (d_a) GOLF_CUDA(cudaMemsetAsync(d_a, 0, (size_t)B * F * M * sizeof(float), st));
+  FfParams pb = pf;
+  pb.ex = gy, pb.ex_stride = pf.out_len, pb.y = d_ex, pb.d_a = d_a, pb.d_gain = d_gain;
+  pb.vws_ex = ex, pb.ex_stride2 = ex_stride;
+  pb.nseg = (pf.pad + pf.Le - 1) / hop - pf.nseg0 + 1;  // d_ex over every input position [0, T_ex)
+  pb.ctas_per_seq = ceil_div(pb.nseg, 33 - pf.NQ);
+  return dispatch_ff_bwd<true>(mp, pf, pb, st);
 }
 
 GOLF_API int golf_biquad_ff_fwd(const float* ex, int64_t ex_stride, const float* gain, const float* biquads,
