@@ -10,7 +10,7 @@ from ctypes import c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("GOLF_B200_SO") or os.path.join(_HERE, "_lib", "libgolf_b200.so")  # env: A/B builds (tools/)
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 _lib = None
 
 P = c_void_p
@@ -35,6 +35,18 @@ _SIGS = {
     "golf_lpc_ff_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
     "golf_lpc_ff_bwd": (c_int, [P, P, c_int64, P, P, P, P, c_int64, P, P] + [c_int] * 6 + [P, c_size_t, P]),
     "golf_biquad_ff_fwd": (c_int, [P, c_int64, P, P, P, P] + [c_int] * 6 + [P]),
+    "golf_biquad_cascade_fwd": (c_int, [P, c_int64, P, P, P, P] + [c_int] * 6 + [P]),
+    "golf_biquad_cascade_bwd_workspace_bytes": (c_size_t, [c_int] * 6),
+    "golf_biquad_cascade_bwd": (c_int, [P, P, c_int64, P, P, P, P, P, P] + [c_int] * 6 + [P, c_size_t, P]),
+    "golf_lpc_frames_out_length": (c_int, [c_int] * 4),
+    "golf_lpc_frames_fwd": (c_int, [P, c_int64, P, P, P, P] + [c_int] * 6 + [P]),
+    "golf_lpc_frames_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
+    "golf_lpc_frames_bwd": (c_int, [P, P, c_int64, P, P, P, P, P, P] + [c_int] * 6 + [P, c_size_t, P]),
+    "golf_lfilter_allpole_fwd": (c_int, [P, c_int64, P, P, P, c_int, c_int, c_int, P]),
+    "golf_lfilter_allpole_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "golf_lfilter_allpole_bwd": (c_int, [P, P, c_int64, P, P, P, P, P, P, c_int, c_int, c_int, P, c_size_t, P]),
+    "golf_biquad_params_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P]),
+    "golf_biquad_params_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_float, P]),
     "golf_lpc_inverse_fwd": (c_int, [P, c_int64, P, P] + [c_int] * 5 + [P]),
     "golf_lpc_inverse_bwd": (c_int, [P, P, c_int64, P, P, P] + [c_int] * 5 + [P]),
     "golf_noise_fir_fwd": (c_int, [P, c_int64, P, P, P, c_int64, P] + [c_int] * 5 + [P]),

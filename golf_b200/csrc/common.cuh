@@ -56,12 +56,17 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: launch sites keep one bit per device ordinal in a
 // static mask (one process per GPU is the supported mode, but a process that drives several must not trip here)
+// Read-only test: the caller sets the attributes, then calls mark_used_on_device() once ALL of them succeeded, so a
+// failed cudaFuncSetAttribute is retried by the next call instead of leaving the bit set (atomic: host threads may race).
 static inline bool first_use_on_device(unsigned long long& mask) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
-  if ((mask >> dev) & 1ull) return false;
-  mask |= 1ull << dev;
-  return true;
+  return ((__atomic_load_n(&mask, __ATOMIC_ACQUIRE) >> dev) & 1ull) == 0;
+}
+static inline void mark_used_on_device(unsigned long long& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return;
+  __atomic_fetch_or(&mask, 1ull << dev, __ATOMIC_RELEASE);
 }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -272,6 +272,7 @@ GOLF_API int golf_noise_fir_design_fwd(const float* ex, int64_t ex_stride, const
     const size_t sm_max = ((size_t)2 * align_up((size_t)xs_max + 1, 32) + (size_t)kDFB * 2 * kDK20 + (size_t)kDFB * kDN) * sizeof(float);
     GOLF_CUDA(cudaFuncSetAttribute(noise_fir_design_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_max));
     GOLF_CUDA(cudaFuncSetAttribute(noise_fir_design_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_max));
+    mark_used_on_device(attr);
   }
   const dim3 grid(ceil_div(n_blocks, kDFB), B);
   if (ex)

@@ -904,6 +904,7 @@ int launch_response(const SsParams& p, cudaStream_t st) {
   static unsigned long long attr = 0;
   if (sm > 48 * 1024 && first_use_on_device(attr)) {
     GOLF_CUDA(cudaFuncSetAttribute(ss_response_kernel<MP, MT, FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    mark_used_on_device(attr);
   }
   ss_response_kernel<MP, MT, FORM><<<ceil_div(p.B * wps, WPB), 32 * WPB, sm, st>>>(p);
   GOLF_CHECK_LAUNCH();
@@ -949,6 +950,7 @@ int launch_mp(const SsParams& p, bool generic, int passes, cudaStream_t st) {
     GOLF_CUDA(cudaFuncSetAttribute(ss_stitch_kernel<MP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stitch));
     GOLF_CUDA(cudaFuncSetAttribute(ss_stitch_kernel<MP, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stitch));
     if (MCS) GOLF_CUDA(cudaFuncSetAttribute(ss_stitch_kernel<MP, (MCS ? MCS : MP)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stitch));
+    mark_used_on_device(attr2);
   }
   const int G = ceil_div(p.C, 32);
   const size_t sm_solve = (FORM == 0 ? 1 : 2) * 32 * (MP + 1) * sizeof(float);

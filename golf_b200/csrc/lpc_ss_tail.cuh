@@ -455,6 +455,7 @@ int launch_tail(const SsParams& p, int passes, cudaStream_t st) {
   static unsigned long long attr = 0;
   if (first_use_on_device(attr)) {
     GOLF_CUDA(cudaFuncSetAttribute(ss_tail_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    mark_used_on_device(attr);
   }
   ss_tail_kernel<MP><<<p.B * kTailCtas, 32 * kTailWarps, sm, st>>>(p, passes);
   GOLF_CHECK_LAUNCH();

@@ -847,6 +847,7 @@ static int glottal_osc_fwd(const float* phase, const float* w, const float* tabl
       GOLF_CUDA(cudaFuncSetAttribute(osc_flow_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       GOLF_CUDA(cudaFuncSetAttribute(osc_flow_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       GOLF_CUDA(cudaFuncSetAttribute(osc_flow_v2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      mark_used_on_device(attr);
     }
     switch (os) {
       case 1: GOLF_CUDA(launch_pdl(osc_flow_v2_kernel<1>, grid, dim3(128), sm2, st, p, w, table, n_tab)); break;
@@ -929,6 +930,7 @@ GOLF_API int golf_glottal_osc_bwd_w(const float* gout, const float* phase, const
       GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      mark_used_on_device(attr);
     }
     switch (os) {
       case 1: osc_dw_v2_kernel<1><<<grid, 128, smv2, st>>>(q); break;

@@ -51,7 +51,14 @@ class LTVFilterInterface(FilterInterface):
 def _logits2lpc(kind: str, max_abs: float):
     if kind in ("coef", "conj", "real"):
         to_bq = get_logits2biquads(kind, max_abs)
-        return lambda lg: biquads2lpc(to_bq(lg.view(lg.shape[0], lg.shape[1], -1, 2))), 0
+
+        def fn_bq(lg):  # one CUDA launch each way (golf_biquad_params_fwd / _bwd) where it applies, else the torch product
+            sections = lg.view(lg.shape[0], lg.shape[1], -1, 2)
+            if lg.is_cuda and lg.dtype == torch.float32 and sections.shape[2] <= 16:
+                return G.logits2lpc(sections, kind, max_abs)
+            return biquads2lpc(to_bq(sections))
+
+        return fn_bq, 0
     if kind == "rc2lpc":
 
         def fn(lg):  # one CUDA launch (golf_rc2lpc_fwd / _bwd) where it applies, else the torch recursion
@@ -114,6 +121,25 @@ def _reverse(ex, y, gain, a):
     return ex * gain, like(y, resid, hop_of(y))
 
 
+def _check_ff_geometry(hop: int, W: int, M: int, needs_grad: bool) -> None:
+    """What the GOLF-ff kernels are built for (golf_lpc_ff_fwd / _bwd), checked where the module is called so that an
+    unsupported configuration fails in forward() with its reason -- not as UNSUPPORTED from the first backward()."""
+    why = None
+    if M > 40:
+        why = f"LPC order {M} > 40"
+    elif hop < 40:
+        why = f"hop {hop} < 40"
+    elif W % hop != 0 or not 2 <= W // hop <= 8:
+        why = f"window_length {W} must be 2..8 times the hop {hop}"
+    elif needs_grad:
+        mp = next(m for m in (4, 8, 12, 16, 20, 24, 32, 40) if M <= m)
+        if W % mp != 0 or hop % mp != 0:
+            why = (f"training needs window_length {W} and hop {hop} to be multiples of the padded order {mp} (order {M}); "
+                   "inference (torch.no_grad) works")
+    if why is not None:
+        raise GolfError(f"LTVMinimumPhaseFilter: {why}; use LTVMinimumPhaseFilterPrecise (any hop, order <= 40) or the reference module")
+
+
 class LTVMinimumPhaseFilter(LTVMinimumPhaseFilterPrecise):
     """Frame-wise variant: windows of `window_length` every hop, per-frame LTI all-pole from
     zero state, windowed overlap-add, normalised (golf_lpc_ff_fwd).  The reference keeps a
@@ -131,6 +157,7 @@ class LTVMinimumPhaseFilter(LTVMinimumPhaseFilterPrecise):
         hop = hop_of(gain) // hop_of(ex)
         W = self._window.shape[0]
         assert W >= hop * 2, f"{W} < {hop * 2}"
+        _check_ff_geometry(hop, W, c.shape[-1], torch.is_grad_enabled() and any(t.requires_grad for t in (x, g, c)))
         if not self.centred:
             x = x[..., hop // 2 :]
         y = G.lpc_ff(x, g, c, self._window, hop)

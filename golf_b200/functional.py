@@ -5,6 +5,9 @@ Functional twins of what the reference's hot path calls:
   lpc_ss(ex, gain, a, hop)        LTVMinimumPhaseFilterPrecise    (models/filters.py:99-113)
   lpc_ff(ex, gain, a, hop, win)   LTVMinimumPhaseFilter           (models/filters.py:131-184)
   biquad_ff(...)                  BatchSecondOrderLPCSynth        (models/lpc.py:94-131)
+  lpc_frames(...)                 LPCSynth / BatchLPCSynth        (models/lpc.py:19-91)
+  lpc_synthesis(x, gains, a)      lpc_synthesis -> lfilter        (models/lpc.py:11-16)
+  logits2biquads / logits2lpc     get_logits2biquads, biquads2lpc (models/utils.py:444-525)
   lpc_inverse(y, a, hop)          reverse()/fir_filt              (models/filters.py:186-195)
   ltv_fir_blocks(ex, kernel, hop) LTVZeroPhaseFIRFilter           (models/filters.py:360-384)
   room_fir(x, k)                  LTIAcousticFilter               (models/filters.py:443-450)
@@ -311,7 +314,7 @@ def lpc_ff(ex, gain, a, window, hop: int) -> torch.Tensor:
     return _LpcFF.apply(ex, gain, a, window, int(hop))
 
 
-def biquad_ff(ex, gain, biquads, window, hop: int) -> torch.Tensor:
+def _biquad_ff_fwd(ex, gain, biquads, window, hop: int) -> torch.Tensor:
     ex = _rows(ex, "ex")
     gain, biquads, window = _cuda_f32(gain, "gain"), _cuda_f32(biquads, "biquads"), _cuda_f32(window, "window")
     B, Tex = ex.shape
@@ -323,10 +326,210 @@ def biquad_ff(ex, gain, biquads, window, hop: int) -> torch.Tensor:
         raise AssertionError(f"{n_frames} frames but only {Fr} control frames")  # lpc.py:102-104
     y = torch.empty(B, (n_frames - 1) * hop + win - 2 * pad, dtype=torch.float32, device=ex.device)
     with _on(ex.device):
-        rc = _lib.lib().golf_biquad_ff_fwd(_ptr(ex), ex.stride(0), _ptr(gain), _ptr(biquads), _ptr(window), _ptr(y), B, Tex,
-                                           Fr, K, hop, win, _stream())
-    check(rc, "golf_biquad_ff_fwd")
+        rc = _lib.lib().golf_biquad_cascade_fwd(_ptr(ex), ex.stride(0), _ptr(gain), _ptr(biquads), _ptr(window), _ptr(y), B, Tex,
+                                                Fr, K, hop, win, _stream())
+    check(rc, "golf_biquad_cascade_fwd")
     return y
+
+
+class _BiquadFF(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ex, gain, biquads, window, hop):
+        y = _biquad_ff_fwd(ex, gain, biquads, window, hop)
+        ctx.save_for_backward(ex, gain, biquads, window)
+        ctx.hop = hop
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        ex, gain, biquads, window = ctx.saved_tensors
+        gy = _cuda_f32(gy, "gy")
+        exr = _rows(ex, "ex")
+        gain_c, bq_c, win_c = _cuda_f32(gain, "gain"), _cuda_f32(biquads, "biquads"), _cuda_f32(window, "window")
+        B, Tex = exr.shape
+        Fr, K = bq_c.shape[1], bq_c.shape[2]
+        win, hop = win_c.numel(), ctx.hop
+        need, dev = ctx.needs_input_grad, gy.device
+        d_ex = torch.empty(B, Tex, dtype=torch.float32, device=dev)
+        d_gain = torch.empty(B, Fr, dtype=torch.float32, device=dev) if need[1] else None
+        d_bq = torch.empty(B, Fr, K, 3, dtype=torch.float32, device=dev) if need[2] else None
+        lib = _lib.lib()
+        ws = _workspace(lib.golf_biquad_cascade_bwd_workspace_bytes(B, Tex, Fr, K, hop, win), dev)
+        with _on(dev):
+            rc = lib.golf_biquad_cascade_bwd(_ptr(gy), _ptr(exr), exr.stride(0), _ptr(gain_c), _ptr(bq_c), _ptr(win_c), _ptr(d_ex),
+                                             _ptr(d_gain), _ptr(d_bq), B, Tex, Fr, K, hop, win, _ptr(ws), ws.numel(), _stream())
+        check(rc, "golf_biquad_cascade_bwd")
+        return (d_ex if need[0] else None), d_gain, d_bq, None, None
+
+
+def biquad_ff(ex, gain, biquads, window, hop: int) -> torch.Tensor:
+    """BatchSecondOrderLPCSynth.forward (models/lpc.py:94-131): ex [B,T], gain [B,F], biquads [B,F,K,3], window [win].
+    Differentiable in ex, gain and the sections (golf_biquad_cascade_fwd / _bwd)."""
+    return _BiquadFF.apply(ex, gain, biquads, window, int(hop))
+
+
+# ------------------------------------------------- LPCSynth / BatchLPCSynth (models/lpc.py:19-91)
+def _lpc_frames_fwd(ex, gain, a, window, hop: int) -> torch.Tensor:
+    ex = _rows(ex, "ex")
+    gain, a, window = _cuda_f32(gain, "gain"), _cuda_f32(a, "a"), _cuda_f32(window, "window")
+    B, Tex = ex.shape
+    Fr, M = a.shape[1], a.shape[2]
+    win = window.numel()
+    pad = (win - hop) // 2
+    n_frames = (Tex + 2 * pad - win) // hop + 1
+    if n_frames > Fr:
+        raise AssertionError(f"{n_frames} frames but only {Fr} control frames")  # lpc.py:71
+    lib = _lib.lib()
+    out_len = lib.golf_lpc_frames_out_length(Tex, Fr, hop, win)
+    if out_len <= 0:
+        raise GolfError(f"lpc_frames: unsupported geometry T={Tex} F={Fr} hop={hop} win={win}")
+    y = torch.empty(B, out_len, dtype=torch.float32, device=ex.device)
+    with _on(ex.device):
+        rc = lib.golf_lpc_frames_fwd(_ptr(ex), ex.stride(0), _ptr(gain), _ptr(a), _ptr(window), _ptr(y), B, Tex, Fr, M, hop, win,
+                                     _stream())
+    check(rc, "golf_lpc_frames_fwd")
+    return y
+
+
+class _LpcFrames(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ex, gain, a, window, hop):
+        y = _lpc_frames_fwd(ex, gain, a, window, hop)
+        ctx.save_for_backward(ex, gain, a, window)
+        ctx.hop = hop
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        ex, gain, a, window = ctx.saved_tensors
+        gy = _cuda_f32(gy, "gy")
+        exr = _rows(ex, "ex")
+        gain_c, a_c, win_c = _cuda_f32(gain, "gain"), _cuda_f32(a, "a"), _cuda_f32(window, "window")
+        B, Tex = exr.shape
+        Fr, M = a_c.shape[1], a_c.shape[2]
+        win, hop = win_c.numel(), ctx.hop
+        need, dev = ctx.needs_input_grad, gy.device
+        d_ex = torch.empty(B, Tex, dtype=torch.float32, device=dev)
+        d_gain = torch.empty(B, Fr, dtype=torch.float32, device=dev) if need[1] else None
+        d_a = torch.empty(B, Fr, M, dtype=torch.float32, device=dev) if need[2] else None
+        lib = _lib.lib()
+        ws = _workspace(lib.golf_lpc_frames_bwd_workspace_bytes(B, Tex, Fr, hop, win), dev)
+        with _on(dev):
+            rc = lib.golf_lpc_frames_bwd(_ptr(gy), _ptr(exr), exr.stride(0), _ptr(gain_c), _ptr(a_c), _ptr(win_c), _ptr(d_ex),
+                                         _ptr(d_gain), _ptr(d_a), B, Tex, Fr, M, hop, win, _ptr(ws), ws.numel(), _stream())
+        check(rc, "golf_lpc_frames_bwd")
+        return (d_ex if need[0] else None), d_gain, d_a, None, None
+
+
+def lpc_frames(ex, gain, a, window, hop: int) -> torch.Tensor:
+    """BatchLPCSynth.forward (models/lpc.py:62-91): per-frame gain and LTI all-pole, zero-pad (win-hop)/2, window OLA."""
+    return _LpcFrames.apply(ex, gain, a, window, int(hop))
+
+
+# ------------------------------------------------- lpc_synthesis (models/lpc.py:11-16), lfilter-shaped
+class _LfilterAllpole(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gains, a):
+        xr = _rows(x, "source")
+        a_c = _cuda_f32(a, "a")
+        g_c = _cuda_f32(gains, "gains") if gains is not None else None
+        C, N = xr.shape
+        if a_c.ndim != 2 or a_c.shape[0] != C or (g_c is not None and g_c.numel() != C):
+            raise GolfError(f"lpc_synthesis: source{tuple(xr.shape)} gains{None if g_c is None else tuple(g_c.shape)} a{tuple(a_c.shape)}")
+        y = torch.empty(C, N, dtype=torch.float32, device=xr.device)
+        with _on(xr.device):
+            rc = _lib.lib().golf_lfilter_allpole_fwd(_ptr(xr), xr.stride(0), _ptr(g_c), _ptr(a_c), _ptr(y), C, N, a_c.shape[1], _stream())
+        check(rc, "golf_lfilter_allpole_fwd")
+        ctx.save_for_backward(x, gains, a, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, gains, a, y = ctx.saved_tensors
+        gy = _cuda_f32(gy, "gy")
+        xr = _rows(x, "source")
+        a_c = _cuda_f32(a, "a")
+        g_c = _cuda_f32(gains, "gains") if gains is not None else None
+        C, N = xr.shape
+        M = a_c.shape[1]
+        need, dev = ctx.needs_input_grad, gy.device
+        d_x = torch.empty(C, N, dtype=torch.float32, device=dev) if need[0] else None
+        d_g = torch.empty(C, dtype=torch.float32, device=dev) if (need[1] and gains is not None) else None
+        d_a = torch.empty(C, M, dtype=torch.float32, device=dev) if need[2] else None
+        lib = _lib.lib()
+        ws = _workspace(lib.golf_lfilter_allpole_bwd_workspace_bytes(C, N), dev)
+        with _on(dev):
+            rc = lib.golf_lfilter_allpole_bwd(_ptr(gy), _ptr(xr), xr.stride(0), _ptr(y), _ptr(g_c), _ptr(a_c), _ptr(d_x), _ptr(d_g),
+                                              _ptr(d_a), C, N, M, _ptr(ws), ws.numel(), _stream())
+        check(rc, "golf_lfilter_allpole_bwd")
+        if d_g is not None:
+            d_g = d_g.view(gains.shape)
+        return d_x, d_g, d_a
+
+
+def lpc_synthesis(source, gains, a) -> torch.Tensor:
+    """models/lpc.py:11-16: `lfilter(source, [1, a], [gains, 0, ...], clamp=False)` for source [C,N], gains [C], a [C,M]:
+    y[c,n] = gains[c] source[c,n] - sum_i a[c,i] y[c,n-1-i] from zero state.  Differentiable in all three."""
+    if source.ndim != 2:
+        raise GolfError(f"lpc_synthesis: source must be [C,N], got {tuple(source.shape)}")
+    return _LfilterAllpole.apply(source, gains, a)
+
+
+# ------------------------------------------------- biquad parameterisations (models/utils.py:444-525)
+_BIQUAD_REPS = {"coef": 0, "conj": 1, "real": 2}
+
+
+class _BiquadParams(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, rep, rho, want_bq, want_a):
+        lg = _cuda_f32(logits, "logits")
+        K = lg.shape[-2]
+        N = lg.numel() // (2 * K)
+        lead = tuple(lg.shape[:-2])
+        bq = torch.empty(*lead, K, 3, dtype=torch.float32, device=lg.device) if want_bq else None
+        a = torch.empty(*lead, 2 * K, dtype=torch.float32, device=lg.device) if want_a else None
+        with _on(lg.device):
+            rc = _lib.lib().golf_biquad_params_fwd(_ptr(lg), _ptr(bq), _ptr(a), N, K, rep, rho, _stream())
+        check(rc, "golf_biquad_params_fwd")
+        ctx.save_for_backward(logits)
+        ctx.cfg = (rep, rho, N, K)
+        ctx.set_materialize_grads(False)
+        outs = tuple(t for t in (bq, a) if t is not None)
+        ctx.slots = (want_bq, want_a)
+        return outs if len(outs) > 1 else outs[0]
+
+    @staticmethod
+    def backward(ctx, *grads):
+        (logits,) = ctx.saved_tensors
+        rep, rho, N, K = ctx.cfg
+        grads = list(grads)
+        d_bq = grads.pop(0) if ctx.slots[0] else None
+        d_a = grads.pop(0) if ctx.slots[1] else None
+        if d_bq is None and d_a is None:
+            return None, None, None, None, None
+        lg = _cuda_f32(logits, "logits")
+        d_bq = _cuda_f32(d_bq, "d_biquads") if d_bq is not None else None
+        d_a = _cuda_f32(d_a, "d_a") if d_a is not None else None
+        d_lg = torch.empty_like(lg)
+        with _on(lg.device):
+            rc = _lib.lib().golf_biquad_params_bwd(_ptr(lg), _ptr(d_bq), _ptr(d_a), _ptr(d_lg), N, K, rep, rho, _stream())
+        check(rc, "golf_biquad_params_bwd")
+        return d_lg, None, None, None, None
+
+
+def logits2biquads(logits, rep_type: str = "coef", max_abs_pole: float = 0.99) -> torch.Tensor:
+    """get_logits2biquads(rep_type, max_abs_pole)(logits) (models/utils.py:487-525): [...,K,2] -> sections [...,K,3]."""
+    if rep_type not in _BIQUAD_REPS:
+        raise ValueError(f"Unknown rep_type: {rep_type}, expected coef, conj or real")
+    return _BiquadParams.apply(logits, _BIQUAD_REPS[rep_type], float(max_abs_pole), True, False)
+
+
+def logits2lpc(logits, rep_type: str = "coef", max_abs_pole: float = 0.99) -> torch.Tensor:
+    """biquads2lpc(get_logits2biquads(...)(logits)) as composed at models/filters.py:73-78: [...,K,2] -> a [...,2K]
+    (one launch each way; the sections never reach HBM)."""
+    if rep_type not in _BIQUAD_REPS:
+        raise ValueError(f"Unknown rep_type: {rep_type}, expected coef, conj or real")
+    return _BiquadParams.apply(logits, _BIQUAD_REPS[rep_type], float(max_abs_pole), False, True)
 
 
 def _lpc_inverse_fwd(y, a, hop: int) -> torch.Tensor:

@@ -94,6 +94,10 @@ class GlottalFlowTable(OscillatorInterface):
         elif normalize_method is not None:
             raise ValueError(f"unknown normalize_method: {normalize_method}")
         if trainable:
+            import warnings
+
+            warnings.warn("golf_b200: GlottalFlowTable(trainable=True) synthesises, but the table gradient is not implemented "
+                          "(backward raises GolfError); shipped GOLF configs use trainable=False", stacklevel=2)
             self.register_parameter("table", nn.Parameter(table))
         else:
             self.register_buffer("table", table)

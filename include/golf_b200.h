@@ -18,6 +18,12 @@
  *   golf_lpc_ff_*            models/filters.py:131-184 LTVMinimumPhaseFilter.forward
  *                            (unfold, models/lpc.py:11-16 lpc_synthesis -> torchaudio lfilter, Hann OLA)
  *   golf_biquad_ff_fwd       models/lpc.py:94-131     BatchSecondOrderLPCSynth.forward
+ *   golf_biquad_cascade_fwd/bwd  the same (SURVEY 8b's names) and its autograd (torchaudio DifferentiableIIR K times + OLA)
+ *   golf_lpc_frames_fwd/bwd  models/lpc.py:19-91      LPCSynth / BatchLPCSynth.forward (per-frame gain, pad (win-hop)/2) + autograd
+ *   golf_lfilter_allpole_fwd/bwd  models/lpc.py:11-16 lpc_synthesis -> torchaudio.functional.lfilter(x, [1,a], [g,0..], clamp=False)
+ *                            and DifferentiableIIR.backward for that b
+ *   golf_biquad_params_fwd/bwd  models/utils.py:487-525 get_logits2biquads (coef|conj|real) + :444-484 biquads2lpc /
+ *                            coeff_product, as composed at models/filters.py:73-78, and their autograd
  *   golf_lpc_inverse_fwd/bwd models/filters.py:186-195 reverse() + models/utils.py:433-441 fir_filt, and its
  *                            autograd (inverse-target training, ltng/vocoder.py:192-198)
  *   golf_noise_fir_*         models/filters.py:350-384 LTVZeroPhaseFIRFilter.forward (block FIR)
@@ -44,7 +50,7 @@
 extern "C" {
 #endif
 
-#define GOLF_B200_ABI_VERSION 5
+#define GOLF_B200_ABI_VERSION 6
 
 enum {
   GOLF_OK = 0,
@@ -145,6 +151,51 @@ int golf_lpc_ff_bwd(const float *gy, const float *ex, int64_t ex_stride, const f
 int golf_biquad_ff_fwd(const float *ex, int64_t ex_stride, const float *gain,
                        const float *biquads, const float *window, float *y, int B, int T_ex,
                        int F, int K, int hop, int win, void *stream);
+
+/* BatchSecondOrderLPCSynth under the name SURVEY 8(b) gives it; identical to golf_biquad_ff_fwd. */
+int golf_biquad_cascade_fwd(const float *ex, int64_t ex_stride, const float *gain,
+                            const float *biquads, const float *window, float *y, int B, int T_ex,
+                            int F, int K, int hop, int win, void *stream);
+/* Adjoint of the cascade for an upstream gradient gy [B,out_len]: d_ex [B,T_ex] (contiguous, required),
+ * d_gain [B,F], d_biquads [B,F,K,3] (either may be NULL; frames beyond n_frames get zeros).  The kernel
+ * recomputes every section's output into the workspace (32*K*win floats per CTA). */
+size_t golf_biquad_cascade_bwd_workspace_bytes(int B, int T_ex, int F, int K, int hop, int win);
+int golf_biquad_cascade_bwd(const float *gy, const float *ex, int64_t ex_stride, const float *gain,
+                            const float *biquads, const float *window, float *d_ex, float *d_gain,
+                            float *d_biquads, int B, int T_ex, int F, int K, int hop, int win,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
+/* LPCSynth / BatchLPCSynth (models/lpc.py:19-91): frames of `win` samples every `hop`, zero-padded by
+ * (win-hop)/2, per-frame LTI all-pole a[b,k,:] on gain[b,k]*frame from zero state, window OLA + normalise.
+ * y [B, out_len], out_len = golf_lpc_frames_out_length(...) (0: invalid geometry). */
+int golf_lpc_frames_out_length(int T_ex, int F, int hop, int win);
+int golf_lpc_frames_fwd(const float *ex, int64_t ex_stride, const float *gain, const float *a,
+                        const float *window, float *y, int B, int T_ex, int F, int M, int hop,
+                        int win, void *stream);
+size_t golf_lpc_frames_bwd_workspace_bytes(int B, int T_ex, int F, int hop, int win);
+int golf_lpc_frames_bwd(const float *gy, const float *ex, int64_t ex_stride, const float *gain,
+                        const float *a, const float *window, float *d_ex, float *d_gain, float *d_a,
+                        int B, int T_ex, int F, int M, int hop, int win, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
+/* lfilter-shaped twin of models/lpc.py:11-16: y[c,n] = gain[c]*x[c,n] - sum_i a[c,i] y[c,n-1-i], zero
+ * initial state; x [C,N] (row stride x_stride), gain [C] or NULL (= 1), a [C,M], y [C,N]. */
+int golf_lfilter_allpole_fwd(const float *x, int64_t x_stride, const float *gain, const float *a,
+                             float *y, int C, int N, int M, void *stream);
+/* Adjoint: gy, y [C,N] -> d_x [C,N], d_gain [C], d_a [C,M] (any may be NULL). */
+size_t golf_lfilter_allpole_bwd_workspace_bytes(int C, int N);
+int golf_lfilter_allpole_bwd(const float *gy, const float *x, int64_t x_stride, const float *y,
+                             const float *gain, const float *a, float *d_x, float *d_gain, float *d_a,
+                             int C, int N, int M, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Biquad parameterisations (rep 0 "coef", 1 "conj", 2 "real"; models/utils.py:487-525) and the polynomial
+ * product of the K sections (models/utils.py:444-484): logits [N,K,2] -> biquads [N,K,3] and / or
+ * a [N,2K] (either may be NULL).  K <= 16. */
+int golf_biquad_params_fwd(const float *logits, float *biquads, float *a, int N, int K, int rep,
+                           float max_abs_pole, void *stream);
+/* d_logits [N,K,2] from d_biquads [N,K,3] and / or d_a [N,2K] (either may be NULL). */
+int golf_biquad_params_bwd(const float *logits, const float *d_biquads, const float *d_a,
+                           float *d_logits, int N, int K, int rep, float max_abs_pole, void *stream);
 
 /* Inverse (analysis) filter: r[t] = y[t] + sum_i up(a)[t,i] y[t-1-i], [B,L]. */
 int golf_lpc_inverse_fwd(const float *y, int64_t y_stride, const float *a, float *r, int B,
