@@ -104,7 +104,7 @@ def install_stubs() -> None:
     if "pyworld" not in sys.modules:
         mod("pyworld", dio=_absent, stonemask=_absent, harvest=_absent)
     if "diffsptk" not in sys.modules:
-        names = ["MLSA", "MelCepstralAnalysis", "MelGeneralizedCepstrumToSpectrum", "PQMF", "IPQMF"]
+        names = ["MLSA", "MelCepstralAnalysis", "MelGeneralizedCepstrumToSpectrum", "PQMF", "IPQMF", "STFT"]
         d = mod("diffsptk", **{n: type(n, (torch.nn.Module,), {}) for n in names})
         d.functional = mod("diffsptk.functional", lsp2lpc=_absent)
     if "torch_fftconv" not in sys.modules:
@@ -116,6 +116,29 @@ def install_stubs() -> None:
         mod("kazane", Decimate=_Decimate)
     if not hasattr(torch, "Any"):  # models/lru/recurrence.py:28 under torch 2.11
         torch.Any = typing.Any
+
+
+def import_harness():
+    """The reference's Lightning-side harness, unmodified: returns (ltng.ae, test_rtf) with `lightning` provided by
+    oracle/lightning_standin.py when the real package is absent."""
+    import importlib
+
+    import_reference()
+    from . import lightning_standin
+
+    try:
+        importlib.import_module("lightning.pytorch")
+    except ImportError:
+        lightning_standin.install()
+    for name, attrs in (("frechet_audio_distance", {"FrechetAudioDistance": object}), ("soundfile", {})):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except ImportError:
+                m = types.ModuleType(name)
+                m.__dict__.update(attrs)
+                sys.modules[name] = m
+    return importlib.import_module("ltng.ae"), importlib.import_module("test_rtf")
 
 
 def import_reference():
