@@ -153,6 +153,7 @@ __global__ void ss_dzi_kernel(const float* __restrict__ u, const float* __restri
 static float g_refine_tol = 1e-4f;
 int g_solve_systolic = 1;
 int g_ss_tail = 0;
+int g_ss_response_mode = 0;
 
 struct SsPlan {
   int B, MP, Lc, C, HB;
@@ -224,7 +225,9 @@ static void plan_pointers(const SsPlan& pl, void* workspace, SsParams* p) {
   p->Dg = reinterpret_cast<float*>(take(plan_gstate_floats(pl) * 4));
   tail_groups(pl.C, &p->NG, &p->G);
   p->room_k = nullptr, p->room_out = nullptr, p->room_n = 0;
-  p->refine_tol = g_refine_tol;
+  // the tensor-core response kernel's transition matrices are ~10x less accurate than the FP32 kernel's (truncating
+  // accumulation): with it the refinement round is not optional
+  p->refine_tol = (g_ss_response_mode == 1 && pl.MP == 24) ? 0.f : g_refine_tol;
 }
 
 
@@ -311,6 +314,9 @@ GOLF_API int golf_lpc_ss_fwd(const float* ex, int64_t ex_stride, const float* ga
                              size_t workspace_bytes, void* stream) {
   return golf_lpc_ss_fwd_passes(ex, ex_stride, gain, a, zi, y, B, L, F, M, hop, chunk, workspace, workspace_bytes, 15, stream);
 }
+
+GOLF_API void golf_lpc_ss_set_response(int mode) { g_ss_response_mode = mode == 1 ? 1 : 0; }
+GOLF_API int golf_lpc_ss_get_response(void) { return g_ss_response_mode; }
 
 GOLF_API void golf_lpc_ss_set_tail(int mode) { g_ss_tail = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 

@@ -890,10 +890,14 @@ __global__ void __launch_bounds__(32) ss_solve_sys_kernel(SsParams p, int round)
 
 }  // namespace golf
 #include "lpc_ss_tail.cuh"
+#include "lpc_ss_tc.cuh"
 namespace golf {
 
 template <int MP, int MT, int FORM>
 int launch_response(const SsParams& p, cudaStream_t st) {
+  if constexpr (MP == 24 && FORM == 0) {
+    if (response_tc_applies(p, MP, FORM)) return launch_response_tc(p, st);
+  }
   constexpr int NC = RespCfg<MP>::NC;
   constexpr int LPC = (MT + 1 + NC - 1) / NC, CPW = 32 / LPC;
   const int nresp = p.C - 1;

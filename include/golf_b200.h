@@ -111,6 +111,12 @@ int golf_lpc_ss_fwd_passes(const float *ex, int64_t ex_stride, const float *gain
  * (measured, profiles/README.md).  Same recurrences, different grouping of the state propagation (results agree to
  * float32 rounding).  Process-wide. */
 void golf_lpc_ss_set_tail(int mode);
+/* Pass 1 (chunk responses) at padded order 24 (orders 21..24, chunk a multiple of 8 samples, forward form): mode 0
+ * (default) the FP32 kernel, 1 the mma.sync TF32 tensor-core kernel with error-compensated (3 x TF32) products.  An opt-in
+ * experiment: on B200 it is slower (83 vs 74 us at B = 32 x 2 s) and its transition matrices are ~10x less accurate, so the
+ * refinement round runs for most sequences.  Other shapes and the adjoint always use the FP32 kernel. */
+void golf_lpc_ss_set_response(int mode);
+int golf_lpc_ss_get_response(void);
 /* GOLF-ss end filter + the room filter behind it (models/sf.py:64: room_filter(end_filter(src, gain, a)) with
  * models/filters.py:99-113 and :443-450) in the same launches: out[t] = y[t] + sum_{j<room_n} room_k[j] y[t-room_n+j],
  * y = golf_lpc_ss_fwd(ex, gain, a, zi).  y may be NULL (the filter output then lives in the workspace only; pass a
