@@ -10,7 +10,7 @@ from ctypes import c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("GOLF_B200_SO") or os.path.join(_HERE, "_lib", "libgolf_b200.so")  # env: A/B builds (tools/)
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 _lib = None
 
 P = c_void_p
@@ -49,6 +49,11 @@ _SIGS = {
     "golf_lfilter_allpole_bwd": (c_int, [P, P, c_int64, P, P, P, P, P, P, c_int, c_int, c_int, P, c_size_t, P]),
     "golf_biquad_params_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P]),
     "golf_biquad_params_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_float, P]),
+    "golf_mss_tables_bytes": (c_size_t, [c_int]),
+    "golf_mss_build_tables": (c_int, [c_int, P, P]),
+    "golf_mss_workspace_bytes": (c_size_t, [c_int, c_int, P, P, c_int]),
+    "golf_mss_loss": (c_int, [P, c_int64, P, c_int64, c_int, c_int, P, P, c_int, P, c_float, c_float, c_float, P, P, c_int64, c_int, P, c_size_t, P]),
+    "golf_mss_gemm": (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int, c_int, c_int, P]),
     "golf_lpc_inverse_fwd": (c_int, [P, c_int64, P, P] + [c_int] * 5 + [P]),
     "golf_lpc_inverse_bwd": (c_int, [P, P, c_int64, P, P, P] + [c_int] * 5 + [P]),
     "golf_noise_fir_fwd": (c_int, [P, c_int64, P, P, P, c_int64, P] + [c_int] * 5 + [P]),

@@ -36,6 +36,8 @@
  *   golf_wavetable_read_fwd  models/synth.py:124-177   GlottalFlowTable.generate
  *   golf_linear_upsample     models/audiotensor/audiotensor.py:11-17 linear_upsample
  *   golf_rc2lpc_fwd/bwd      models/utils.py:581-593   rc2lpc (with the tanh*max_abs of filters.py:80) and its autograd
+ *   golf_mss_*               loss/spec.py:11-67 SSSLoss / MSSLoss (torchaudio Spectrogram power=1 -> L1 + alpha log2-L1) and its
+ *                            autograd w.r.t. the prediction: the training-step consumer of the decoder output (ltng/ae.py:119-121)
  *   golf_exp_to_complex      models/filters.py:295-296 `torch.exp(log_mag) + 0j` of get_zero_phase_fir
  *   (golf_set_pdl, golf_fir_set_variant, golf_lpc_ss_set_*, golf_glottal_osc_set_variant: process-wide kernel
  *    selection switches for A/B timing and tests; no reference counterpart)
@@ -50,7 +52,7 @@
 extern "C" {
 #endif
 
-#define GOLF_B200_ABI_VERSION 6
+#define GOLF_B200_ABI_VERSION 7
 
 enum {
   GOLF_OK = 0,
@@ -211,6 +213,27 @@ int golf_lpc_inverse_fwd(const float *y, int64_t y_stride, const float *a, float
  * an inverse-filtered target (ltng/vocoder.py:192-198). */
 int golf_lpc_inverse_bwd(const float *g, const float *y, int64_t y_stride, const float *a, float *d_y,
                          float *d_a, int B, int L, int F, int M, int hop, void *stream);
+
+/* ------------------------------------------------- multi-scale spectral loss ---- */
+/* loss/spec.py:11-67 with torchaudio's Spectrogram defaults (centre / reflect padding, periodic Hann of n_fft, hop =
+ * n_fft - int(0.75 n_fft), onesided, power 1):  loss = ratio * sum_scales ( mean|Sp - St| + alpha mean|log2(St + eps) -
+ * log2(Sp + eps)| ).  The STFTs are DFT-as-GEMM on the tcgen05 tensor cores (the shipped sizes 509 / 1021 / 2053 are primes),
+ * prec3 != 0: error-compensated 3 x TF32 products (float32-grade).  tables[i]: the DFT bases of n_ffts[i], built once by
+ * golf_mss_build_tables into golf_mss_tables_bytes(n_fft) bytes.  loss: one float on the device.  d_pred (optional, [B, L]
+ * with row stride dpred_stride): d loss / d pred.  pred, target [B, L].  hops: one hop per scale, or NULL for the 75 % overlap
+ * of the shipped config.  At most 8 scales, n_fft <= 4096, L > n_fft / 2. */
+size_t golf_mss_tables_bytes(int n_fft);
+int golf_mss_build_tables(int n_fft, float *tables, void *stream);
+size_t golf_mss_workspace_bytes(int B, int L, const int *n_ffts, const int *hops, int n_scales);
+int golf_mss_loss(const float *pred, int64_t pred_stride, const float *target, int64_t target_stride, int B,
+                  int L, const int *n_ffts, const int *hops, int n_scales, const float *const *tables, float alpha,
+                  float ratio,
+                  float eps, float *loss, float *d_pred, int64_t dpred_stride, int prec3, void *workspace,
+                  size_t workspace_bytes, void *stream);
+/* The GEMM underneath (D [M,N] = A [M,K] . Bt [N,K]^T, float32 in and out, row pitches in floats and multiples of 4, bn =
+ * N tile: a multiple of 16 up to 256): TMA-staged operands, tcgen05.mma kind::tf32, accumulator in TMEM. */
+int golf_mss_gemm(const float *A, int64_t pitchA, const float *Bt, int64_t pitchB, float *D, int64_t pitchD, int M,
+                  int N, int K, int bn, int prec3, void *stream);
 
 /* -------------------------------------------------------------- FIR stages ---- */
 /* Block-wise time-varying FIR: output block k (hop samples) is the valid
