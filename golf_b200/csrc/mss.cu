@@ -12,9 +12,9 @@
 //                       shared-memory ring, tcgen05.mma.kind::tf32 issued by one thread, accumulator in TMEM, read back with
 //                       tcgen05.ld by four epilogue warps.  Warp roles: 0 TMA producer, 1 MMA issuer (+ TMEM allocation),
 //                       2..5 splitter during the main loop, epilogue afterwards.
-//                       Float32-grade products (the log-magnitude term reads bins 60 dB below a frame's peak): the tensor core
-//                       reads the top 19 bits of an fp32 operand (hi); the splitter warps write lo = x - hi (exact) into a
-//                       second pair of tiles in the SAME swizzled layout, and every k-step issues hi*hi + lo*hi + hi*lo.
+//                       Float32-grade products (the log-magnitude term reads bins 60 dB below a frame's peak): the splitter
+//                       warps round every operand to TF32 in place (hi) and write lo = x - hi (exact) into a second pair of
+//                       tiles in the SAME swizzled layout; every k-step issues hi*hi + lo*hi + hi*lo.
 //                       Epilogues: magnitudes of the target (mode 0); loss terms + d loss / d(re, im) for the prediction
 //                       (mode 1: the two signals' spectra never exist in HBM as complex tensors); plain store (mode 2, adjoint).
 //   mss_ola_kernel      adjoint of framing + window + reflect padding: gather, no atomics
@@ -32,18 +32,23 @@ constexpr int kMssMaxScales = 8;
 constexpr int kGemmThreads = 320;
 constexpr int kBM = 128;          // rows per tile (TMEM lanes)
 constexpr int kBK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int kMaxBN = 256;
-constexpr int kStages = 2;
+constexpr int kMaxBN = 128;       // TMEM columns per accumulator and rows of a B tile in shared memory
+constexpr int kAccCols = 128;     // columns per tile actually used: one float32 REGISTER accumulator per column and epilogue thread
+constexpr int kStages = 3;
+constexpr int kAccBufs = 4;       // TMEM accumulators (kMaxBN columns each): the tensor cores may run this many chunks ahead
 constexpr int kTileA = kBM * kBK * 4;        // 16 KB
-constexpr int kTileB = kMaxBN * kBK * 4;     // 32 KB
+constexpr int kTileB = kMaxBN * kBK * 4;     // 16 KB
 constexpr int kStageBytes = 2 * kTileA + 2 * kTileB;  // A | A_lo | B | B_lo
-constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int kSst = kMaxBN / 2 + 1;         // row stride of the staged target magnitudes (conflict-free column reads)
+constexpr int kSstBytes = kBM * kSst * 4;
+constexpr int kGemmSmem = kStages * kStageBytes + kSstBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 struct MssGemmParams {
   int M, N, K;          // D [M x N] = A [M x K] . Bt[N x K]^T
   int bn;               // N tile (multiple of 16, <= 256)
   int mode;             // 0: magnitudes -> out [M, N/2]; 1: loss + gradient -> out [M, N] (needs s_true); 2: plain store
   int prec3;            // error-compensated products
+  int chunk_kb;         // k-blocks summed inside the tensor core before the sum moves to float32 registers
   float* out;
   int64_t out_pitch;
   const float* s_true;  // [M, N/2]
@@ -77,6 +82,15 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -104,27 +118,37 @@ __host__ __device__ inline uint32_t umma_idesc_tf32(int m, int n) {
 }
 
 // ---- the GEMM -------------------------------------------------------------------------------------------------------
-// Persistent: CTA c works on tiles c, c + gridDim.x, ... (n fastest, so CTAs of a wave share A row blocks in L2).  Two TMEM
-// accumulators (2 x 256 columns): the epilogue warps drain tile i while the tensor cores already run tile i + 1.
+// Persistent: CTA c works on tiles c, c + gridDim.x, ... (n fastest, so the CTAs of a wave share A row blocks in L2).
+//
+// Accumulation.  The tensor core adds products into its fp32 accumulator with TRUNCATION; over the 770 MMA steps of a
+// K = 2053 product the bias reaches 2e-5 of the largest partial sum, which is fatal for this loss: the partial sums of a
+// spectral valley next to a strong harmonic are as large as the harmonic until the window closes, and the log-magnitude term
+// (and its 1/S gradient) reads exactly those valleys.  So TMEM only ever holds the sum of a few k-blocks (p.chunk_kb = 4: K = 128, 48
+// MMAs): four 128-column accumulators rotate, and the epilogue warps add each finished chunk into float32 REGISTERS
+// (round-to-nearest, one row of <= 128 columns per thread) while the tensor cores run the next chunk.  Measured: gradient
+// error in -60 dB valleys from 1e-1 to the level of torch's own float32 cuFFT path.
 //   warp 0      TMA producer            full[s]  <- TMA bytes          (waits empty[s])
 //   warp 1      MMA issuer, TMEM alloc  empty[s] <- tcgen05.commit     (waits ready[s] | full[s], tempty[b]);  tfull[b] <- commit
 //   warps 2..5  splitter (prec3)        ready[s] <- 128 arrivals       (waits full[s])
-//   warps 6..9  epilogue                tempty[b] <- 128 arrivals      (waits tfull[b])
+//   warps 6..9  accumulate + epilogue   tempty[b] <- 128 arrivals      (waits tfull[b])
+template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     mss_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, MssGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + kStages * kStageBytes);
+  float* sst = reinterpret_cast<float*>(tiles + kStages * kStageBytes);  // [128][kSst] target magnitudes of the tile (mode 1)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + kStages * kStageBytes + kSstBytes);
   uint64_t* full = bars;                 // [kStages]
   uint64_t* ready = bars + kStages;      // [kStages]
   uint64_t* empty = bars + 2 * kStages;  // [kStages]
-  uint64_t* tfull = bars + 3 * kStages;  // [2]
-  uint64_t* tempty = bars + 3 * kStages + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 4);
+  uint64_t* tfull = bars + 3 * kStages;  // [kAccBufs]
+  uint64_t* tempty = bars + 3 * kStages + kAccBufs;  // [kAccBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 2 * kAccBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.K + kBK - 1) / kBK;
+  const int nch = (nkb + p.chunk_kb - 1) / p.chunk_kb;
   const int tiles_n = (p.N + p.bn - 1) / p.bn, tiles_m = (p.M + kBM - 1) / kBM;
   const int n_tiles = tiles_n * tiles_m;
   const uint32_t stage_tx = (uint32_t)(kBM * kBK * 4 + p.bn * kBK * 4);
@@ -135,14 +159,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       mbar_init(ready + s, 128);
       mbar_init(empty + s, 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kAccBufs; ++b) {
       mbar_init(tfull + b, 1);
       mbar_init(tempty + b, 128);
     }
     mbar_fence_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kAccBufs * kMaxBN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -170,33 +194,37 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     // ===== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(kBM, p.bn);
-      int it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-        const int buf = ti & 1;
-        if (ti >= 2) {
-          mbar_wait(tempty + buf, ((ti >> 1) - 1) & 1);  // the epilogue has drained this accumulator
-          tc_fence_after();
-        }
-        const uint32_t acc = tmem + (uint32_t)(buf * kMaxBN);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % kStages;
-          mbar_wait(p.prec3 ? ready + s : full + s, (it / kStages) & 1);
-          tc_fence_after();
-          const uint32_t sa = base + s * kStageBytes;
-          const uint64_t da = umma_desc(sa), dal = umma_desc(sa + kTileA), db = umma_desc(sa + 2 * kTileA),
-                         dbl = umma_desc(sa + 2 * kTileA + kTileB);
-#pragma unroll
-          for (int k = 0; k < kBK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes: +2 in the (>> 4) start-address field
-            const uint64_t o = (uint64_t)(2 * k);
-            tc_mma_tf32(acc, da + o, db + o, idesc, (kb | k) ? 1u : 0u);
-            if (p.prec3) {
-              tc_mma_tf32(acc, dal + o, db + o, idesc, 1u);
-              tc_mma_tf32(acc, da + o, dbl + o, idesc, 1u);
-            }
+      int it = 0, gc = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int ch = 0; ch < nch; ++ch, ++gc) {
+          const int buf = gc % kAccBufs;
+          if (gc >= kAccBufs) {
+            mbar_wait(tempty + buf, ((gc / kAccBufs) - 1) & 1);  // the accumulate warps have drained this accumulator
+            tc_fence_after();
           }
-          tc_commit(empty + s);  // frees the stage once these MMAs have read it
+          const uint32_t acc = tmem + (uint32_t)(buf * kMaxBN);
+          const int kb_end = min(nkb, (ch + 1) * p.chunk_kb);
+          for (int kb = ch * p.chunk_kb; kb < kb_end; ++kb, ++it) {
+            const int s = it % kStages;
+            mbar_wait(p.prec3 ? ready + s : full + s, (it / kStages) & 1);
+            tc_fence_after();
+            const uint32_t sa = base + s * kStageBytes;
+            const uint64_t da = umma_desc(sa), dal = umma_desc(sa + kTileA), db = umma_desc(sa + 2 * kTileA),
+                           dbl = umma_desc(sa + 2 * kTileA + kTileB);
+            const bool first = kb == ch * p.chunk_kb;
+#pragma unroll
+            for (int k = 0; k < kBK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes: +2 in the (>> 4) start-address field
+              const uint64_t o = (uint64_t)(2 * k);
+              tc_mma_tf32(acc, da + o, db + o, idesc, (first && k == 0) ? 0u : 1u);
+              if (p.prec3) {
+                tc_mma_tf32(acc, dal + o, db + o, idesc, 1u);
+                tc_mma_tf32(acc, da + o, dbl + o, idesc, 1u);
+              }
+            }
+            tc_commit(empty + s);  // frees the stage once these MMAs have read it
+          }
+          tc_commit(tfull + buf);
         }
-        tc_commit(tfull + buf);
       }
     }
   } else if (warp < 6) {
@@ -204,25 +232,36 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     if (p.prec3) {
       const int st_tid = threadIdx.x - 64;  // 0..127
       const int nA = kBM * kBK / 4, nB = p.bn * kBK / 4;  // float4 counts
-      auto lo = [](float x) { return __fsub_rn(x, __uint_as_float(__float_as_uint(x) & 0xffffe000u)); };
+      // hi = x rounded to nearest TF32 (written back in place: the tensor core would otherwise TRUNCATE x to its top 19
+      // bits), lo = x - hi exactly (|lo| <= 2^-12 |x|, 12 significant bits of which the tensor core keeps 11)
+      auto split = [](float x, float& hi, float& lo) {
+        uint32_t h;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+        hi = __uint_as_float(h);
+        lo = __fsub_rn(x, hi);
+      };
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(full + s, (it / kStages) & 1);
-          const float4* a = reinterpret_cast<const float4*>(tiles + s * kStageBytes);
+          float4* a = reinterpret_cast<float4*>(tiles + s * kStageBytes);
           float4* al = reinterpret_cast<float4*>(tiles + s * kStageBytes + kTileA);
-          const float4* b = reinterpret_cast<const float4*>(tiles + s * kStageBytes + 2 * kTileA);
+          float4* b = reinterpret_cast<float4*>(tiles + s * kStageBytes + 2 * kTileA);
           float4* bl = reinterpret_cast<float4*>(tiles + s * kStageBytes + 2 * kTileA + kTileB);
 #pragma unroll 4
           for (int i = st_tid; i < nA; i += 128) {
             const float4 v = a[i];
-            al[i] = make_float4(lo(v.x), lo(v.y), lo(v.z), lo(v.w));
+            float4 h, l;
+            split(v.x, h.x, l.x), split(v.y, h.y, l.y), split(v.z, h.z, l.z), split(v.w, h.w, l.w);
+            a[i] = h, al[i] = l;
           }
 #pragma unroll 4
           for (int i = st_tid; i < nB; i += 128) {
             const float4 v = b[i];
-            bl[i] = make_float4(lo(v.x), lo(v.y), lo(v.z), lo(v.w));
+            float4 h, l;
+            split(v.x, h.x, l.x), split(v.y, h.y, l.y), split(v.z, h.z, l.z), split(v.w, h.w, l.w);
+            b[i] = h, bl[i] = l;
           }
           fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
           mbar_arrive(ready + s);
@@ -230,90 +269,109 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       }
     }
   } else {
-    // ===== epilogue
+    // ===== accumulate + epilogue: thread = one row of the tile
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int nbins = p.N >> 1;
-    float lin = 0.f, lg = 0.f;
+    const int trow = 32 * q + lane;  // row within the tile
     double lin_d = 0.0, lg_d = 0.0;
-    int ti = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-      const int buf = ti & 1;
+    int gc = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * p.bn;
-      const int row = m0 + 32 * q + lane;
+      const int row = m0 + trow;
       const bool row_ok = row < p.M;
-      // mode 1: the target magnitudes of this row, one chunk (8 bins, two 16-byte loads) ahead of their use
-      const float* strow = p.s_true + (size_t)(row_ok ? row : 0) * p.st_pitch + (n0 >> 1);
-      float4 nx0 = make_float4(0.f, 0.f, 0.f, 0.f), nx1 = nx0;
-      if (p.mode == 1 && row_ok) {
-        if ((n0 >> 1) < p.st_pitch) nx0 = __ldg(reinterpret_cast<const float4*>(strow));
-        if ((n0 >> 1) + 4 < p.st_pitch) nx1 = __ldg(reinterpret_cast<const float4*>(strow) + 1);
+      if (MODE == 1) {
+        // this warp's 32 rows of the target magnitudes, read along the bins (coalesced, independent loads) long before use
+        const int hb = p.bn >> 1, b0 = n0 >> 1;
+        __syncwarp();  // the previous tile's reads of sst are done
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+          const int grow = m0 + 32 * q + rr;
+          for (int j = lane; j < hb; j += 32)
+            sst[(32 * q + rr) * kSst + j] = (grow < p.M && b0 + j < nbins) ? __ldg(p.s_true + (size_t)grow * p.st_pitch + b0 + j) : 0.f;
+        }
+        __syncwarp();
       }
-      mbar_wait(tfull + buf, (ti >> 1) & 1);
-      tc_fence_after();
-      const uint32_t tq = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * kMaxBN);
-#pragma unroll 1
-      for (int c = 0; c < p.bn / 16; ++c) {
-        uint32_t r[16];
-        tc_ld16(tq + (uint32_t)(16 * c), r);
-        const int col0 = n0 + 16 * c;
-        if (p.mode == 2) {
-          if (row_ok) {
-            float* dst = p.out + (size_t)row * p.out_pitch + col0;
+      float acc[kAccCols];
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              if (col0 + j + 3 < p.N) {
-                *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                 __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-              } else {
-                for (int jj = j; jj < j + 4; ++jj)
-                  if (col0 + jj < p.N) dst[jj] = __uint_as_float(r[jj]);
-              }
-          }
-        } else {
-          const int bin0 = col0 >> 1;
-          const float stv[8] = {nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w};
-          if (p.mode == 1 && row_ok && 16 * (c + 1) < p.bn) {
-            const int nb0 = (n0 >> 1) + 8 * (c + 1);
-            if (nb0 < p.st_pitch) nx0 = __ldg(reinterpret_cast<const float4*>(strow + 8 * (c + 1)));
-            if (nb0 + 4 < p.st_pitch) nx1 = __ldg(reinterpret_cast<const float4*>(strow + 8 * (c + 1)) + 1);
-          }
-          float mag[8];
+      for (int i = 0; i < kAccCols; ++i) acc[i] = 0.f;
+      for (int ch = 0; ch < nch; ++ch, ++gc) {
+        const int buf = gc % kAccBufs;
+        mbar_wait(tfull + buf, (gc / kAccBufs) & 1);
+        tc_fence_after();
+        const uint32_t tq = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * kMaxBN);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float re = __uint_as_float(r[2 * j]), im = __uint_as_float(r[2 * j + 1]);
-            const float s2 = fmaf(re, re, im * im);
-            const float rs = s2 > 0.f ? rsqrtf(s2) : 0.f;  // 1 / |S|; 0 at the origin, where torch's abs() backward is 0 too
-            const float sp = s2 * rs;
-            mag[j] = sp;
-            if (p.mode == 1 && row_ok && bin0 + j < nbins) {
-              const float st = stv[j];
-              const float dl = sp - st;
-              // log2 through the special-function unit (absolute error ~2^-22): the loss averages millions of these
-              const float dg = __log2f(st + p.eps) - __log2f(sp + p.eps);
-              lin += fabsf(dl);
-              lg += fabsf(dg);
-              // d/dSp [ |Sp - St| + alpha |log2(St+eps) - log2(Sp+eps)| ]
-              const float sgn_l = dl > 0.f ? 1.f : (dl < 0.f ? -1.f : 0.f);
-              const float sgn_g = dg > 0.f ? -1.f : (dg < 0.f ? 1.f : 0.f);
-              const float gs = fmaf(p.alpha * sgn_g * 1.4426950408889634f, __frcp_rn(sp + p.eps), sgn_l);
-              const float inv = gs * rs;
-              float* dst = p.out + (size_t)row * p.out_pitch + col0 + 2 * j;
-              *reinterpret_cast<float2*>(dst) = make_float2(inv * re, inv * im);
+        for (int c = 0; c < kAccCols / 16; ++c) {
+          if (16 * c < p.bn) {
+            uint32_t r[16];
+            tc_ld16(tq + (uint32_t)(16 * c), r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[16 * c + i] += __uint_as_float(r[i]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty + buf);
+      }
+      // ---- the tile's epilogue, from registers
+      float lin = 0.f, lg = 0.f;
+#pragma unroll
+      for (int c = 0; c < kAccCols / 16; ++c) {
+        if (16 * c < p.bn) {
+          const int col0 = n0 + 16 * c;
+          if (MODE == 2) {
+            if (row_ok) {
+              float* dst = p.out + (size_t)row * p.out_pitch + col0;
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                if (col0 + j + 3 < p.N) {
+                  *reinterpret_cast<float4*>(dst + j) = make_float4(acc[16 * c + j], acc[16 * c + j + 1], acc[16 * c + j + 2], acc[16 * c + j + 3]);
+                } else {
+                  for (int jj = j; jj < j + 4; ++jj)
+                    if (col0 + jj < p.N) dst[jj] = acc[16 * c + jj];
+                }
             }
-          }
-          if (p.mode == 0 && row_ok) {  // out pitch is a multiple of 4: whole 16-byte groups inside the pitch are written
-            float* dst = p.out + (size_t)row * p.out_pitch + bin0;
-            if (bin0 + 3 < p.out_pitch) *reinterpret_cast<float4*>(dst) = make_float4(mag[0], mag[1], mag[2], mag[3]);
-            if (bin0 + 7 < p.out_pitch) *reinterpret_cast<float4*>(dst + 4) = make_float4(mag[4], mag[5], mag[6], mag[7]);
+          } else {
+            const int bin0 = col0 >> 1;
+            float mag[8], gq[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float re = acc[16 * c + 2 * j], im = acc[16 * c + 2 * j + 1];
+              const float s2 = fmaf(re, re, im * im);
+              const float rs = s2 > 0.f ? rsqrtf(s2) : 0.f;  // 1 / |S|; 0 at the origin, where torch's abs() backward is 0 too
+              const float sp = s2 * rs;
+              mag[j] = sp;
+              gq[2 * j] = gq[2 * j + 1] = 0.f;
+              if (MODE == 1 && row_ok && bin0 + j < nbins) {
+                const float st = sst[trow * kSst + 8 * c + j];
+                const float dl = sp - st;
+                // log2 through the special-function unit (absolute error ~2^-22): the loss averages millions of these
+                const float dg = __log2f(st + p.eps) - __log2f(sp + p.eps);
+                lin += fabsf(dl);
+                lg += fabsf(dg);
+                // d/dSp [ |Sp - St| + alpha |log2(St+eps) - log2(Sp+eps)| ]
+                const float sgn_l = dl > 0.f ? 1.f : (dl < 0.f ? -1.f : 0.f);
+                const float sgn_g = dg > 0.f ? -1.f : (dg < 0.f ? 1.f : 0.f);
+                const float gs = fmaf(p.alpha * sgn_g * 1.4426950408889634f, __frcp_rn(sp + p.eps), sgn_l);
+                const float inv = gs * rs;
+                gq[2 * j] = inv * re, gq[2 * j + 1] = inv * im;
+              }
+            }
+            if (MODE == 1 && row_ok) {  // the gradient buffer's pitch is a multiple of 32 columns: whole 16-byte groups fit
+              float* dst = p.out + (size_t)row * p.out_pitch + col0;
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                if (col0 + j < p.out_pitch) *reinterpret_cast<float4*>(dst + j) = make_float4(gq[j], gq[j + 1], gq[j + 2], gq[j + 3]);
+            }
+            if (MODE == 0 && row_ok) {  // out pitch is a multiple of 4: whole 16-byte groups inside the pitch are written
+              float* dst = p.out + (size_t)row * p.out_pitch + bin0;
+              if (bin0 + 3 < p.out_pitch) *reinterpret_cast<float4*>(dst) = make_float4(mag[0], mag[1], mag[2], mag[3]);
+              if (bin0 + 7 < p.out_pitch) *reinterpret_cast<float4*>(dst + 4) = make_float4(mag[4], mag[5], mag[6], mag[7]);
+            }
           }
         }
       }
       lin_d += (double)lin, lg_d += (double)lg;  // float partial sums only within one tile row
-      lin = lg = 0.f;
-      tc_fence_before();
-      mbar_arrive(tempty + buf);
     }
-    if (p.mode == 1) {
+    if (MODE == 1) {
       for (int o = 16; o; o >>= 1) {
         lin_d += __shfl_xor_sync(0xffffffffu, lin_d, o);
         lg_d += __shfl_xor_sync(0xffffffffu, lg_d, o);
@@ -326,7 +384,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kAccBufs * kMaxBN) : "memory");
 }
 
 // ---- framing / overlap-add -----------------------------------------------------------------------------------------------
@@ -442,7 +500,7 @@ static int make_map(CUtensorMap* tm, const float* ptr, int rows, int cols, int64
 }
 
 static int launch_gemm(const float* A, int64_t pitchA, const float* Bt, int64_t pitchB, MssGemmParams p, cudaStream_t st) {
-  if (p.bn % 16 != 0 || p.bn < 16 || p.bn > kMaxBN || (pitchA & 3) || (pitchB & 3)) return GOLF_ERR_INVALID;
+  if (p.bn % 16 != 0 || p.bn < 16 || p.bn > kAccCols || (pitchA & 3) || (pitchB & 3)) return GOLF_ERR_INVALID;
   if (((uintptr_t)A & 15) || ((uintptr_t)Bt & 15)) return GOLF_ERR_INVALID;
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, A, p.M, p.K, pitchA, kBM);
@@ -451,13 +509,18 @@ static int launch_gemm(const float* A, int64_t pitchA, const float* Bt, int64_t 
   if (rc) return rc;
   static unsigned long long attr = 0;
   if (first_use_on_device(attr)) {
-    GOLF_CUDA(cudaFuncSetAttribute(mss_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+    GOLF_CUDA(cudaFuncSetAttribute(mss_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+    GOLF_CUDA(cudaFuncSetAttribute(mss_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+    GOLF_CUDA(cudaFuncSetAttribute(mss_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     mark_used_on_device(attr);
   }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int n_tiles = ceil_div(p.N, p.bn) * ceil_div(p.M, kBM);
-  mss_gemm_kernel<<<n_tiles < sms ? n_tiles : sms, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p);
+  const int grid = n_tiles < sms ? n_tiles : sms;
+  if (p.mode == 0) mss_gemm_kernel<0><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p);
+  else if (p.mode == 1) mss_gemm_kernel<1><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p);
+  else mss_gemm_kernel<2><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p);
   GOLF_CHECK_LAUNCH();
   return GOLF_OK;
 }
@@ -468,7 +531,7 @@ struct MssScale {
 static bool mss_scale(int n_fft, int hop, int B, int L, MssScale* s) {
   if (n_fft < 16 || n_fft > 4096 || L <= n_fft / 2) return false;  // reflect padding needs pad < L
   s->n_fft = n_fft;
-  s->hop = hop > 0 ? hop : n_fft - (int)(n_fft * 0.75);  // loss/spec.py:57: hop_length = int(n_fft - n_fft * overlap)
+  s->hop = hop > 0 ? hop : (int)(n_fft - n_fft * 0.75);  // loss/spec.py:57: hop_length = int(n_fft - n_fft * overlap)
   if (s->hop > n_fft) return false;
   s->nbins = n_fft / 2 + 1;
   s->N = 2 * s->nbins;
@@ -479,9 +542,9 @@ static bool mss_scale(int n_fft, int hop, int B, int L, MssScale* s) {
   s->rows = B * s->nfr;
   const int m_tiles = ceil_div(s->rows, kBM);
   auto pick = [m_tiles](int n) {  // N tile (multiple of 16): useful fraction of the work of the last wave x of the padded columns
-    int best = 256;
+    int best = kAccCols;
     double best_eff = 0.0;
-    for (int bn = 256; bn >= 128; bn -= 16) {
+    for (int bn = kAccCols; bn >= 64; bn -= 16) {
       const int nt = ceil_div(n, bn), tiles = nt * m_tiles;
       const double eff = ((double)n / (nt * bn)) * ((double)tiles / (ceil_div(tiles, 148) * 148));
       if (eff > best_eff + 1e-9) best_eff = eff, best = bn;
@@ -568,7 +631,7 @@ GOLF_API int golf_mss_loss(const float* pred, int64_t pred_stride, const float* 
     mss_frames_kernel<<<fgrid, 128, 0, st>>>(target, target_stride, fr_t, pred, pred_stride, fr_p, s.Kp, L, s.n_fft, s.hop, s.nfr);
     GOLF_CHECK_LAUNCH();
     MssGemmParams p{};
-    p.M = s.rows, p.N = s.N, p.K = s.n_fft, p.bn = s.bn_f, p.prec3 = prec3 ? 1 : 0, p.alpha = alpha, p.eps = eps;
+    p.M = s.rows, p.N = s.N, p.K = s.n_fft, p.bn = s.bn_f, p.prec3 = (prec3 & 1) ? 1 : 0, p.chunk_kb = 4, p.alpha = alpha, p.eps = eps;
     p.mode = 0, p.out = s_true, p.out_pitch = s.nbp;
     int rc = launch_gemm(fr_t, s.Kp, fwd, s.Kp, p, st);
     if (rc) return rc;
@@ -577,7 +640,7 @@ GOLF_API int golf_mss_loss(const float* pred, int64_t pred_stride, const float* 
     if (rc) return rc;
     if (d_pred) {
       MssGemmParams b{};
-      b.M = s.rows, b.N = s.n_fft, b.K = s.N, b.bn = s.bn_b, b.prec3 = 0, b.mode = 2, b.out = fr_t, b.out_pitch = s.Kp;
+      b.M = s.rows, b.N = s.n_fft, b.K = s.N, b.bn = s.bn_b, b.prec3 = (prec3 & 2) ? 1 : 0, b.chunk_kb = (prec3 & 2) ? 4 : 16, b.mode = 2, b.out = fr_t, b.out_pitch = s.Kp;
       rc = launch_gemm(G, s.Kb, bwd, s.Kb, b, st);
       if (rc) return rc;
       mss_ola_kernel<<<dim3(ceil_div(L, 256), B), 256, 0, st>>>(fr_t, s.Kp, d_pred, dpred_stride, B, L, s.n_fft, s.hop, s.nfr,
@@ -595,6 +658,6 @@ GOLF_API int golf_mss_gemm(const float* A, int64_t pitchA, const float* Bt, int6
                            int K, int bn, int prec3, void* stream) {
   if (!A || !Bt || !D || M <= 0 || N <= 0 || K <= 0 || (pitchD & 3) || ((uintptr_t)D & 15)) return GOLF_ERR_INVALID;
   MssGemmParams p{};
-  p.M = M, p.N = N, p.K = K, p.bn = bn, p.prec3 = prec3 ? 1 : 0, p.mode = 2, p.out = D, p.out_pitch = pitchD;
+  p.M = M, p.N = N, p.K = K, p.bn = bn, p.prec3 = prec3 ? 1 : 0, p.chunk_kb = prec3 ? 4 : 16, p.mode = 2, p.out = D, p.out_pitch = pitchD;
   return launch_gemm(A, pitchA, Bt, pitchB, p, (cudaStream_t)stream);
 }

@@ -218,7 +218,7 @@ int golf_lpc_inverse_bwd(const float *g, const float *y, int64_t y_stride, const
 /* loss/spec.py:11-67 with torchaudio's Spectrogram defaults (centre / reflect padding, periodic Hann of n_fft, hop =
  * n_fft - int(0.75 n_fft), onesided, power 1):  loss = ratio * sum_scales ( mean|Sp - St| + alpha mean|log2(St + eps) -
  * log2(Sp + eps)| ).  The STFTs are DFT-as-GEMM on the tcgen05 tensor cores (the shipped sizes 509 / 1021 / 2053 are primes),
- * prec3 != 0: error-compensated 3 x TF32 products (float32-grade).  tables[i]: the DFT bases of n_ffts[i], built once by
+ * prec3: bit 0 error-compensated 3 x TF32 products (float32-grade) in the forward GEMMs, bit 1 in the adjoint GEMM (3 = both).  tables[i]: the DFT bases of n_ffts[i], built once by
  * golf_mss_build_tables into golf_mss_tables_bytes(n_fft) bytes.  loss: one float on the device.  d_pred (optional, [B, L]
  * with row stride dpred_stride): d loss / d pred.  pred, target [B, L].  hops: one hop per scale, or NULL for the 75 % overlap
  * of the shipped config.  At most 8 scales, n_fft <= 4096, L > n_fft / 2. */

@@ -15,8 +15,8 @@ and the same zero-initialised output layer (models/enc.py:24-27) produces the lo
 therefore the decoder side exactly, plus a DDP gradient exchange of the right size overlapped with a backward of
 comparable shape (torch DistributedDataParallel buckets, as Lightning uses).
 
-    python tools/fit_step.py [steps] [ss|ff]                                                  # one GPU
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/fit_step.py [steps] [ss|ff]
+    python tools/fit_step.py [steps] [ss|ff] [tcgen05|torch]                                  # one GPU
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/fit_step.py [steps] [ss|ff] [tcgen05|torch]
 
 Prints one JSON line: samples/s over all ranks, ms per step (max over ranks), the per-phase split, and the time of a
 bare 24.3 MB all-reduce on the same communicator (what DDP has to hide).
@@ -42,6 +42,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 variant = sys.argv[2] if len(sys.argv) > 2 else "ss"  # "ff": GOLF-ff (frame-wise filter), cfg/ae/decoder/golf.yaml
+loss_impl = sys.argv[3] if len(sys.argv) > 3 else "tcgen05"  # "tcgen05-fastbwd": single-TF32 adjoint GEMM; "torch": the torch.stft / cuFFT restatement of loss/spec.py
 B, T, SR, HOP = bench.BATCH, bench.T, bench.SR, bench.HOP
 FRAMES = T // HOP  # 200: the U-Net's frame count for sample-rate f0 (models/unet.py:160-162)
 
@@ -105,8 +106,16 @@ f0 = torch.where(unv, torch.zeros_like(f0), f0)
 x = (torch.randn(B, T, device=dev) * 0.05).contiguous()
 
 
+from golf_b200.loss import MSSLoss  # noqa: E402
+
+criterion = MSSLoss([509, 1021, 2053], alpha=1.0, overlap=0.75, window="hann", precision=1 if loss_impl == "tcgen05-fastbwd" else 3)  # cfg/ae/vctk.yaml:58-67 on tcgen05
+
+
 def mss(pred, true):
-    """loss/spec.py:11-67 (Spectrogram power=1, periodic Hann, centre / reflect padding), torch.stft restatement"""
+    """loss/spec.py:11-67 (Spectrogram power=1, periodic Hann, centre / reflect padding): golf_b200.loss.MSSLoss (DFT-as-GEMM
+    on the tensor cores, csrc/mss.cu) or, with `torch` as the third argument, the torch.stft / cuFFT restatement"""
+    if loss_impl != "torch":
+        return criterion(pred.contiguous(), true.contiguous())
     loss = 0.0
     for n, win in windows.items():
         sp, st = (torch.stft(v, n, hop_length=int(n - n * 0.75), window=win, return_complex=True).abs() for v in (pred, true))
@@ -165,7 +174,7 @@ if rank == 0:
     print(json.dumps({
         "workload": f"GOLF-{variant} fit step (stand-in encoder {n_params / 1e6:.2f} M params -> .ctrl -> decoder fwd -> MSS loss -> bwd "
                     f"(CUDA adjoints){' + DDP all-reduce' if world > 1 else ''} -> clip 0.5 -> Adam), {B} x 2 s per GPU, eager",
-        "n_gpus": world, "ms_per_step": float(t), "samples_per_s": world * B * T / (float(t) * 1e-3),
+        "n_gpus": world, "mss_loss": f"golf_b200.loss ({loss_impl} DFT-as-GEMM)" if loss_impl != "torch" else "torch.stft (cuFFT Bluestein)", "ms_per_step": float(t), "samples_per_s": world * B * T / (float(t) * 1e-3),
         "split_ms": {"encoder_decoder_fwd": tot[0] / steps, "mss_loss_fwd": tot[1] / steps, "backward_incl_allreduce": tot[2] / steps,
                      "clip_adam": tot[3] / steps},
         "bare_allreduce_ms": allreduce_ms, "grad_bytes": 4 * n_params, "loss": float(loss)}))
