@@ -435,6 +435,7 @@ def run_gpu(args):
         "in_flight": IN_FLIGHT, "ms_per_step_one_at_a_time": ms_seq / args.steps,
     }
     if world == 1 and not args.no_cpu:
+        line["fit_step"] = fit_step_extra()
         keep = {}
         val, cores, dt = run_cpu(args.cpu_steps, 1, BATCH, keep)
         line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
@@ -443,6 +444,23 @@ def run_gpu(args):
     if world > 1:
         dist.destroy_process_group()
     return line
+
+
+def fit_step_extra():
+    """BASELINE.json configs[3] (the autoencode.py fit step) as an extra key, N = 1: tools/fit_step.py in a child process,
+    once with the tcgen05 multi-scale spectral loss (golf_b200.loss) and once with the torch.stft / cuFFT restatement of the
+    reference's loss.  The multi-GPU runs of the same script are under profiles/.  Never costs the main line."""
+    out = {"what": "VoiceAutoEncoder.training_step semantics (ltng/ae.py:86-143) with a 6.09 M-parameter stand-in encoder: encoder -> "
+                   ".ctrl -> golf_b200 decoder -> MSS loss -> CUDA adjoints -> clip 0.5 -> Adam, 32 x 2 s, eager (tools/fit_step.py)"}
+    for key, impl in (("golf_mss_loss", "tcgen05"), ("torch_stft_loss", "torch")):
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fit_step.py"), "10", "ss", impl], capture_output=True,
+                               text=True, timeout=300, env={**os.environ, "RANK": "0", "WORLD_SIZE": "1", "LOCAL_RANK": "0"})
+            rec = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+            out[key] = {"ms_per_step": rec["ms_per_step"], "samples_per_s": rec["samples_per_s"], "split_ms": rec["split_ms"]}
+        except Exception as e:  # noqa: BLE001
+            out[key] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    return out
 
 
 def parity_check(dev, keep, AudioTensor):

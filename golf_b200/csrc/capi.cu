@@ -6,7 +6,7 @@
 namespace golf {
 static std::atomic<uint64_t> g_launches{0};
 static thread_local int g_last_cuda = 0;
-int g_pdl = 1;
+std::atomic<int> g_pdl{1};
 
 void note_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 int note_cuda(cudaError_t e) {

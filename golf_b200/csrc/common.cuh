@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/golf_b200.h"
 
 #define GOLF_API extern "C" __attribute__((visibility("default")))
@@ -39,7 +41,7 @@ int note_cuda(cudaError_t e);  // records e, returns GOLF_ERR_CUDA if e != cudaS
 // scan.  Measured on the other edges of the decoder chain (wait at the top of the dependent kernel) it
 // gained nothing: early-launched CTAs only hold registers while they wait (profiles/README.md).
 // golf_set_pdl(0) turns the attribute off.
-extern int g_pdl;
+extern std::atomic<int> g_pdl;  // process-wide switches are relaxed atomics: host threads may flip them while others launch
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

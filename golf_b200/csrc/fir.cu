@@ -19,7 +19,7 @@
 
 namespace golf {
 
-int g_fir_x2 = 1;  // 1 (default): packed-FP32 (FFMA2) kernels where they apply; 0: scalar register tile
+std::atomic<int> g_fir_x2{1};  // 1 (default): packed-FP32 (FFMA2) kernels where they apply; 0: scalar register tile
 
 // ---- time-varying block FIR ---------------------------------------------------------
 // grid (n_blocks, B), 32*ceil(hop/256) threads.  smem: xs[hop + K12 + 32] | ks[K12]

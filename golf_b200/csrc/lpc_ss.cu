@@ -150,10 +150,10 @@ __global__ void ss_dzi_kernel(const float* __restrict__ u, const float* __restri
 // solve to a few float32 ulps (well-conditioned filters) -- see DESIGN.md 3.1.  (At 1e-4 the encoder-derived
 // controls never trigger it and stay at the float32 floor; of 128 random order-32 trajectories one ends at 20x its
 // floor, 2.4e-4 -- 1e-5 leaves none above 10x but also fires on realistic controls, +45 us per pass: tools/diag_accuracy.py.)
-static float g_refine_tol = 1e-4f;
-int g_solve_systolic = 1;
-int g_ss_tail = 0;
-int g_ss_response_mode = 0;
+static std::atomic<float> g_refine_tol{1e-4f};
+std::atomic<int> g_solve_systolic{1};
+std::atomic<int> g_ss_tail{0};
+std::atomic<int> g_ss_response_mode{0};
 
 struct SsPlan {
   int B, MP, Lc, C, HB;
@@ -227,7 +227,7 @@ static void plan_pointers(const SsPlan& pl, void* workspace, SsParams* p) {
   p->room_k = nullptr, p->room_out = nullptr, p->room_n = 0;
   // the tensor-core response kernel's transition matrices are ~10x less accurate than the FP32 kernel's (truncating
   // accumulation): with it the refinement round is not optional
-  p->refine_tol = (g_ss_response_mode == 1 && pl.MP == 24) ? 0.f : g_refine_tol;
+  p->refine_tol = (g_ss_response_mode.load() == 1 && pl.MP == 24) ? 0.f : g_refine_tol.load();
 }
 
 

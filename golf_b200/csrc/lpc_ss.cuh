@@ -42,8 +42,8 @@
 
 namespace golf {
 
-extern int g_solve_systolic;  // 1 (default): 4-lanes-per-chunk solve where it applies; 0: lane-per-chunk
-extern int g_ss_tail;         // stitch + solve + refinement (+ room) in one cluster launch: 0 (default) never, 1 where it applies, 2 small batches
+extern std::atomic<int> g_solve_systolic;  // 1 (default): 4-lanes-per-chunk solve where it applies; 0: lane-per-chunk
+extern std::atomic<int> g_ss_tail;         // stitch + solve + refinement (+ room) in one cluster launch: 0 (default) never, 1 where it applies, 2 small batches
 constexpr int kTailAutoMaxBatch = 8;
 
 struct SsParams {

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(32 * kTcWarps, 4) ss_response_tc_kernel(SsPara
   }
 }
 
-extern int g_ss_response_mode;  // 0: FP32 kernel (default), 1: tensor cores, 3 x TF32
+extern std::atomic<int> g_ss_response_mode;  // 0: FP32 kernel (default), 1: tensor cores, 3 x TF32
 
 inline bool response_tc_applies(const SsParams& p, int MP, int FORM) {
   return g_ss_response_mode != 0 && FORM == 0 && MP == 24 && p.Lc % 8 == 0 && p.Lc >= 24 && p.M <= 24;

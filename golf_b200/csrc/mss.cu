@@ -29,15 +29,16 @@
 namespace golf {
 
 constexpr int kMssMaxScales = 8;
-constexpr int kGemmThreads = 320;
+constexpr int kGemmThreads = 512;  // 4 warpgroups: producer + MMA | splitter | epilogue (column half 0) | epilogue (column half 1)
 constexpr int kBM = 128;          // rows per tile (TMEM lanes)
 constexpr int kBK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int kMaxBN = 128;       // TMEM columns per accumulator and rows of a B tile in shared memory
-constexpr int kAccCols = 128;     // columns per tile actually used: one float32 REGISTER accumulator per column and epilogue thread
-constexpr int kStages = 3;
-constexpr int kAccBufs = 4;       // TMEM accumulators (kMaxBN columns each): the tensor cores may run this many chunks ahead
+constexpr int kAccCols = 112;     // float32 REGISTER accumulators per epilogue thread (one row, one column half of the tile)
+constexpr int kMaxBN = 208;       // columns per tile (two epilogue warpgroups share a row: 7 + 6 groups of 16); rows of a B tile
+constexpr int kTmemCols = 256;    // TMEM columns per accumulator (allocation granularity)
+constexpr int kStages = 2;
+constexpr int kAccBufs = 2;       // TMEM accumulators: the tensor cores run one chunk ahead of the register accumulation
 constexpr int kTileA = kBM * kBK * 4;        // 16 KB
-constexpr int kTileB = kMaxBN * kBK * 4;     // 16 KB
+constexpr int kTileB = kMaxBN * kBK * 4;     // 26 KB
 constexpr int kStageBytes = 2 * kTileA + 2 * kTileB;  // A | A_lo | B | B_lo
 constexpr int kSst = kMaxBN / 2 + 1;         // row stride of the staged target magnitudes (conflict-free column reads)
 constexpr int kSstBytes = kBM * kSst * 4;
@@ -53,7 +54,8 @@ struct MssGemmParams {
   int64_t out_pitch;
   const float* s_true;  // [M, N/2]
   int64_t st_pitch;
-  double* loss_acc;     // [2]: sum |Sp - St|, sum |log2(St + eps) - log2(Sp + eps)|
+  double* loss_acc;     // [gridDim.x][2] per-CTA partial sums: |Sp - St|, |log2(St + eps) - log2(Sp + eps)| (no atomics: same-address
+                        // atomics serialise in L2 -- 1 184 of them cost 46 us per launch -- and the sum stays deterministic)
   float alpha, eps;
 };
 
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
   float* sst = reinterpret_cast<float*>(tiles + kStages * kStageBytes);  // [128][kSst] target magnitudes of the tile (mode 1)
+  constexpr int kRegProducer = 40, kRegSplit = 96, kRegEpilogue = 184;  // 128 x (40 + 96 + 2 x 184) = 64 512 <= 65 536
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + kStages * kStageBytes + kSstBytes);
   uint64_t* full = bars;                 // [kStages]
   uint64_t* ready = bars + kStages;      // [kStages]
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   uint64_t* tfull = bars + 3 * kStages;  // [kAccBufs]
   uint64_t* tempty = bars + 3 * kStages + kAccBufs;  // [kAccBufs]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 2 * kAccBufs);
+  double* red = reinterpret_cast<double*>(bars + 3 * kStages + 2 * kAccBufs + 1);  // [16] per-warp loss partial sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.K + kBK - 1) / kBK;
@@ -161,12 +165,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
     for (int b = 0; b < kAccBufs; ++b) {
       mbar_init(tfull + b, 1);
-      mbar_init(tempty + b, 128);
+      mbar_init(tempty + b, 256);
     }
     mbar_fence_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kAccBufs * kMaxBN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kAccBufs * kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -174,6 +178,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegProducer));
   if (warp == 0) {
     // ===== TMA producer
     if (lane == 0) {
@@ -202,7 +208,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             mbar_wait(tempty + buf, ((gc / kAccBufs) - 1) & 1);  // the accumulate warps have drained this accumulator
             tc_fence_after();
           }
-          const uint32_t acc = tmem + (uint32_t)(buf * kMaxBN);
+          const uint32_t acc = tmem + (uint32_t)(buf * kTmemCols);
           const int kb_end = min(nkb, (ch + 1) * p.chunk_kb);
           for (int kb = ch * p.chunk_kb; kb < kb_end; ++kb, ++it) {
             const int s = it % kStages;
@@ -227,10 +233,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
       }
     }
-  } else if (warp < 6) {
+  }
+  // (warps 2 and 3 of the producer warpgroup idle)
+  } else if (warp < 8) {
     // ===== splitter: lo = x - hi for both operand tiles, same swizzled positions
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegSplit));
     if (p.prec3) {
-      const int st_tid = threadIdx.x - 64;  // 0..127
+      const int st_tid = threadIdx.x - 128;  // 0..127
       const int nA = kBM * kBK / 4, nB = p.bn * kBK / 4;  // float4 counts
       // hi = x rounded to nearest TF32 (written back in place: the tensor core would otherwise TRUNCATE x to its top 19
       // bits), lo = x - hi exactly (|lo| <= 2^-12 |x|, 12 significant bits of which the tensor core keeps 11)
@@ -269,10 +278,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       }
     }
   } else {
-    // ===== accumulate + epilogue: thread = one row of the tile
+    // ===== accumulate + epilogue: thread = one row of the tile, one column half
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegEpilogue));
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int nbins = p.N >> 1;
     const int trow = 32 * q + lane;  // row within the tile
+    // the tile's 16-column groups are divided between the two epilogue warpgroups: [0, cs) and [cs, bn)
+    const int ngrp = p.bn >> 4, g_half = (ngrp + 1) >> 1;
+    const int cs = warp >= 12 ? 16 * g_half : 0;                  // first column of this thread's part
+    const int cw = warp >= 12 ? p.bn - 16 * g_half : 16 * g_half;  // its width (<= kAccCols)
     double lin_d = 0.0, lg_d = 0.0;
     int gc = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -281,15 +295,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       const bool row_ok = row < p.M;
       if (MODE == 1) {
         // this warp's 32 rows of the target magnitudes, read along the bins (coalesced, independent loads) long before use
-        const int hb = p.bn >> 1, b0 = n0 >> 1;
+        const int hb = cw >> 1, b0 = (n0 + cs) >> 1, s0 = cs >> 1;  // this warp: its 32 rows, its column half
         __syncwarp();  // the previous tile's reads of sst are done
-#pragma unroll 8
+        // asynchronous copies (LDGSTS, zero fill outside the matrix): nothing waits for them until the tile's last chunk
         for (int rr = 0; rr < 32; ++rr) {
           const int grow = m0 + 32 * q + rr;
-          for (int j = lane; j < hb; j += 32)
-            sst[(32 * q + rr) * kSst + j] = (grow < p.M && b0 + j < nbins) ? __ldg(p.s_true + (size_t)grow * p.st_pitch + b0 + j) : 0.f;
+          for (int j = lane; j < hb; j += 32) {
+            const bool ok = grow < p.M && b0 + j < nbins;
+            cp_async4(sst + (32 * q + rr) * kSst + s0 + j, p.s_true + (ok ? (size_t)grow * p.st_pitch + b0 + j : 0), ok);
+          }
         }
-        __syncwarp();
       }
       float acc[kAccCols];
 #pragma unroll
@@ -298,10 +313,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         const int buf = gc % kAccBufs;
         mbar_wait(tfull + buf, (gc / kAccBufs) & 1);
         tc_fence_after();
-        const uint32_t tq = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * kMaxBN);
+        const uint32_t tq = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * kTmemCols + cs);
 #pragma unroll
         for (int c = 0; c < kAccCols / 16; ++c) {
-          if (16 * c < p.bn) {
+          if (16 * c < cw) {
             uint32_t r[16];
             tc_ld16(tq + (uint32_t)(16 * c), r);
 #pragma unroll
@@ -312,11 +327,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         mbar_arrive(tempty + buf);
       }
       // ---- the tile's epilogue, from registers
+      if (MODE == 1) {
+        cp_async_wait_all();
+        __syncwarp();
+      }
       float lin = 0.f, lg = 0.f;
 #pragma unroll
       for (int c = 0; c < kAccCols / 16; ++c) {
-        if (16 * c < p.bn) {
-          const int col0 = n0 + 16 * c;
+        if (16 * c < cw) {
+          const int col0 = n0 + cs + 16 * c;
           if (MODE == 2) {
             if (row_ok) {
               float* dst = p.out + (size_t)row * p.out_pitch + col0;
@@ -341,7 +360,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
               mag[j] = sp;
               gq[2 * j] = gq[2 * j + 1] = 0.f;
               if (MODE == 1 && row_ok && bin0 + j < nbins) {
-                const float st = sst[trow * kSst + 8 * c + j];
+                const float st = sst[trow * kSst + (cs >> 1) + 8 * c + j];
                 const float dl = sp - st;
                 // log2 through the special-function unit (absolute error ~2^-22): the loss averages millions of these
                 const float dg = __log2f(st + p.eps) - __log2f(sp + p.eps);
@@ -376,15 +395,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         lin_d += __shfl_xor_sync(0xffffffffu, lin_d, o);
         lg_d += __shfl_xor_sync(0xffffffffu, lg_d, o);
       }
-      if (lane == 0) {
-        atomicAdd(p.loss_acc, lin_d);
-        atomicAdd(p.loss_acc + 1, lg_d);
-      }
+      if (lane == 0) red[2 * (warp - 8)] = lin_d, red[2 * (warp - 8) + 1] = lg_d;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kAccBufs * kMaxBN) : "memory");
+  if (MODE == 1 && threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < 8; ++w) a += red[2 * w], b += red[2 * w + 1];
+    p.loss_acc[2 * blockIdx.x] = a, p.loss_acc[2 * blockIdx.x + 1] = b;
+  }
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kAccBufs * kTmemCols) : "memory");
 }
 
 // ---- framing / overlap-add -----------------------------------------------------------------------------------------------
@@ -463,12 +484,19 @@ __global__ void mss_tables_kernel(float* __restrict__ fwd, int64_t kp, float* __
 
 struct MssCounts {
   double inv[kMssMaxScales];
+  int grid[kMssMaxScales];
 };
-__global__ void mss_finish_kernel(const double* __restrict__ acc, MssCounts cnt, int n_scales, float alpha, float ratio,
-                                  float* __restrict__ loss) {
+constexpr int kMaxGrid = 256;  // per-CTA partial sums kept per scale (the persistent grid is at most one CTA per SM)
+__global__ void __launch_bounds__(32) mss_finish_kernel(const double* __restrict__ acc, MssCounts cnt, int n_scales, float alpha,
+                                                        float ratio, float* __restrict__ loss) {
   double tot = 0.0;
-  for (int s = 0; s < n_scales; ++s) tot += (acc[2 * s] + (double)alpha * acc[2 * s + 1]) * cnt.inv[s];
-  loss[0] = (float)(tot * ratio);
+  for (int s = 0; s < n_scales; ++s) {
+    double lin = 0.0, lg = 0.0;
+    for (int c = threadIdx.x; c < cnt.grid[s]; c += 32) lin += acc[(size_t)(s * kMaxGrid + c) * 2], lg += acc[(size_t)(s * kMaxGrid + c) * 2 + 1];
+    tot += (lin + (double)alpha * lg) * cnt.inv[s];
+  }
+  for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  if (threadIdx.x == 0) loss[0] = (float)(tot * ratio);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
@@ -499,8 +527,16 @@ static int make_map(CUtensorMap* tm, const float* ptr, int rows, int cols, int64
   return r == CUDA_SUCCESS ? GOLF_OK : GOLF_ERR_CUDA;
 }
 
+static int gemm_grid(const MssGemmParams& p) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms > kMaxGrid) sms = kMaxGrid;
+  const int n_tiles = ceil_div(p.N, p.bn) * ceil_div(p.M, kBM);
+  return n_tiles < sms ? n_tiles : sms;
+}
+
 static int launch_gemm(const float* A, int64_t pitchA, const float* Bt, int64_t pitchB, MssGemmParams p, cudaStream_t st) {
-  if (p.bn % 16 != 0 || p.bn < 16 || p.bn > kAccCols || (pitchA & 3) || (pitchB & 3)) return GOLF_ERR_INVALID;
+  if (p.bn % 16 != 0 || p.bn < 16 || p.bn > kMaxBN || (pitchA & 3) || (pitchB & 3)) return GOLF_ERR_INVALID;
   if (((uintptr_t)A & 15) || ((uintptr_t)Bt & 15)) return GOLF_ERR_INVALID;
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, A, p.M, p.K, pitchA, kBM);
@@ -514,10 +550,7 @@ static int launch_gemm(const float* A, int64_t pitchA, const float* Bt, int64_t 
     GOLF_CUDA(cudaFuncSetAttribute(mss_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     mark_used_on_device(attr);
   }
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int n_tiles = ceil_div(p.N, p.bn) * ceil_div(p.M, kBM);
-  const int grid = n_tiles < sms ? n_tiles : sms;
+  const int grid = gemm_grid(p);
   if (p.mode == 0) mss_gemm_kernel<0><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p);
   else if (p.mode == 1) mss_gemm_kernel<1><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p);
   else mss_gemm_kernel<2><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p);
@@ -542,9 +575,9 @@ static bool mss_scale(int n_fft, int hop, int B, int L, MssScale* s) {
   s->rows = B * s->nfr;
   const int m_tiles = ceil_div(s->rows, kBM);
   auto pick = [m_tiles](int n) {  // N tile (multiple of 16): useful fraction of the work of the last wave x of the padded columns
-    int best = kAccCols;
+    int best = kMaxBN;
     double best_eff = 0.0;
-    for (int bn = kAccCols; bn >= 64; bn -= 16) {
+    for (int bn = kMaxBN; bn >= 128; bn -= 16) {
       const int nt = ceil_div(n, bn), tiles = nt * m_tiles;
       const double eff = ((double)n / (nt * bn)) * ((double)tiles / (ceil_div(tiles, 148) * 148));
       if (eff > best_eff + 1e-9) best_eff = eff, best = bn;
@@ -590,7 +623,7 @@ GOLF_API size_t golf_mss_workspace_bytes(int B, int L, const int* n_ffts, const 
     g = std::max(g, (size_t)s.rows * s.Kb);
   }
   // frames(pred) | frames(true) / d_frames | S_true | G | accumulators
-  return align_up(frames * 4, 256) * 2 + align_up(strue * 4, 256) + align_up(g * 4, 256) + 256 + 1024;
+  return align_up(frames * 4, 256) * 2 + align_up(strue * 4, 256) + align_up(g * 4, 256) + (size_t)kMssMaxScales * kMaxGrid * 2 * sizeof(double) + 1024;
 }
 
 // loss[0] = ratio * sum_s ( mean|Sp - St| + alpha * mean|log2(St+eps) - log2(Sp+eps)| );  d_pred (optional) = d loss / d pred.
@@ -620,7 +653,6 @@ GOLF_API int golf_mss_loss(const float* pred, int64_t pred_stride, const float* 
   float* s_true = reinterpret_cast<float*>(ws + 2 * align_up(frames * 4, 256));
   float* G = reinterpret_cast<float*>(ws + 2 * align_up(frames * 4, 256) + align_up(strue * 4, 256));
   double* acc = reinterpret_cast<double*>(ws + 2 * align_up(frames * 4, 256) + align_up(strue * 4, 256) + align_up(g * 4, 256));
-  GOLF_CUDA(cudaMemsetAsync(acc, 0, 2 * kMssMaxScales * sizeof(double), st));
   MssCounts cnt{};
   for (int i = 0; i < n_scales; ++i) cnt.inv[i] = 1.0 / ((double)sc[i].rows * sc[i].nbins);
   for (int i = 0; i < n_scales; ++i) {
@@ -635,7 +667,8 @@ GOLF_API int golf_mss_loss(const float* pred, int64_t pred_stride, const float* 
     p.mode = 0, p.out = s_true, p.out_pitch = s.nbp;
     int rc = launch_gemm(fr_t, s.Kp, fwd, s.Kp, p, st);
     if (rc) return rc;
-    p.mode = 1, p.out = G, p.out_pitch = s.Kb, p.s_true = s_true, p.st_pitch = s.nbp, p.loss_acc = acc + 2 * i;
+    p.mode = 1, p.out = G, p.out_pitch = s.Kb, p.s_true = s_true, p.st_pitch = s.nbp, p.loss_acc = acc + (size_t)i * kMaxGrid * 2;
+    cnt.grid[i] = gemm_grid(p);
     rc = launch_gemm(fr_p, s.Kp, fwd, s.Kp, p, st);
     if (rc) return rc;
     if (d_pred) {
@@ -648,7 +681,7 @@ GOLF_API int golf_mss_loss(const float* pred, int64_t pred_stride, const float* 
       GOLF_CHECK_LAUNCH();
     }
   }
-  mss_finish_kernel<<<1, 1, 0, st>>>(acc, cnt, n_scales, alpha, ratio, loss);
+  mss_finish_kernel<<<1, 32, 0, st>>>(acc, cnt, n_scales, alpha, ratio, loss);
   GOLF_CHECK_LAUNCH();
   return GOLF_OK;
 }

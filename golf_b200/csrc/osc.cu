@@ -799,7 +799,7 @@ static OscParams osc_params(const float* phase, const float* tables, const doubl
   return p;
 }
 
-static int g_osc_v2 = 1;
+static std::atomic<int> g_osc_v2{1};
 
 }  // namespace golf
 

@@ -123,7 +123,7 @@ def test_tcgen05_gemm_against_float64():
 
     L = _lib.lib()
     g = torch.Generator(device=DEV).manual_seed(0)
-    for (M, N, K, bn) in ((128, 16, 32, 16), (300, 80, 100, 80), (1000, 510, 509, 96), (517, 1022, 1021, 112)):
+    for (M, N, K, bn) in ((128, 16, 32, 16), (300, 80, 100, 80), (1000, 510, 509, 96), (517, 1022, 1021, 208), (200, 300, 70, 176)):
         def padded(rows, cols):
             t = torch.zeros(rows, (cols + 31) // 32 * 32, device=DEV)
             t[:, :cols] = torch.randn(rows, cols, generator=g, device=DEV)

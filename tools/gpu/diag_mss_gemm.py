@@ -19,7 +19,7 @@ def padded(rows, cols, gen):
     t[:, :cols] = torch.randn(rows, cols, generator=gen, device=dev)
     return t[:, :cols]  # a view with pitch p
 g = torch.Generator(device=dev).manual_seed(0)
-for (M, N, K, bn) in ((128, 16, 32, 16), (128, 112, 32, 112), (128, 64, 64, 64), (300, 80, 100, 80), (1000, 510, 509, 112), (3008, 2054, 2053, 112), (3008, 2053, 2054, 112)):
+for (M, N, K, bn) in ((128, 16, 32, 16), (128, 112, 32, 112), (128, 64, 64, 64), (300, 80, 100, 80), (1000, 510, 509, 176), (3008, 2054, 2053, 208), (3008, 2053, 2054, 208)):
     A, Bt = padded(M, K, g), padded(N, K, g)
     ref = A.double() @ Bt.double().T
     for prec3 in (0, 1):
@@ -32,10 +32,10 @@ pd = 2056
 D = torch.empty(3008, pd, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 for prec3 in (0, 1):
-    for _ in range(3): L.golf_mss_gemm(A.data_ptr(), A.stride(0), Bt.data_ptr(), Bt.stride(0), D.data_ptr(), pd, 3008, 2054, 2053, 112, prec3, st)
+    for _ in range(3): L.golf_mss_gemm(A.data_ptr(), A.stride(0), Bt.data_ptr(), Bt.stride(0), D.data_ptr(), pd, 3008, 2054, 2053, 208, prec3, st)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(10): L.golf_mss_gemm(A.data_ptr(), A.stride(0), Bt.data_ptr(), Bt.stride(0), D.data_ptr(), pd, 3008, 2054, 2053, 112, prec3, st)
+    for _ in range(10): L.golf_mss_gemm(A.data_ptr(), A.stride(0), Bt.data_ptr(), Bt.stride(0), D.data_ptr(), pd, 3008, 2054, 2053, 208, prec3, st)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     fl = 2 * 3008 * 2054 * 2053 * (3 if prec3 else 1)
