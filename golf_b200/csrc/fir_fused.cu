@@ -14,9 +14,9 @@
 //   raw[d] = E[d] + O[d],  raw[255-d] = E[d] - O[d],   E / O = the even-k / odd-k halves of the series, d < 128.
 // That is two [frames x 128] x [128 x 128] matrix products per group of frames: a CTA designs the 8 frames it is
 // about to apply, thread d keeps 8 + 8 accumulators, the spectra sit in shared memory ([k][frame], broadcast reads) and
-// the cosine matrices (128 KB, coefficients 1/K and 2/K folded in, built once per device in double precision) stream
-// through L1.  32.8 k FMA per frame, a quarter of the 122 k FMA the FIR itself costs -- against 13 MB written and read
-// back plus three launches for the cuFFT route.
+// the cosine matrix entries are formed in registers by angle addition from two small tables (see g_design_aa below; the
+// first version streamed the whole 128 KB matrix through L1 / L2 once per CTA).  32.8 k FMA per frame, a quarter of the
+// 122 k FMA the FIR itself costs -- against 13 MB written and read back plus three launches for the cuFFT route.
 //
 // Noise.  With ex == NULL the strip is filled by Philox4x32-10 (counter = sample index / 4, utterance, call offset;
 // key = seed) + Box-Muller: same distribution as torch.randn, not the same stream -- opt-in (the exact-stream mode
@@ -36,18 +36,33 @@ constexpr int kDD = kDN / 2;           // 128 paired outputs d
 constexpr int kDFB = 8;                // frames (blocks) designed and applied per CTA
 constexpr int kDK20 = (kDK + kTapStep - 1) / kTapStep * kTapStep;  // 520
 
-// [parity][k'][d] = c_k cos(2 pi k d / K), k = 2k' + parity, c_0 = c_{N-1} = 1/K, else 2/K
-__device__ float g_design_cos[2][kDD][kDD];
+// Cosine matrix of the design, never stored whole (its 128 KB would stream through L1 / L2 once per CTA: 102 MB of L2 reads
+// per launch, the kernel's largest stall).  With k' = 16 kh + kl the entry for even k = 2k' is cos(A_h + A_l), A_h = 2 pi 16 kh d
+// / 255, A_l = 2 pi kl d / 255, and for odd k = 2k' + 1 it is cos(A_h + A_l + pi d / 255): a thread (fixed d) keeps cos / sin of
+// the 16 A_l, of the 16 (A_l + pi d / 255) -- scaled by 2/K -- in 64 registers and fetches cos / sin of A_h once per 16 terms.
+// [kind][index][d], kinds: 0 cos A_h, 1 sin A_h (index kh < 8), 2 / 3 cos / sin A_l, 4 / 5 cos / sin (A_l + pi d / 255); 48 KB,
+// built once per device in double precision.  (c_0 = c_{N-1} = 1/K instead of 2/K: the spectrum values of those two bins are
+// halved when they are staged.)
+__device__ float g_design_aa[6][16][kDD];
 static std::atomic<unsigned long long> g_design_ready{0};  // bit per device ordinal
 
 __global__ void design_table_kernel() {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 2 * kDD * kDD) return;
-  const int par = idx / (kDD * kDD), kp = (idx / kDD) % kDD, d = idx % kDD;
-  const int k = 2 * kp + par;
-  const int m = (k * d) % kDK;
-  const double c = (k == 0 || k == kDN - 1) ? 1.0 / kDK : 2.0 / kDK;
-  g_design_cos[par][kp][d] = (float)(c * cospi(2.0 * (double)m / (double)kDK));
+  if (idx >= 6 * 16 * kDD) return;
+  const int kind = idx / (16 * kDD), i = (idx / kDD) % 16, d = idx % kDD;
+  double v;
+  if (kind < 2) {
+    const int m = (16 * i * d) % kDH;  // A_h = 2 pi m / 255
+    v = kind == 0 ? cospi(2.0 * m / (double)kDH) : sinpi(2.0 * m / (double)kDH);
+    if (i >= 8) v = 0.0;
+  } else if (kind < 4) {
+    const int m = (i * d) % kDH;
+    v = (2.0 / kDK) * (kind == 2 ? cospi(2.0 * m / (double)kDH) : sinpi(2.0 * m / (double)kDH));
+  } else {
+    const int m = ((2 * i + 1) * d) % kDK;  // A_l + pi d / 255 = pi m / 255
+    v = (2.0 / kDK) * (kind == 4 ? cospi(m / (double)kDH) : sinpi(m / (double)kDH));
+  }
+  g_design_aa[kind][i][d] = (float)v;
 }
 
 static int ensure_design_table(cudaStream_t st) {
@@ -57,7 +72,7 @@ static int ensure_design_table(cudaStream_t st) {
   if ((g_design_ready.load(std::memory_order_acquire) >> dev) & 1ull) return GOLF_OK;
   // first use on this device: built on the caller's stream, ahead of the kernel that reads it (if that first use is
   // being captured into a CUDA graph the build is captured too and simply repeats on every replay)
-  design_table_kernel<<<ceil_div(2 * kDD * kDD, 256), 256, 0, st>>>();
+  design_table_kernel<<<ceil_div(6 * 16 * kDD, 256), 256, 0, st>>>();
   GOLF_CHECK_LAUNCH();
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
@@ -164,7 +179,7 @@ __global__ void __launch_bounds__(128) noise_fir_design_kernel(const float* __re
     const float* __restrict__ lm = log_mag + ((size_t)b * F + k0) * kDN;
     for (int i = tid; i < kDFB * kDN; i += 128) {
       const int f = i / kDN, k = i - f * kDN;
-      sx[k * kDFB + f] = f < nb ? expf(__ldg(lm + (size_t)f * kDN + k)) : 0.f;
+      sx[k * kDFB + f] = f < nb ? expf(__ldg(lm + (size_t)f * kDN + k)) * ((k == 0 || k == kDN - 1) ? 0.5f : 1.f) : 0.f;
     }
   }
   __syncthreads();
@@ -174,18 +189,27 @@ __global__ void __launch_bounds__(128) noise_fir_design_kernel(const float* __re
   for (int f = 0; f < kDFB; ++f) aE[f] = aO[f] = 0.f;
   {
     const int d = tid;
-    const float* __restrict__ cE = &g_design_cos[0][0][d];
-    const float* __restrict__ cO = &g_design_cos[1][0][d];
-#pragma unroll 4
-    for (int kp = 0; kp < kDD; ++kp) {
-      const float ce = __ldg(cE + kp * kDD), co = __ldg(cO + kp * kDD);
-      const float4* xe = reinterpret_cast<const float4*>(sx + (2 * kp) * kDFB);
-      const float4* xo = reinterpret_cast<const float4*>(sx + (2 * kp + 1) * kDFB);
-      const float4 e0 = xe[0], e1 = xe[1], o0 = xo[0], o1 = xo[1];
-      aE[0] = fmaf(ce, e0.x, aE[0]), aE[1] = fmaf(ce, e0.y, aE[1]), aE[2] = fmaf(ce, e0.z, aE[2]), aE[3] = fmaf(ce, e0.w, aE[3]);
-      aE[4] = fmaf(ce, e1.x, aE[4]), aE[5] = fmaf(ce, e1.y, aE[5]), aE[6] = fmaf(ce, e1.z, aE[6]), aE[7] = fmaf(ce, e1.w, aE[7]);
-      aO[0] = fmaf(co, o0.x, aO[0]), aO[1] = fmaf(co, o0.y, aO[1]), aO[2] = fmaf(co, o0.z, aO[2]), aO[3] = fmaf(co, o0.w, aO[3]);
-      aO[4] = fmaf(co, o1.x, aO[4]), aO[5] = fmaf(co, o1.y, aO[5]), aO[6] = fmaf(co, o1.z, aO[6]), aO[7] = fmaf(co, o1.w, aO[7]);
+    float cl[16], sl[16], clo[16], slo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      cl[i] = __ldg(&g_design_aa[2][i][d]), sl[i] = __ldg(&g_design_aa[3][i][d]);
+      clo[i] = __ldg(&g_design_aa[4][i][d]), slo[i] = __ldg(&g_design_aa[5][i][d]);
+    }
+#pragma unroll 1
+    for (int kh = 0; kh < kDD / 16; ++kh) {
+      const float ch = __ldg(&g_design_aa[0][kh][d]), sh = __ldg(&g_design_aa[1][kh][d]);
+#pragma unroll
+      for (int kl = 0; kl < 16; ++kl) {
+        const int kp = 16 * kh + kl;
+        const float ce = fmaf(ch, cl[kl], -sh * sl[kl]), co = fmaf(ch, clo[kl], -sh * slo[kl]);
+        const float4* xe = reinterpret_cast<const float4*>(sx + (2 * kp) * kDFB);
+        const float4* xo = reinterpret_cast<const float4*>(sx + (2 * kp + 1) * kDFB);
+        const float4 e0 = xe[0], e1 = xe[1], o0 = xo[0], o1 = xo[1];
+        aE[0] = fmaf(ce, e0.x, aE[0]), aE[1] = fmaf(ce, e0.y, aE[1]), aE[2] = fmaf(ce, e0.z, aE[2]), aE[3] = fmaf(ce, e0.w, aE[3]);
+        aE[4] = fmaf(ce, e1.x, aE[4]), aE[5] = fmaf(ce, e1.y, aE[5]), aE[6] = fmaf(ce, e1.z, aE[6]), aE[7] = fmaf(ce, e1.w, aE[7]);
+        aO[0] = fmaf(co, o0.x, aO[0]), aO[1] = fmaf(co, o0.y, aO[1]), aO[2] = fmaf(co, o0.z, aO[2]), aO[3] = fmaf(co, o0.w, aO[3]);
+        aO[4] = fmaf(co, o1.x, aO[4]), aO[5] = fmaf(co, o1.y, aO[5]), aO[6] = fmaf(co, o1.z, aO[6]), aO[7] = fmaf(co, o1.w, aO[7]);
+      }
     }
   }
   __syncthreads();  // every thread has read the spectra: the buffer becomes raw[f][0..255]
