@@ -410,31 +410,35 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
 // ---- framing / overlap-add -----------------------------------------------------------------------------------------------
 // frames[b * nfr + f][c] = xpad[f * hop + c] * w[c], xpad = reflect padding by n_fft / 2 (torch.stft center=True);
-// blockIdx.z selects the signal (0: x0 -> fr0, 1: x1 -> fr1); a thread writes 4 consecutive columns
+// blockIdx.z selects the signal (0: x0 -> fr0, 1: x1 -> fr1); a thread writes 4 consecutive columns of kFrRows rows
+constexpr int kFrRows = 8;
 __global__ void __launch_bounds__(128) mss_frames_kernel(const float* __restrict__ x0, int64_t x0_stride, float* __restrict__ fr0,
                                                          const float* __restrict__ x1, int64_t x1_stride, float* __restrict__ fr1,
-                                                         int64_t pitch, int L, int n_fft, int hop, int nfr) {
+                                                         int64_t pitch, int L, int n_fft, int hop, int nfr, int rows) {
   const int c0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
-  const int r = blockIdx.y;
   if (c0 >= n_fft) return;
   const float* __restrict__ x = blockIdx.z ? x1 : x0;
   const int64_t xs = blockIdx.z ? x1_stride : x0_stride;
   float* __restrict__ fr = blockIdx.z ? fr1 : fr0;
-  const int b = r / nfr, f = r - b * nfr;
-  const float* xb = x + (size_t)b * xs;
+  // periodic Hann (torch.hann_window(n_fft), scipy get_window("hann", n_fft)): 0.5 - 0.5 cos(2 pi c / n_fft)
   const float inv_n = 2.f / (float)n_fft;
-  float v[4];
+  float w[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = c0 + i;
-    int idx = f * hop + c - n_fft / 2;
-    if (idx < 0) idx = -idx;
-    if (idx >= L) idx = 2 * (L - 1) - idx;
-    // periodic Hann (torch.hann_window(n_fft), scipy get_window("hann", n_fft)): 0.5 - 0.5 cos(2 pi c / n_fft)
-    const float w = 0.5f - 0.5f * cospif((float)c * inv_n);
-    v[i] = c < n_fft ? __ldg(xb + idx) * w : 0.f;
+  for (int i = 0; i < 4; ++i) w[i] = c0 + i < n_fft ? 0.5f - 0.5f * cospif((float)(c0 + i) * inv_n) : 0.f;
+  const int r_end = min(rows, (int)(blockIdx.y + 1) * kFrRows);
+  for (int r = blockIdx.y * kFrRows; r < r_end; ++r) {
+    const int b = r / nfr, f = r - b * nfr;
+    const float* xb = x + (size_t)b * xs;
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int idx = f * hop + c0 + i - n_fft / 2;
+      if (idx < 0) idx = -idx;
+      if (idx >= L) idx = 2 * (L - 1) - idx;
+      v[i] = __ldg(xb + min(max(idx, 0), L - 1)) * w[i];
+    }
+    *reinterpret_cast<float4*>(fr + (size_t)r * pitch + c0) = make_float4(v[0], v[1], v[2], v[3]);  // pitch % 32 == 0: in bounds
   }
-  *reinterpret_cast<float4*>(fr + (size_t)r * pitch + c0) = make_float4(v[0], v[1], v[2], v[3]);  // pitch % 32 == 0: in bounds
 }
 
 // d_x[b][t] (+)= scale * sum over padded positions P that read x[t] and frames f covering P of dfr[b*nfr+f][P - f*hop] * w
@@ -659,8 +663,8 @@ GOLF_API int golf_mss_loss(const float* pred, int64_t pred_stride, const float* 
     const MssScale& s = sc[i];
     const float* fwd = tables[i];
     const float* bwd = tables[i] + (size_t)s.N * s.Kp;
-    const dim3 fgrid(ceil_div(s.n_fft, 512), s.rows, 2);
-    mss_frames_kernel<<<fgrid, 128, 0, st>>>(target, target_stride, fr_t, pred, pred_stride, fr_p, s.Kp, L, s.n_fft, s.hop, s.nfr);
+    const dim3 fgrid(ceil_div(s.n_fft, 512), ceil_div(s.rows, kFrRows), 2);
+    mss_frames_kernel<<<fgrid, 128, 0, st>>>(target, target_stride, fr_t, pred, pred_stride, fr_p, s.Kp, L, s.n_fft, s.hop, s.nfr, s.rows);
     GOLF_CHECK_LAUNCH();
     MssGemmParams p{};
     p.M = s.rows, p.N = s.N, p.K = s.n_fft, p.bn = s.bn_f, p.prec3 = (prec3 & 1) ? 1 : 0, p.chunk_kb = 4, p.alpha = alpha, p.eps = eps;
