@@ -562,9 +562,11 @@ def kernel_rooflines(dev, dec, dev_sets, G, AudioTensor):
     add("GOLF-ss chunk responses (pass 1)", ["ss_response_kernel"], lambda i: lpc(i, 1, False), (4 + ctl) * n,
         flops=2.0 * ORDER * (ORDER + 1) * n, note="reads ex + controls; its output (chunk transition blocks, 15 MB) is an L2-resident intermediate")
     lpc(0, 1, False)
-    add("GOLF-ss tail: two-level stitch + solve + refinement (cluster launch, passes 2-4)", ["ss_tail_kernel"], lambda i: lpc(i, 14, False),
+    tail_kernels = ["ss_tail_kernel"] if golf_b200_lib().golf_lpc_ss_get_tail() else ["ss_stitch_kernel", "ss_solve_sys_kernel"]
+    add("GOLF-ss tail: stitch + solve + adaptive refinement (passes 2-4" + (", one cluster launch)" if len(tail_kernels) == 1 else ", four light launches)"),
+        tail_kernels, lambda i: lpc(i, 14, False),
         (8 + ctl) * n, flops=2.0 * ORDER * n, note="reads ex + controls, writes y; timed on the chunk blocks of one response pass")
-    filt = add("GOLF-ss filter + room FIR (golf_lpc_ss_room_fwd: responses + tail)", ["ss_response_kernel", "ss_tail_kernel"],
+    filt = add("GOLF-ss filter + room FIR (golf_lpc_ss_room_fwd: responses + tail + room)", ["ss_response_kernel"] + tail_kernels + ([] if len(tail_kernels) == 1 else ["room_fir_kernel"]),
                lambda i: lpc(i, 15, True), (8 + ctl) * n, flops=2.0 * (ORDER * (ORDER + 1) + ORDER + 128) * n)
     add("oscillator (knot prefix + flow / 4x decimation)", ["osc_knot_prefix_q64_kernel", "osc_flow_v2_kernel"],
         lambda i: G.glottal_osc(dev_sets[i % N_SETS]["phase"], 1, dev_sets[i % N_SETS]["w"], 2400, osc.table, osc.decimater.kernel,

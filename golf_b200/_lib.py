@@ -27,6 +27,7 @@ _SIGS = {
     "golf_lpc_ss_fwd": (c_int, [P, c_int64, P, P, P, P] + [c_int] * 6 + [P, c_size_t, P]),
     "golf_lpc_ss_fwd_passes": (c_int, [P, c_int64, P, P, P, P] + [c_int] * 6 + [P, c_size_t, c_int, P]),
     "golf_lpc_ss_set_tail": (None, [c_int]),
+    "golf_lpc_ss_get_tail": (c_int, []),
     "golf_lpc_ss_set_response": (None, [c_int]),
     "golf_lpc_ss_get_response": (c_int, []),
     "golf_lpc_ss_room_workspace_bytes": (c_size_t, [c_int] * 5),

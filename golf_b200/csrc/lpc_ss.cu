@@ -318,6 +318,7 @@ GOLF_API int golf_lpc_ss_fwd(const float* ex, int64_t ex_stride, const float* ga
 GOLF_API void golf_lpc_ss_set_response(int mode) { g_ss_response_mode = mode == 1 ? 1 : 0; }
 GOLF_API int golf_lpc_ss_get_response(void) { return g_ss_response_mode; }
 
+GOLF_API int golf_lpc_ss_get_tail(void) { return g_ss_tail; }
 GOLF_API void golf_lpc_ss_set_tail(int mode) { g_ss_tail = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 
 GOLF_API size_t golf_lpc_ss_room_workspace_bytes(int B, int L, int M, int hop, int chunk) {

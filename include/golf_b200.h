@@ -113,6 +113,7 @@ int golf_lpc_ss_fwd_passes(const float *ex, int64_t ex_stride, const float *gain
  * (measured, profiles/README.md).  Same recurrences, different grouping of the state propagation (results agree to
  * float32 rounding).  Process-wide. */
 void golf_lpc_ss_set_tail(int mode);
+int golf_lpc_ss_get_tail(void);
 /* Pass 1 (chunk responses) at padded order 24 (orders 21..24, chunk a multiple of 8 samples, forward form): mode 0
  * (default) the FP32 kernel, 1 the mma.sync TF32 tensor-core kernel with error-compensated (3 x TF32) products.  An opt-in
  * experiment: on B200 it is slower (83 vs 74 us at B = 32 x 2 s) and its transition matrices are ~10x less accurate, so the
