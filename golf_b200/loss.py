@@ -95,12 +95,23 @@ def mss_loss(pred, target, n_ffts: Sequence[int], alpha: float = 1.0, ratio: flo
     return _MSS.apply(pred, target, tuple(int(n) for n in n_ffts), tuple(hops), float(alpha), float(ratio), float(eps), int(precision))
 
 
+_SPECTROGRAM_DEFAULTS = {"win_length": None, "pad": 0, "normalized": False, "wkwargs": None, "center": True, "pad_mode": "reflect",
+                         "onesided": True, "return_complex": None, "power": 1}
+
+
 def _check_window(window: str, kwargs: dict):
+    """the kernels implement torchaudio.transforms.Spectrogram at its defaults (the only way the reference's configs call it:
+    cfg/ae/vctk.yaml:58-67, ckpts/ismir23/*/config.yaml `criterion`); explicit arguments are accepted when they say the same"""
     if window not in ("hann", "hanning"):
         raise ValueError(f"golf_b200.loss: only the Hann window is built into the kernels (got {window!r})")
-    extra = set(kwargs) - {"n_fft", "hop_length"}
-    if extra:
-        raise ValueError(f"golf_b200.loss: unsupported Spectrogram arguments {sorted(extra)}")
+    for k, v in kwargs.items():
+        if k in ("n_fft", "hop_length"):
+            continue
+        if k not in _SPECTROGRAM_DEFAULTS:
+            raise ValueError(f"golf_b200.loss: unsupported Spectrogram argument {k!r}")
+        ok = v == _SPECTROGRAM_DEFAULTS[k] or (k == "onesided" and v is None) or (k == "win_length" and v == kwargs.get("n_fft"))
+        if not ok:
+            raise ValueError(f"golf_b200.loss: Spectrogram argument {k}={v!r} differs from the default the kernels implement")
 
 
 class SSSLoss(nn.Module):

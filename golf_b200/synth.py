@@ -166,7 +166,12 @@ class DownsampledIndexedGlottalFlowTable(IndexedGlottalFlowTable):
         self.model = get_downsampler(hop_rate, in_channels, 1)
 
         def trsfm(h):
-            w = self.model(plain(h).transpose(1, 2)).squeeze(1).sigmoid()
-            return (like(h, w, hop_of(h) * self.hop_rate),)
+            x = plain(h).transpose(1, 2)
+            if x.is_cuda:  # float32 products like the reference's CPU path (cuDNN would run these 1x1 convolutions in TF32)
+                with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                    w = self.model(x)
+            else:
+                w = self.model(x)
+            return (like(h, w.squeeze(1).sigmoid(), hop_of(h) * self.hop_rate),)
 
         self.ctrl = wrap_ctrl_fn(split_size=(in_channels,), trsfm_fn=trsfm)

@@ -1,0 +1,110 @@
+"""Golden vectors for the two other shipped decoder families, produced by the UNMODIFIED reference with the real checkpoints:
+
+  decoder_v1.npz     ckpts/interspeech24/golf-v1 -- HarmonicPlusNoiseSynth (models/hpn.py:31-57), harmonic branch through
+                     LTVMinimumPhaseFilter (rc2lpc, hanning 960, hop 240), noise branch through the zero-phase FIR
+  decoder_ismir.npz  ckpts/ismir23/glottal_d_f1 (converted checkpoint) -- HarmonicPlusNoiseSynth with BOTH branches through
+                     LTVMinimumPhaseFilter(lpc_parameterisation="coef", max_abs_value 0.99, window 480, hop 120,
+                     centred=False), table from the iterative LF fit (lf v1), no oversampling
+
+    python tests/golden/make_golden_decoders.py          (build container only: needs /root/reference)
+
+Controls: smooth synthetic encoder logits pushed through the decoder's OWN .ctrl transforms (split sizes and transforms
+from decoder.split_sizes_and_trsfms, as VocoderParameterEncoderInterface does), f0 at frame rate, noise injected.  Stored:
+the logits, the transformed controls, the noise draw, the output, and the small learned parameters."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+import yaml
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from oracle import refimport  # noqa: E402
+from make_golden import np32, smooth  # noqa: E402
+
+
+def inst(c):
+    from importlib import import_module
+
+    if isinstance(c, dict):
+        c = {k: inst(v) for k, v in c.items()}
+        if "class_path" in c:
+            mod, cls = c["class_path"].rsplit(".", 1)
+            return getattr(import_module(mod), cls)(**c.get("init_args", {}))
+    return c
+
+
+@torch.no_grad()
+def run(name, cfg_path, ckpt_path, hop, seconds, out_name, scale):
+    from models.audiotensor import AudioTensor
+    from models.noise import NoiseInterface
+
+    cfg = yaml.safe_load(open(cfg_path))["model"]
+    cfg = cfg.get("init_args", cfg)
+    dec = inst(cfg["decoder"]).eval()
+    sd = torch.load(ckpt_path, map_location="cpu", weights_only=True)["state_dict"]
+    res = dec.load_state_dict({k[8:]: v for k, v in sd.items() if k.startswith("decoder.")}, strict=False)
+    print(name, res)
+    sizes, trsfms, keys = dec.split_sizes_and_trsfms
+    torch.manual_seed(2434)
+    B, T = 2, int(seconds * 24000)
+    F = T // hop + 1
+    out = {"hop": hop, "keys": np.array(keys), "sizes": np.array([len(s) for s in sizes])}
+    params = {}
+    for key, grp, fn in zip(keys, sizes, trsfms):
+        # filter logits stay moderate (random trajectories at larger scales are unstable or wildly resonant)
+        logits = [(0.15 if "filter" in key and n > 1 and n < 100 else scale) * smooth(torch.randn(B, F, n)) - (3.0 if n == 1 else 0.0) for n in grp]
+        args = [AudioTensor(l.squeeze(2) if n == 1 else l, hop_length=hop) for l, n in zip(logits, grp)]
+        vals = fn(*args)
+        params[key] = vals
+        for i, (l, v) in enumerate(zip(logits, vals)):
+            out[f"{key}_logits{i}"] = np32(l)
+        for i, v in enumerate(vals):
+            out[f"{key}_{i}"] = np32(v.as_tensor())
+            out[f"{key}_{i}_hop"] = v.hop_length
+    f0 = 110.0 + 60.0 * torch.sigmoid(smooth(torch.randn(B, F)))
+    phase = AudioTensor(f0 / 24000.0, hop_length=hop)
+    out["phase"] = np32(phase.as_tensor())
+    harm = dec.harm_oscillator(phase, *params["harm_oscillator_params"])
+    noise = torch.randn_like(harm.as_tensor())
+    out["noise"] = np32(noise)
+
+    class Fixed(NoiseInterface):
+        def __init__(self):
+            super().__init__(torch.distributions.Normal(0, 1))
+
+        def forward(self, ref, *a):
+            return AudioTensor(noise[:, : ref.shape[1]])
+
+    dec.noise_generator = Fixed()
+    y = dec(phase=phase, **params)
+    out["out"] = np32(y.as_tensor())
+    out["harm"] = np32(harm.as_tensor())
+    for k, v in dec.state_dict().items():
+        if v.numel() <= 20000:
+            out["sd_" + k] = np32(v)
+    for k_ in ("harm", "out"):
+        print(name, k_, "finite", bool(np.isfinite(out[k_]).all()))
+    print(name, "out", tuple(y.shape), "rms", float(y.as_tensor().square().mean().sqrt()), "max", float(y.as_tensor().abs().max()))
+    np.savez(os.path.join(HERE, out_name), **out)
+
+
+def main():
+    refimport.import_reference()
+    R = refimport.REF_ROOT
+    v1 = os.path.join(R, "ckpts", "interspeech24", "golf-v1")
+    ck = os.path.join(v1, "checkpoints", sorted(os.listdir(os.path.join(v1, "checkpoints")))[0])
+    run("golf-v1", os.path.join(v1, "config.yaml"), ck, 240, 1.0, "decoder_v1.npz", 0.5)
+    ism = os.path.join(R, "ckpts", "ismir23", "glottal_d_f1")
+    run("ismir23", os.path.join(ism, "config.yaml"), os.path.join(ism, "epoch=2669-step=792990_converted.ckpt"), 120, 1.0,
+        "decoder_ismir.npz", 0.5)
+
+
+if __name__ == "__main__":
+    main()
