@@ -34,6 +34,7 @@ _SIGS = {
     "golf_lpc_ss_room_fwd": (c_int, [P, c_int64, P, P, P, P, c_int, P, P] + [c_int] * 7 + [P, c_size_t, P]),
     "golf_lpc_ss_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
     "golf_lpc_ss_bwd": (c_int, [P, P, P, c_int64, P, P, P, P, P, P, P] + [c_int] * 7 + [P, c_size_t, P]),
+    "golf_lpc_ff_set_exact_order": (None, [c_int]),
     "golf_lpc_ff_fwd": (c_int, [P, c_int64, P, P, P, P] + [c_int] * 6 + [P]),
     "golf_lpc_ff_bwd_workspace_bytes": (c_size_t, [c_int] * 5),
     "golf_lpc_ff_bwd": (c_int, [P, P, c_int64, P, P, P, P, c_int64, P, P] + [c_int] * 6 + [P, c_size_t, P]),

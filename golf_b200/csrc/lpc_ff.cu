@@ -408,8 +408,22 @@ static int dispatch_ff_bwd(int mp, const FfParams& pf, const FfParams& pb, cudaS
   }
 }
 
+std::atomic<int> g_ff_exact{0};  // 1: forward filters reproduce libtorchaudio's CPU summation order (golf_lpc_ff_set_exact_order)
+
 template <bool STORE_V>
 static int dispatch_ff_fwd(int M, const FfParams& p, cudaStream_t st) {
+  if constexpr (!STORE_V) {
+    if (g_ff_exact.load()) {
+      if (M <= 4) return launch_ff_fwd<AllPole<4, true>, false>(p, st);
+      if (M <= 8) return launch_ff_fwd<AllPole<8, true>, false>(p, st);
+      if (M <= 12) return launch_ff_fwd<AllPole<12, true>, false>(p, st);
+      if (M <= 16) return launch_ff_fwd<AllPole<16, true>, false>(p, st);
+      if (M <= 20) return launch_ff_fwd<AllPole<20, true>, false>(p, st);
+      if (M <= 24) return launch_ff_fwd<AllPole<24, true>, false>(p, st);
+      if (M <= 32) return launch_ff_fwd<AllPole<32, true>, false>(p, st);
+      return launch_ff_fwd<AllPole<40, true>, false>(p, st);
+    }
+  }
   if (M <= 4) return launch_ff_fwd<AllPole<4>, STORE_V>(p, st);
   if (M <= 8) return launch_ff_fwd<AllPole<8>, STORE_V>(p, st);
   if (M <= 12) return launch_ff_fwd<AllPole<12>, STORE_V>(p, st);
@@ -423,6 +437,8 @@ static int dispatch_ff_fwd(int M, const FfParams& p, cudaStream_t st) {
 }  // namespace golf
 
 using namespace golf;
+
+GOLF_API void golf_lpc_ff_set_exact_order(int on) { g_ff_exact = on ? 1 : 0; }
 
 GOLF_API int golf_lpc_ff_fwd(const float* ex, int64_t ex_stride, const float* gain, const float* a, const float* window,
                              float* y, int B, int T_ex, int F, int M, int hop, int win, void* stream) {

@@ -25,7 +25,10 @@ struct FfParams {
 };
 
 // ---- per-frame filters ------------------------------------------------------------
-template <int MP>
+// EXACT: libtorchaudio's CPU arithmetic bit for bit -- one accumulator, taps oldest first, a rounded multiply and a rounded
+// subtract per tap (oracle/golf_oracle.c: oracle_allpole_lti_f32, pinned bitwise against torchaudio.functional.lfilter); the
+// default sums three interleaved FMA chains (a third of the dependent latency, float32 rounding in a different order).
+template <int MP, bool EXACT = false>
 struct AllPole {
   static constexpr int TILE = MP;
   float na[MP];  // na[j] = -a[MP-1-j]: index j pairs with the output MP-j steps back (oldest first)
@@ -41,6 +44,13 @@ struct AllPole {
   }
   template <int S>
   __device__ __forceinline__ float step(float x) {
+    if (EXACT) {
+      float acc = x;
+#pragma unroll
+      for (int j = 0; j < MP; ++j) acc = __fadd_rn(acc, __fmul_rn(na[j], h[(S + j) % MP]));  // acc - a*y: the negation is exact
+      h[S] = acc;
+      return acc;
+    }
     float acc0 = x, acc1 = 0.f, acc2 = 0.f;
 #pragma unroll
     for (int j = 0; j < MP - 1; ++j) {  // y[n-MP+j] sits in slot (S+j)%MP

@@ -144,6 +144,10 @@ int golf_lpc_ss_bwd(const float *gy, const float *y, const float *ex, int64_t ex
  * n_frames = (L_e + 2*(win/2) - win)/hop + 1 <= F where L_e = min(T_ex,(F-1)*hop+1);
  * y [B, (n_frames-1)*hop].  Requires win == 4*hop (the reference's shipped ratio).
  * window: [win] device array (the module's window buffer). */
+/* 1: the per-frame recurrences of golf_lpc_ff_fwd / golf_lpc_frames_fwd sum their taps exactly like libtorchaudio's CPU loop
+ * (one accumulator, oldest tap first, rounded multiply then rounded subtract): per frame bit-identical to
+ * torchaudio.functional.lfilter, ~2.5x the dependent latency.  0 (default): three interleaved FMA chains.  Process-wide. */
+void golf_lpc_ff_set_exact_order(int on);
 int golf_lpc_ff_fwd(const float *ex, int64_t ex_stride, const float *gain, const float *a,
                     const float *window, float *y, int B, int T_ex, int F, int M, int hop,
                     int win, void *stream);

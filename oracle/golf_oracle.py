@@ -203,17 +203,22 @@ def _overlap_add(frames: torch.Tensor, win: torch.Tensor, hop: int, p: int) -> t
     B, n_frames, W = frames.shape
     full = (n_frames - 1) * hop + W
     pos = (torch.arange(n_frames)[:, None] * hop + torch.arange(W)[None, :]).reshape(-1)
-    acc = torch.zeros(B, full)
+    win = win.to(frames.dtype)
+    acc = torch.zeros(B, full, dtype=frames.dtype)
     acc.index_add_(1, pos, (frames * win).reshape(B, -1))
-    norm = torch.zeros(full)
+    norm = torch.zeros(full, dtype=frames.dtype)
     norm.index_add_(0, pos, win.repeat(n_frames))
     out_len = full - 2 * p
     return acc[:, p : p + out_len] / norm[p : p + out_len]
 
 
-def lpc_ff(ex, gain, a, hop: int, window_length: int, centred: bool = True, window: str = "hanning") -> torch.Tensor:
-    """LTVMinimumPhaseFilter.forward, models/filters.py:131-184."""
-    ex, gain, a = _f32(ex), _f32(gain), _f32(a)
+def lpc_ff(ex, gain, a, hop: int, window_length: int, centred: bool = True, window: str = "hanning", double: bool = False) -> torch.Tensor:
+    """LTVMinimumPhaseFilter.forward, models/filters.py:131-184.  double=True: the same computation in float64 (truth for the
+    float32 floor of resonant frames; returns float64)."""
+    if double:
+        ex, gain, a = (t.detach().to("cpu", torch.float64) for t in (ex, gain, a))
+    else:
+        ex, gain, a = _f32(ex), _f32(gain), _f32(a)
     assert window_length >= 2 * hop
     if not centred:
         ex = ex[:, hop // 2 :]

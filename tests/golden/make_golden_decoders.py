@@ -41,7 +41,7 @@ def inst(c):
 
 
 @torch.no_grad()
-def run(name, cfg_path, ckpt_path, hop, seconds, out_name, scale):
+def run(name, cfg_path, ckpt_path, hop, seconds, out_name, scale, filter_scale=0.15):
     from models.audiotensor import AudioTensor
     from models.noise import NoiseInterface
 
@@ -59,7 +59,7 @@ def run(name, cfg_path, ckpt_path, hop, seconds, out_name, scale):
     params = {}
     for key, grp, fn in zip(keys, sizes, trsfms):
         # filter logits stay moderate (random trajectories at larger scales are unstable or wildly resonant)
-        logits = [(0.15 if "filter" in key and n > 1 and n < 100 else scale) * smooth(torch.randn(B, F, n)) - (3.0 if n == 1 else 0.0) for n in grp]
+        logits = [(filter_scale if "filter" in key and n > 1 and n < 100 else scale) * smooth(torch.randn(B, F, n)) - (3.0 if n == 1 else 0.0) for n in grp]
         args = [AudioTensor(l.squeeze(2) if n == 1 else l, hop_length=hop) for l, n in zip(logits, grp)]
         vals = fn(*args)
         params[key] = vals
@@ -103,7 +103,9 @@ def main():
     run("golf-v1", os.path.join(v1, "config.yaml"), ck, 240, 1.0, "decoder_v1.npz", 0.5)
     ism = os.path.join(R, "ckpts", "ismir23", "glottal_d_f1")
     run("ismir23", os.path.join(ism, "config.yaml"), os.path.join(ism, "epoch=2669-step=792990_converted.ckpt"), 120, 1.0,
-        "decoder_ismir.npz", 0.5)
+        "decoder_ismir.npz", 0.5, filter_scale=0.06)  # eleven `coef` sections: larger logits ring 45x above the signal's RMS and make
+    # float32 outputs depend on 1e-6 changes of the coefficients at the 1e-3 level (measured: the reference's own output then sits
+    # 3e-4 from float64)
 
 
 if __name__ == "__main__":

@@ -82,3 +82,52 @@ def test_decoder_family_reference_golden(which):
         out = dec(phase=AudioTensor(T(g["phase"]).to(DEV), hop_length=hop), **params)
     assert out.hop_length == 1 and tuple(out.shape) == tuple(g["out"].shape)
     assert rel_rms(out.as_tensor(), T(g["out"])) < REL_TOL
+    if which == "ismir":  # and with the filters in libtorchaudio's summation order
+        from golf_b200 import _lib
+
+        L = _lib.lib()
+        L.golf_lpc_ff_set_exact_order(1)
+        try:
+            with torch.no_grad():
+                out_exact = dec(phase=AudioTensor(T(g["phase"]).to(DEV), hop_length=hop), **params)
+        finally:
+            L.golf_lpc_ff_set_exact_order(0)
+        assert rel_rms(out_exact.as_tensor(), T(g["out"])) < REL_TOL
+
+
+def test_ff_exact_order_is_bitwise_torchaudio_per_frame(oracle):
+    """golf_lpc_ff_set_exact_order(1): every frame's recurrence is libtorchaudio's CPU loop bit for bit (through
+    lpc_synthesis-shaped frames: window length == hop count of one frame is not expressible, so the check goes through
+    golf_lpc_frames_fwd with a rectangular window and non-overlapping frames, where the OLA is the identity)"""
+    from golf_b200 import _lib, functional as G
+
+    gen = torch.Generator().manual_seed(11)
+    B, hop, M = 3, 240, 22
+    Fr = 12
+    ex = torch.randn(B, Fr * hop, generator=gen)
+    gain = torch.rand(B, Fr, generator=gen) + 0.5
+    a = oracle.rc2lpc(torch.tanh(0.4 * torch.randn(B, Fr, M, generator=gen)))
+    # frames of 2*hop every hop, rectangular window: out = (y_k second half + y_{k+1} first half) / 2 in the interior;
+    # compare the kernel in both orders with the same composition of the bit-exact oracle loop
+    win = torch.ones(2 * hop)
+    pad = hop // 2
+    fr = torch.nn.functional.pad(ex, (pad, pad)).unfold(1, 2 * hop, hop) * gain[:, : Fr, None][:, : (ex.shape[1] + 2 * pad - 2 * hop) // hop + 1]
+    nfr = fr.shape[1]
+    yk = oracle.allpole_lti(fr.reshape(B * nfr, 2 * hop).contiguous(), a[:, :nfr].reshape(B * nfr, M)).view(B, nfr, 2 * hop)
+    full = torch.zeros(B, (nfr - 1) * hop + 2 * hop)
+    norm = torch.zeros((nfr - 1) * hop + 2 * hop)
+    for k in range(nfr):
+        full[:, k * hop : k * hop + 2 * hop] += yk[:, k]
+        norm[k * hop : k * hop + 2 * hop] += 1
+    ref = (full / norm)[:, pad : pad + (nfr - 1) * hop + 2 * hop - 2 * pad]
+    L = _lib.lib()
+    L.golf_lpc_ff_set_exact_order(1)
+    try:
+        y_exact = G.lpc_frames(ex.to(DEV), gain.to(DEV), a.to(DEV), win.to(DEV), hop)
+    finally:
+        L.golf_lpc_ff_set_exact_order(0)
+    y_fast = G.lpc_frames(ex.to(DEV), gain.to(DEV), a.to(DEV), win.to(DEV), hop)
+    assert y_exact.shape == ref.shape
+    # single-frame regions (the first and last half hop... none here) aside, sums of two bit-identical frames divided by 2
+    assert torch.equal(y_exact.cpu(), ref), float((y_exact.cpu() - ref).abs().max())
+    assert rel_rms(y_fast, ref) < 1e-5 and not torch.equal(y_fast.cpu(), ref)
