@@ -12,9 +12,9 @@
 //                       shared-memory ring, tcgen05.mma.kind::tf32 issued by one thread, accumulator in TMEM, read back with
 //                       tcgen05.ld by four epilogue warps.  Warp roles: 0 TMA producer, 1 MMA issuer (+ TMEM allocation),
 //                       2..5 splitter during the main loop, epilogue afterwards.
-//                       Float32-grade products (the log-magnitude term reads bins 60 dB below a frame's peak): the splitter
-//                       warps round every operand to TF32 in place (hi) and write lo = x - hi (exact) into a second pair of
-//                       tiles in the SAME swizzled layout; every k-step issues hi*hi + lo*hi + hi*lo.
+//                       Float32-grade products (the log-magnitude term reads bins 60 dB below a frame's peak): the tensor
+//                       core reads the top 19 bits of an operand (hi); the splitter warps write lo = rna_tf32(x - hi) into a
+//                       second pair of tiles in the SAME swizzled layout; every k-step issues hi*hi + lo*hi + hi*lo.
 //                       Epilogues: magnitudes of the target (mode 0); loss terms + d loss / d(re, im) for the prediction
 //                       (mode 1: the two signals' spectra never exist in HBM as complex tensors); plain store (mode 2, adjoint).
 //   mss_ola_kernel      adjoint of framing + window + reflect padding: gather, no atomics
@@ -240,37 +240,36 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegSplit));
     if (p.prec3) {
       const int st_tid = threadIdx.x - 128;  // 0..127
-      const int nA = kBM * kBK / 4, nB = p.bn * kBK / 4;  // float4 counts
-      // hi = x rounded to nearest TF32 (written back in place: the tensor core would otherwise TRUNCATE x to its top 19
-      // bits), lo = x - hi exactly (|lo| <= 2^-12 |x|, 12 significant bits of which the tensor core keeps 11)
-      auto split = [](float x, float& hi, float& lo) {
+      // The tensor core reads the top 19 bits of an fp32 operand, i.e. hi = x truncated to TF32, for free; the remainder
+      // x - hi is exact in fp32 (13 significant bits) and is stored ROUNDED to TF32 (cvt.rna), so what the tensor core then
+      // truncates away of it is nothing: x = hi + lo to 2^-22 |x|, unbiased.  (Writing a rounded hi back in place as well was
+      // 2x closer still but cost a third more shared-memory traffic -- the resource this kernel is bound by: TMA fill +
+      // splitter + three operand reads per MMA.)
+      auto lo_of = [](float x) {
+        const float r = __fsub_rn(x, __uint_as_float(__float_as_uint(x) & 0xffffe000u));
         uint32_t h;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-        hi = __uint_as_float(h);
-        lo = __fsub_rn(x, hi);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(r));
+        return __uint_as_float(h);
       };
+      const int nb16 = p.bn >> 4;  // B: 8 float4 per row, 128 threads -> bn / 16 float4 per thread
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(full + s, (it / kStages) & 1);
-          float4* a = reinterpret_cast<float4*>(tiles + s * kStageBytes);
-          float4* al = reinterpret_cast<float4*>(tiles + s * kStageBytes + kTileA);
-          float4* b = reinterpret_cast<float4*>(tiles + s * kStageBytes + 2 * kTileA);
-          float4* bl = reinterpret_cast<float4*>(tiles + s * kStageBytes + 2 * kTileA + kTileB);
-#pragma unroll 4
-          for (int i = st_tid; i < nA; i += 128) {
-            const float4 v = a[i];
-            float4 h, l;
-            split(v.x, h.x, l.x), split(v.y, h.y, l.y), split(v.z, h.z, l.z), split(v.w, h.w, l.w);
-            a[i] = h, al[i] = l;
+          const float4* a = reinterpret_cast<const float4*>(tiles + s * kStageBytes) + st_tid;
+          float4* al = reinterpret_cast<float4*>(tiles + s * kStageBytes + kTileA) + st_tid;
+          const float4* b = reinterpret_cast<const float4*>(tiles + s * kStageBytes + 2 * kTileA) + st_tid;
+          float4* bl = reinterpret_cast<float4*>(tiles + s * kStageBytes + 2 * kTileA + kTileB) + st_tid;
+#pragma unroll
+          for (int i = 0; i < kBM * kBK / 4 / 128; ++i) {
+            const float4 v = a[128 * i];
+            al[128 * i] = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
           }
 #pragma unroll 4
-          for (int i = st_tid; i < nB; i += 128) {
-            const float4 v = b[i];
-            float4 h, l;
-            split(v.x, h.x, l.x), split(v.y, h.y, l.y), split(v.z, h.z, l.z), split(v.w, h.w, l.w);
-            b[i] = h, bl[i] = l;
+          for (int i = 0; i < nb16; ++i) {
+            const float4 v = b[128 * i];
+            bl[128 * i] = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
           }
           fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
           mbar_arrive(ready + s);
