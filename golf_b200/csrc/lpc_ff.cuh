@@ -26,7 +26,7 @@ struct FfParams {
 
 // ---- per-frame filters ------------------------------------------------------------
 // EXACT: libtorchaudio's CPU arithmetic bit for bit -- one accumulator, taps oldest first, a rounded multiply and a rounded
-// subtract per tap (oracle/golf_oracle.c: oracle_allpole_lti_f32, pinned bitwise against torchaudio.functional.lfilter); the
+// subtract per tap (the arithmetic the test-suite pins bitwise against torchaudio.functional.lfilter on the CPU); the
 // default sums three interleaved FMA chains (a third of the dependent latency, float32 rounding in a different order).
 template <int MP, bool EXACT = false>
 struct AllPole {
