@@ -102,6 +102,9 @@ __device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y
 #ifndef GOLF_RESP_WPB
 #define GOLF_RESP_WPB 4  // warps per CTA: they meet at a barrier every tile, which keeps them in the same part of the 48 KB loop body (81 -> 77 us; 8 per CTA: the same)
 #endif
+#ifndef GOLF_RESP_RES_BIG
+#define GOLF_RESP_RES_BIG 8  // resident warps per SM the padded orders 32 / 40 are compiled for (4: 255 registers, one CTA)
+#endif
 template <int MP>
 struct RespCfg {
   static constexpr int NC = (MP == 24) ? GOLF_RESP_NC : 4;  // columns per lane
@@ -109,7 +112,7 @@ struct RespCfg {
 #ifdef GOLF_RESP_RES
   static constexpr int RES = MP > 24 ? 4 : GOLF_RESP_RES;
 #else
-  static constexpr int RES = MP > 24 ? 4 : (NC <= 4 ? 12 : 8);
+  static constexpr int RES = MP > 24 ? GOLF_RESP_RES_BIG : (NC <= 4 ? 12 : 8);
 #endif
 };
 
@@ -936,10 +939,18 @@ int launch_mp(const SsParams& p, bool generic, int passes, cudaStream_t st) {
   if (nresp > 0 && (passes & 1)) {
     constexpr int MTS = MP >= 8 ? MP - 2 : MP;  // short-tap variant for M <= MP - 2
     int rc;
-    if (p.M <= MTS)
+    if constexpr (MP == 40) {  // order 25..32 at hops that 32 does not divide (240, 120) runs at padded order 40: 32 taps, not 38
+      if (p.M <= 32)
+        rc = launch_response<MP, 32, FORM>(p, st);
+      else if (p.M <= MTS)
+        rc = launch_response<MP, MTS, FORM>(p, st);
+      else
+        rc = launch_response<MP, MP, FORM>(p, st);
+    } else if (p.M <= MTS) {
       rc = launch_response<MP, MTS, FORM>(p, st);
-    else
+    } else {
       rc = launch_response<MP, MP, FORM>(p, st);
+    }
     if (rc) return rc;
   }
   if constexpr (FORM == 0 && MP >= 16 && MP % 8 == 0 && MP <= 32) {
@@ -948,12 +959,14 @@ int launch_mp(const SsParams& p, bool generic, int passes, cudaStream_t st) {
   const size_t sm_stitch =
       ((size_t)kStitchStages * kStitchGroup * ((MP + 1) * MP + 2 * MP) + 2 * MP) * sizeof(float) + kStitchStages * 8 + 128;
   constexpr int MCS = MP >= 8 ? MP - 2 : 0;  // compile-time column counts: M == MP - 2 and M == MP
-  const int mc = p.M == MP ? MP : (MCS && p.M == MCS ? MCS : 0);
+  constexpr int MC8 = MP == 40 ? 32 : 0;     // ... and order 32 at padded order 40 (the run-time-M walk is 6x slower: 174 vs 27 us)
+  const int mc = p.M == MP ? MP : (MCS && p.M == MCS ? MCS : (MC8 && p.M == MC8 ? MC8 : 0));
   static unsigned long long attr2 = 0;
   if (first_use_on_device(attr2)) {
     GOLF_CUDA(cudaFuncSetAttribute(ss_stitch_kernel<MP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stitch));
     GOLF_CUDA(cudaFuncSetAttribute(ss_stitch_kernel<MP, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stitch));
     if (MCS) GOLF_CUDA(cudaFuncSetAttribute(ss_stitch_kernel<MP, (MCS ? MCS : MP)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stitch));
+    if (MC8) GOLF_CUDA(cudaFuncSetAttribute(ss_stitch_kernel<MP, (MC8 ? MC8 : MP)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stitch));
     mark_used_on_device(attr2);
   }
   const int G = ceil_div(p.C, 32);
@@ -983,6 +996,8 @@ int launch_mp(const SsParams& p, bool generic, int passes, cudaStream_t st) {
     if (refine || (passes & 2)) {
       if (mc == MP)
         ss_stitch_kernel<MP, MP><<<p.B, 32, sm_stitch, st>>>(p, refine ? 1 : 0);
+      else if (MC8 && mc == MC8)
+        ss_stitch_kernel<MP, (MC8 ? MC8 : MP)><<<p.B, 32, sm_stitch, st>>>(p, refine ? 1 : 0);
       else if (mc != 0)
         ss_stitch_kernel<MP, (MCS ? MCS : MP)><<<p.B, 32, sm_stitch, st>>>(p, refine ? 1 : 0);
       else
