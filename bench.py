@@ -584,7 +584,9 @@ def kernel_rooflines(dev, dec, dev_sets, G, AudioTensor):
             "fp32": {"tflops": filt["fp32_tflops"], "peak_tflops": FP32_PEAK_TFLOPS, "frac": filt["frac_fp32"],
                      "peak_source": "148 SMs x 128 FMA/clk x 1.965 GHz x 2"},
             "note": "FP32-issue / latency bound by design (M(M+1) FMA per sample buys the time-parallel split; see DESIGN.md 3.1): "
-                    "frac is against the HBM peak on SURVEY 8(d)'s 8.383 B/sample",
+                    "frac is against the HBM peak on SURVEY 8(d)'s 8.383 B/sample; traffic sums the kernels' DRAM bytes from the committed "
+                    "`ncu --set full` capture, which flushes the caches before every launch -- in a pass's natural cache state the "
+                    "15 MB of chunk blocks between the kernels stay in L2 and the same kernels move about 17 MB (profiles/r2_dram_per_pass.txt)",
             "kernels": entries}
     return roof
 
