@@ -75,6 +75,7 @@ _SIGS = {
     "golf_glottal_osc_fwd": (c_int, [P, P, P, P, P] + [c_int] * 11 + [P, c_size_t, P]),
     "golf_glottal_osc_fwd_from": (c_int, [P, P, P, P, P, P] + [c_int] * 11 + [P, c_size_t, P]),
     "golf_glottal_osc_bwd_w": (c_int, [P, P, P, P, P, P] + [c_int] * 11 + [P, c_size_t, P]),
+    "golf_glottal_osc_bwd": (c_int, [P, P, P, P, P, P, P] + [c_int] * 11 + [P, c_size_t, P]),
     "golf_wavetable_read_fwd": (c_int, [P, P, P] + [c_int] * 5 + [P]),
     "golf_linear_upsample": (c_int, [P, P, c_int, c_int, c_int, P]),
     "golf_rc2lpc_fwd": (c_int, [P, P, c_int, c_int, c_float, P]),

@@ -552,6 +552,7 @@ struct OscBwdParams {
   const float* w;       // [B, Fw]
   const float* table;   // [n_tab, P]
   float* d_w;           // [B, Fw], zero-initialised
+  float* d_table;       // [n_tab, P], zero-initialised (table adjoint only)
   int n_tab;
 };
 
@@ -641,13 +642,20 @@ __global__ void __launch_bounds__(128) osc_dw_kernel(OscBwdParams q) {
 // row = t / hop_tab by one compare); the knot setup is done once per output index and the phase advances by
 // integer increments over its `os` samples; the three per-row sums are reduced by shuffles, one shared-memory
 // atomic per warp and row, one global atomic per CTA and row.
-template <int OS>
+//
+// TABLE = true is the adjoint w.r.t. the wavetable itself (IndexedGlottalFlowTable(trainable=True), models/synth.py:
+// the table is an nn.Parameter there).  The output is bilinear in the table, so every oversampled sample scatters
+// g * {1-fy, fy} * {1-p, p} * {1-fx, fx} onto 8 table entries.  The tile touches at most kOscRows control frames and
+// two table rows per frame, so the scatter goes into [kOscRows][2][P] shared-memory accumulators (48 KB at P = 2048)
+// with shared atomics and is flushed once per CTA with global atomics on the non-zero entries.
+template <int OS, bool TABLE>
 __global__ void __launch_bounds__(128) osc_dw_v2_kernel(OscBwdParams q) {
   const OscParams& p = q.f;
   extern __shared__ __align__(16) float smem[];
   float* gs = smem;                       // gout[m0 - Z + i]
   float* hr = smem + p.plen;              // [OS][kp12] reversed polyphase taps
   float* slope = hr + OS * p.kp12;        // [kOscRows][P] T[lo+1] - T[lo] of control frames ybase .. ybase+2
+                                          // TABLE: [kOscRows][2][P] accumulators for rows lo, lo+1 of those frames
   __shared__ unsigned long long soff_s[kPrefSplit];
   __shared__ float dws[kOscRows];
   if (threadIdx.x < 32) span_offsets(p.totals + (size_t)blockIdx.y * kPrefSplit, soff_s, p.phase0, blockIdx.y);
@@ -669,10 +677,20 @@ __global__ void __launch_bounds__(128) osc_dw_v2_kernel(OscBwdParams q) {
     const int n = (2 * Z - qr) * OS + phs;  // reversed: hr[phs][q'] = h[(2Z - q')*os + phs]
     hr[i] = (qr <= 2 * Z && n >= 0 && n <= 2 * Z * OS) ? (p.dec ? p.dec[n] : 1.f) : 0.f;
   }
+  float pr[kOscRows];  // TABLE: row blend p = w (n_tab-1) - lo of the staged control frames
+  int lor[kOscRows];
+#pragma unroll
   for (int i = 0; i < kOscRows; ++i) {
     const int f = min(ybase + i, p.Fw - 1);
     const float raw = __fmul_rn(__ldg(q.w + (size_t)b * p.Fw + f), (float)(q.n_tab - 1));
     const int lo = min(max((int)raw, 0), q.n_tab - 2);
+    pr[i] = __fsub_rn(raw, (float)lo);
+    lor[i] = lo;
+    if constexpr (TABLE) {
+      float4* dst = reinterpret_cast<float4*>(slope + (size_t)i * 2 * P);
+      for (int c = tid; c < P / 2; c += blockDim.x) dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
     const float4* t0 = reinterpret_cast<const float4*>(q.table + (size_t)lo * P);
     const float4* t1 = reinterpret_cast<const float4*>(q.table + (size_t)(lo + 1) * P);
     float4* dst = reinterpret_cast<float4*>(slope + i * P);
@@ -727,8 +745,6 @@ __global__ void __launch_bounds__(128) osc_dw_v2_kernel(OscBwdParams q) {
         const int tr = t0 + phs - trow0;
         const bool up = tr >= p.hop_tab;
         const float fy = __fmul_rn((float)(up ? tr - p.hop_tab : tr), inv_hop_tab);
-        const float* s0p = slope + (up ? P : 0);
-        const float* s1p = s0p + P;
         float g = gv[phs][i];
         if (p.equal_energy) {
           const float l1 = __fmul_rn((float)(rr0 + phs), inv_hp);
@@ -738,6 +754,26 @@ __global__ void __launch_bounds__(128) osc_dw_v2_kernel(OscBwdParams q) {
           g = __fmul_rn(g, rs);
         }
         const float gx1 = 1.f - fx;
+        if constexpr (TABLE) {
+          float* A0 = slope + (up ? 2 * P : 0);  // frame `up`: planes lo, lo+1
+          float* A1 = A0 + 2 * P;                // next frame
+          const float p0 = up ? pr[1] : pr[0], p1 = up ? pr[2] : pr[1];
+          const float gl = g * (1.f - fy), gh = g * fy;
+          const float gl0 = gl * (1.f - p0), gl1 = gl * p0, gh0 = gh * (1.f - p1), gh1 = gh * p1;
+          atomicAdd(A0 + c0, gl0 * gx1);
+          atomicAdd(A0 + c1, gl0 * fx);
+          atomicAdd(A0 + P + c0, gl1 * gx1);
+          atomicAdd(A0 + P + c1, gl1 * fx);
+          atomicAdd(A1 + c0, gh0 * gx1);
+          atomicAdd(A1 + c1, gh0 * fx);
+          atomicAdd(A1 + P + c0, gh1 * gx1);
+          atomicAdd(A1 + P + c1, gh1 * fx);
+          phi += d;
+          d += dd;
+          continue;
+        }
+        const float* s0p = slope + (up ? P : 0);
+        const float* s1p = s0p + P;
         const float lo_part = g * (1.f - fy) * __fmaf_rn(fx, s0p[c1], gx1 * s0p[c0]);
         const float hi_part = g * fy * __fmaf_rn(fx, s1p[c1], gx1 * s1p[c0]);
         a0 += up ? 0.f : lo_part;
@@ -747,6 +783,16 @@ __global__ void __launch_bounds__(128) osc_dw_v2_kernel(OscBwdParams q) {
       phi += d;
       d += dd;
     }
+  }
+  if constexpr (TABLE) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kOscRows; ++i)
+      for (int c = tid; c < 2 * P; c += blockDim.x) {
+        const float v = slope[(size_t)i * 2 * P + c];
+        if (v != 0.f) atomicAdd(q.d_table + (size_t)lor[i] * P + c, v);  // plane 1 is row lo+1: contiguous after row lo
+      }
+    return;
   }
 #pragma unroll
   for (int sh = 16; sh > 0; sh >>= 1) {
@@ -894,11 +940,12 @@ GOLF_API int golf_glottal_osc_fwd_from(const float* phase, const float* w, const
                          workspace, workspace_bytes, stream, phase0);
 }
 
-GOLF_API int golf_glottal_osc_bwd_w(const float* gout, const float* phase, const float* w, const float* table,
-                                    const float* dec_kernel, float* d_w, int B, int Np, int phase_hop, int Fw, int w_hop,
-                                    int n_tab, int P, int os, int zeros, int accumulate, int flags, void* workspace,
-                                    size_t workspace_bytes, void* stream) {
-  if (!gout || !phase || !w || !table || !d_w || n_tab < 2 || w_hop <= 0 || zeros < 0) return GOLF_ERR_INVALID;
+// d_w and d_table are each optional (at least one): the two adjoints are separate launches of one kernel template
+static int glottal_osc_bwd(const float* gout, const float* phase, const float* w, const float* table,
+                           const float* dec_kernel, float* d_w, float* d_table, int B, int Np, int phase_hop, int Fw, int w_hop,
+                           int n_tab, int P, int os, int zeros, int accumulate, int flags, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (!gout || !phase || !w || !table || (!d_w && !d_table) || n_tab < 2 || w_hop <= 0 || zeros < 0) return GOLF_ERR_INVALID;
   if (os > 1 && !dec_kernel) return GOLF_ERR_INVALID;
   if (accumulate != 0 && accumulate != 1) return GOLF_ERR_INVALID;
   OscLayout L;
@@ -917,34 +964,67 @@ GOLF_API int golf_glottal_osc_bwd_w(const float* gout, const float* phase, const
   else
     osc_knot_prefix_kernel<<<B, 256, 0, st>>>(phase, pref, Np, L.hp, os, 0);
   GOLF_CHECK_LAUNCH();
-  GOLF_CUDA(cudaMemsetAsync(d_w, 0, (size_t)B * Fw * sizeof(float), st));
+  if (d_w) GOLF_CUDA(cudaMemsetAsync(d_w, 0, (size_t)B * Fw * sizeof(float), st));
+  if (d_table) GOLF_CUDA(cudaMemsetAsync(d_table, 0, (size_t)n_tab * P * sizeof(float), st));
   OscBwdParams q{};
   q.f = osc_params(phase, nullptr, pref, totals, span, dec_kernel, nullptr, B, Np, Fw, w_hop, P, os, zeros, accumulate, flags, L);
-  q.gout = gout, q.w = w, q.table = table, q.d_w = d_w, q.n_tab = n_tab;
+  q.gout = gout, q.w = w, q.table = table, q.d_w = d_w, q.d_table = d_table, q.n_tab = n_tab;
   dim3 grid(ceil_div(L.n_out, kOscTile), B);
-  const size_t smv2 = ((size_t)q.f.plen + (size_t)os * q.f.kp12 + (size_t)kOscRows * P) * sizeof(float);
+  const size_t smv2 = ((size_t)q.f.plen + (size_t)os * q.f.kp12 + (size_t)kOscRows * P * (d_table ? 2 : 1)) * sizeof(float);
   if (g_osc_v2 && accumulate == 0 && (os == 1 || os == 2 || os == 4) && P >= 4 && (P & (P - 1)) == 0 && smv2 <= 200 * 1024 &&
       (int64_t)kOscTile * os < (int64_t)q.f.hop_tab) {
     static unsigned long long attr = 0;
     if (first_use_on_device(attr)) {
-      GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GOLF_CUDA(cudaFuncSetAttribute(osc_dw_v2_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       mark_used_on_device(attr);
     }
-    switch (os) {
-      case 1: osc_dw_v2_kernel<1><<<grid, 128, smv2, st>>>(q); break;
-      case 2: osc_dw_v2_kernel<2><<<grid, 128, smv2, st>>>(q); break;
-      default: osc_dw_v2_kernel<4><<<grid, 128, smv2, st>>>(q); break;
+    if (d_w) {
+      const size_t smw = smv2 - (d_table ? (size_t)kOscRows * P * sizeof(float) : 0);
+      switch (os) {
+        case 1: osc_dw_v2_kernel<1, false><<<grid, 128, smw, st>>>(q); break;
+        case 2: osc_dw_v2_kernel<2, false><<<grid, 128, smw, st>>>(q); break;
+        default: osc_dw_v2_kernel<4, false><<<grid, 128, smw, st>>>(q); break;
+      }
+      GOLF_CHECK_LAUNCH();
     }
-    GOLF_CHECK_LAUNCH();
+    if (d_table) {
+      switch (os) {
+        case 1: osc_dw_v2_kernel<1, true><<<grid, 128, smv2, st>>>(q); break;
+        case 2: osc_dw_v2_kernel<2, true><<<grid, 128, smv2, st>>>(q); break;
+        default: osc_dw_v2_kernel<4, true><<<grid, 128, smv2, st>>>(q); break;
+      }
+      GOLF_CHECK_LAUNCH();
+    }
     return GOLF_OK;
   }
+  if (d_table) return GOLF_ERR_UNSUPPORTED;  // table adjoint: integer-phase path only (power-of-two P, os 1/2/4)
   const size_t sm = (size_t)(q.f.plen + os * q.f.kp12 + Fw) * sizeof(float);
   if (sm > 48 * 1024) return GOLF_ERR_UNSUPPORTED;
   osc_dw_kernel<<<grid, 128, sm, st>>>(q);
   GOLF_CHECK_LAUNCH();
   return GOLF_OK;
+}
+
+GOLF_API int golf_glottal_osc_bwd_w(const float* gout, const float* phase, const float* w, const float* table,
+                                    const float* dec_kernel, float* d_w, int B, int Np, int phase_hop, int Fw, int w_hop,
+                                    int n_tab, int P, int os, int zeros, int accumulate, int flags, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  if (!d_w) return GOLF_ERR_INVALID;
+  return glottal_osc_bwd(gout, phase, w, table, dec_kernel, d_w, nullptr, B, Np, phase_hop, Fw, w_hop, n_tab, P, os, zeros,
+                         accumulate, flags, workspace, workspace_bytes, stream);
+}
+
+GOLF_API int golf_glottal_osc_bwd(const float* gout, const float* phase, const float* w, const float* table,
+                                  const float* dec_kernel, float* d_w, float* d_table, int B, int Np, int phase_hop, int Fw,
+                                  int w_hop, int n_tab, int P, int os, int zeros, int accumulate, int flags, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  return glottal_osc_bwd(gout, phase, w, table, dec_kernel, d_w, d_table, B, Np, phase_hop, Fw, w_hop, n_tab, P, os, zeros,
+                         accumulate, flags, workspace, workspace_bytes, stream);
 }
 
 GOLF_API int golf_wavetable_read_fwd(const float* wrapped, const float* tables, float* out, int B, int N, int R, int P,

@@ -813,9 +813,10 @@ class _GlottalOsc(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
-        if ctx.needs_input_grad[0] or ctx.needs_input_grad[2]:
-            raise GolfError("glottal_osc: gradients w.r.t. phase / table are not implemented (detach f0; trainable=False)")
-        if not ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[0]:
+            raise GolfError("glottal_osc: the gradient w.r.t. phase is not implemented (detach f0, as the shipped configs do)")
+        need_w, need_t = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        if not (need_w or need_t):
             return (None,) * 10
         phase_c, w_c, table_c, dk = ctx.saved_tensors
         phase_hop, w_hop, os_, zeros, equal_energy, mode = ctx.geom
@@ -823,20 +824,21 @@ class _GlottalOsc(torch.autograd.Function):
         B, Np = phase_c.shape
         Fw = w_c.shape[1]
         n_tab, P = table_c.shape
-        d_w = torch.empty_like(w_c)
+        d_w = torch.empty_like(w_c) if need_w else None
+        d_table = torch.empty_like(table_c) if need_t else None
         lib = _lib.lib()
         ws = _workspace(lib.golf_glottal_osc_workspace_bytes(B, Np, phase_hop, Fw, P, os_), gout.device)
         with _on(gout.device):
-            rc = lib.golf_glottal_osc_bwd_w(_ptr(gout), _ptr(phase_c), _ptr(w_c), _ptr(table_c), _ptr(dk), _ptr(d_w), B, Np,
-                                            phase_hop, Fw, w_hop, n_tab, P, os_, zeros, mode, 1 if equal_energy else 0,
-                                            _ptr(ws), ws.numel(), _stream())
-        check(rc, "golf_glottal_osc_bwd_w")
-        return None, d_w, None, None, None, None, None, None, None, None
+            rc = lib.golf_glottal_osc_bwd(_ptr(gout), _ptr(phase_c), _ptr(w_c), _ptr(table_c), _ptr(dk), _ptr(d_w), _ptr(d_table),
+                                          B, Np, phase_hop, Fw, w_hop, n_tab, P, os_, zeros, mode, 1 if equal_energy else 0,
+                                          _ptr(ws), ws.numel(), _stream())
+        check(rc, "golf_glottal_osc_bwd" + (" (table gradient: exact-phase mode, oversampling 1/2/4, power-of-two table length)" if need_t else ""))
+        return None, d_w, d_table, None, None, None, None, None, None, None
 
 
 def glottal_osc(phase, phase_hop: int, w, w_hop: int, table, dec_kernel=None, oversampling: int = 1,
                 equal_energy: bool = False, accumulate: str = "exact", phase0=None) -> torch.Tensor:
-    """IndexedGlottalFlowTable.forward; differentiable in the table-selection weight `w`.  phase0 [B]: running
+    """IndexedGlottalFlowTable.forward; differentiable in the table-selection weight `w` and in the table (trainable tables).  phase0 [B]: running
     phase (cycles) each utterance starts from (a per-utterance constant `phase_offset`, exact-phase mode)."""
     return _GlottalOsc.apply(phase, w, table, dec_kernel, int(phase_hop), int(w_hop), int(oversampling), bool(equal_energy),
                              _OSC_MODES[accumulate], phase0)

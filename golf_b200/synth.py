@@ -93,11 +93,7 @@ class GlottalFlowTable(OscillatorInterface):
                 table = table / table.max(dim=1, keepdim=True).values
         elif normalize_method is not None:
             raise ValueError(f"unknown normalize_method: {normalize_method}")
-        if trainable:
-            import warnings
-
-            warnings.warn("golf_b200: GlottalFlowTable(trainable=True) synthesises, but the table gradient is not implemented "
-                          "(backward raises GolfError); shipped GOLF configs use trainable=False", stacklevel=2)
+        if trainable:  # the table adjoint is golf_glottal_osc_bwd (csrc/osc.cu)
             self.register_parameter("table", nn.Parameter(table))
         else:
             self.register_buffer("table", table)

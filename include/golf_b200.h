@@ -33,6 +33,7 @@
  *   golf_glottal_osc_fwd     models/synth.py:213-263   IndexedGlottalFlowTable.forward
  *   golf_glottal_osc_fwd_from  the same with phase_offset (models/synth.py:195-218,251-252) as a per-utterance constant
  *   golf_glottal_osc_bwd_w   autograd of the above w.r.t. table_select_weight
+ *   golf_glottal_osc_bwd     ... and w.r.t. the wavetable (trainable tables)
  *   golf_wavetable_read_fwd  models/synth.py:124-177   GlottalFlowTable.generate
  *   golf_linear_upsample     models/audiotensor/audiotensor.py:11-17 linear_upsample
  *   golf_rc2lpc_fwd/bwd      models/utils.py:581-593   rc2lpc (with the tanh*max_abs of filters.py:80) and its autograd
@@ -314,6 +315,15 @@ int golf_glottal_osc_bwd_w(const float *gout, const float *phase, const float *w
                            int phase_hop, int Fw, int w_hop, int n_tab, int P, int os, int zeros,
                            int accumulate, int flags, void *workspace, size_t workspace_bytes,
                            void *stream);
+/* Both adjoints of the oscillator that the reference's autograd provides for a detached f0: d_w [B,Fw] as above and
+ * d_table [n_tab,P], the gradient w.r.t. the wavetable itself (GlottalFlowTable(trainable=True) registers the table as
+ * an nn.Parameter, models/synth.py:157-166).  Either pointer may be NULL (not both).  d_table needs the exact-phase
+ * mode, oversampling 1/2/4 and a power-of-two table length (GOLF_ERR_UNSUPPORTED otherwise). */
+int golf_glottal_osc_bwd(const float *gout, const float *phase, const float *w, const float *table,
+                         const float *dec_kernel, float *d_w, float *d_table, int B, int Np,
+                         int phase_hop, int Fw, int w_hop, int n_tab, int P, int os, int zeros,
+                         int accumulate, int flags, void *workspace, size_t workspace_bytes,
+                         void *stream);
 /* GlottalFlowTable.generate: wrapped [B,N] in [0,1), tables [B,R,P] at hop hop_tab. */
 int golf_wavetable_read_fwd(const float *wrapped, const float *tables, float *out, int B,
                             int N, int R, int P, int hop_tab, void *stream);

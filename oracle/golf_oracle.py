@@ -483,7 +483,9 @@ def glottal_osc(
 ) -> torch.Tensor:
     """IndexedGlottalFlowTable.forward, models/synth.py:213-263.  phase [B,Np] at
     `phase_hop` (cycles/sample), w [B,Fw] at `w_hop`."""
-    phase, table = _f32(phase), _f32(table)
+    phase = _f32(phase)
+    if not table.requires_grad:  # a trainable table (models/synth.py:117-118) keeps its autograd graph
+        table = _f32(table)
     if not w.requires_grad:
         w = _f32(w)
     tables = select_tables(table, w)

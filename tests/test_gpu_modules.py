@@ -367,3 +367,32 @@ def test_harmonic_plus_noise_synth_matches_oracle_composition(oracle):
                    harm_filter_params=(A("gain", H), A("a", H)), noise_filter_params=(A("log_mag", H),),
                    voicing=AudioTensor(torch.full_like(T(g["phase"]), 0.5).to(DEV), hop_length=int(g["phase_hop"])))
     assert torch.isfinite(out0.as_tensor()).all() and not torch.equal(out0.as_tensor(), out.as_tensor())
+
+
+def test_trainable_glottal_table_trains_through_the_decoder():
+    """GlottalFlowTable(trainable=True) (models/synth.py:117-118): the table is an nn.Parameter of the decoder and receives
+    its gradient from the CUDA adjoint; a small gradient step lowers a waveform loss by the first-order amount"""
+    from golf_b200 import synth
+    from golf_b200.audiotensor import AudioTensor
+
+    osc = synth.IndexedGlottalFlowTable(oversampling=4, equal_energy=True, table_type="derivative",
+                                        normalize_method="constant_power", align_peak=True, trainable=True, lf_v2=True,
+                                        points=2048).to(DEV)
+    assert isinstance(osc.table, torch.nn.Parameter) and "table" in dict(osc.named_parameters())
+    gen = torch.Generator().manual_seed(3)
+    phase = AudioTensor((torch.full((2, 100), 150.0) / 24000).to(DEV), hop_length=240)
+    w = AudioTensor(torch.rand(2, 11, generator=gen).to(DEV), hop_length=2400)
+    target = torch.randn(2, 24000, generator=gen).to(DEV)
+
+    def loss_fn():
+        y = osc(phase, w).as_tensor()
+        return ((y - target[:, : y.shape[1]]) ** 2).mean()
+
+    loss = loss_fn()
+    loss.backward()
+    g = osc.table.grad
+    assert g is not None and g.shape == osc.table.shape and torch.isfinite(g).all() and g.abs().sum() > 0
+    with torch.no_grad():  # a step sized for a 1 % first-order decrease; the loss is quadratic in the table
+        osc.table -= 0.01 * loss / (g * g).sum() * g
+        drop = float(loss - loss_fn()) / float(loss)
+    assert 0.005 < drop < 0.0101

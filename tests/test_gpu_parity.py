@@ -392,6 +392,47 @@ def test_oscillator_weight_gradient(G, oracle):
     assert rel_rms(g_w, g_ref) < 1e-3  # sums of ~1e4 terms in a different order, float atomics
 
 
+@pytest.mark.parametrize("os_,phase_hop,equal_energy", [(4, 1, True), (4, 240, False), (2, 1, True), (1, 1, False)])
+def test_oscillator_table_gradient(G, oracle, os_, phase_hop, equal_energy):
+    """d/dtable of the oscillator (GlottalFlowTable(trainable=True), models/synth.py:117-118) together with d/dw, vs torch
+    autograd through the CPU restatement (float64 phase); both gradients from one backward"""
+    B, Tn = 3, 9600
+    gen = torch.Generator().manual_seed(15 + os_)
+    f0 = (180 + 0.5 * torch.cumsum(torch.randn(B, Tn // phase_hop + (phase_hop > 1), generator=gen), 1)).clamp(80, 400)
+    ph = f0 / 24000
+    w = torch.rand(B, Tn // 2400 + 1, generator=gen)
+    w[0, 0], w[1, -1] = 0.0, 1.0  # both ends of the table
+    table, _ = oracle.glottal_table()
+    dk = oracle.decimate_kernel(os_) if os_ > 1 else None
+    wr, tr = w.clone().requires_grad_(), table.clone().requires_grad_()
+    ref = oracle.glottal_osc(ph, phase_hop, wr, 2400, tr, os_, equal_energy, "fp64")
+    up = torch.randn(ref.shape, generator=gen)
+    gw_ref, gt_ref = torch.autograd.grad(ref, (wr, tr), up)
+    wg, tg = w.to(DEV).requires_grad_(), table.to(DEV).requires_grad_()
+    y = G.glottal_osc(ph.to(DEV), phase_hop, wg, 2400, tg, None if dk is None else dk.to(DEV), os_, equal_energy, "exact")
+    assert rel_rms(y, ref.detach()) < 2e-5
+    g_w, g_t = torch.autograd.grad(y, (wg, tg), up.to(DEV))
+    assert g_t.shape == table.shape and rel_rms(g_w, gw_ref) < 1e-3
+    assert rel_rms(g_t, gt_ref) < 1e-3  # bilinear scatter; the column split of a sample at a cell edge moves with the phase's last bit
+    untouched = gt_ref == 0
+    assert torch.equal(g_t.cpu()[untouched], gt_ref[untouched])  # rows no frame selected stay exactly zero
+    # table gradient alone (w detached): same numbers
+    y2 = G.glottal_osc(ph.to(DEV), phase_hop, w.to(DEV), 2400, tg, None if dk is None else dk.to(DEV), os_, equal_energy, "exact")
+    (g_t2,) = torch.autograd.grad(y2, tg, up.to(DEV))
+    assert rel_rms(g_t2, g_t) < 1e-5
+
+
+def test_oscillator_table_gradient_unsupported_modes_fail_loudly(G, oracle):
+    from golf_b200 import GolfError
+
+    table, _ = oracle.glottal_table()
+    tg = table.to(DEV).requires_grad_()
+    ph, w = torch.full((1, 4800), 200 / 24000), torch.rand(1, 3)
+    y = G.glottal_osc(ph.to(DEV), 1, w.to(DEV), 2400, tg, oracle.decimate_kernel(4).to(DEV), 4, True, "aten_cpu")
+    with pytest.raises(GolfError, match="table gradient"):
+        y.sum().backward()
+
+
 def test_wavetable_read_matches_generate(G, oracle):
     gen = torch.Generator().manual_seed(6)
     table, _ = oracle.glottal_table()
