@@ -10,7 +10,7 @@ from ctypes import c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("GOLF_B200_SO") or os.path.join(_HERE, "_lib", "libgolf_b200.so")  # env: A/B builds (tools/)
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 _lib = None
 
 P = c_void_p

@@ -39,6 +39,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "fir_tile.cuh"  // f32x2 / pack2 / unpack2 / ffma2
 
 namespace golf {
 
@@ -99,6 +100,14 @@ __device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y
 #ifndef GOLF_RESP_NC
 #define GOLF_RESP_NC 3  // columns per lane at padded order 24; -DGOLF_RESP_NC=4|5|6 for experiments (tools/resp_nc_sweep.sh)
 #endif
+#ifndef GOLF_RESP_F2
+// 1: direct-form recurrence on packed FP32 (fma.rn.f32x2; SASS FFMA2), half the FMA issue slots.  Measured on B200
+// (B = 32 x 47 760, M = 22): the kernel takes 73.8 us either way -- it is bound by the per-tile latency chain, not by
+// issue -- and the two partial sums per column round differently from the sequential solve, so the chunk-boundary
+// mismatch rises above refine_tol and the refinement launches run (filter 137 -> 197 us alone; 7.42e9 vs 7.44e9
+// samples/s with 8 passes in flight).  Kept as a compile-time experiment, off by default.
+#define GOLF_RESP_F2 0
+#endif
 #ifndef GOLF_RESP_WPB
 #define GOLF_RESP_WPB 4  // warps per CTA: they meet at a barrier every tile, which keeps them in the same part of the 48 KB loop body (81 -> 77 us; 8 per CTA: the same)
 #endif
@@ -129,6 +138,7 @@ __global__ void __launch_bounds__(32 * GOLF_RESP_WPB, (RespCfg<MP>::RES / GOLF_R
   constexpr int TPL = ((MP + SQ0 - 1) / SQ0 + 1) / 2 * 2;  // taps per staging lane (even: 8-byte stores)
   constexpr int SQ = (MP + TPL - 1) / TPL;                // staging lanes used per chunk
   constexpr int NQ = (MT + 3) / 4;                        // coefficient quads read per step
+  constexpr bool F2 = GOLF_RESP_F2 && FORM == 0 && MT <= MP - 1 && MP % 4 == 0;
   static_assert(LPC * CPW <= 32 && SQ * CPW <= 32 && MT <= MP && MT >= 1, "response kernel geometry");
   extern __shared__ __align__(128) float smem_all[];
   constexpr int kWarpFloats = (CPW * TSTR + ROWS * 5 + 31) / 32 * 32;  // shared memory of one warp
@@ -170,6 +180,13 @@ __global__ void __launch_bounds__(32 * GOLF_RESP_WPB, (RespCfg<MP>::RES / GOLF_R
       const int comp = FORM == 0 ? MP - 1 - k : k;  // state component stored in slot k
       st[c][k] = (col < p.M && comp == col) ? 1.f : 0.f;
     }
+  }
+  f32x2 sp[F2 ? NC : 1][F2 ? MP / 2 : 1];  // packed ring (F2): slots 2k, 2k+1
+  if constexpr (F2) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int k = 0; k < MP / 2; ++k) sp[c][k] = pack2(st[c][2 * k], st[c][2 * k + 1]);
   }
   const float* myc = ctile + gi * TSTR;
   const float* mye = etile + gi * MP;
@@ -246,7 +263,20 @@ __global__ void __launch_bounds__(32 * GOLF_RESP_WPB, (RespCfg<MP>::RES / GOLF_R
             float2 v;
             v.x = __fmaf_rn(wv.x, qa0[i], __fmul_rn(wv.y, qa1[i]));
             v.y = __fmaf_rn(wv.x, qa0[i + 1], __fmul_rn(wv.y, qa1[i + 1]));
-            *reinterpret_cast<float2*>(dst + i) = v;
+            if constexpr (F2) {
+              // packed layout: the row of step sr holds lag L at word (MP - (sr & 1) - L) mod MP -- descending lags, so
+              // that an aligned pair of words meets an aligned pair of ring slots (see the recurrence below)
+              float* row = ctile + sk * TSTR + sr * MP;
+              const int t0 = TPL * sg + i;  // taps t0, t0 + 1 = lags t0 + 1, t0 + 2
+              if ((sr & 1) == 0) {
+                *reinterpret_cast<float2*>(row + (MP - 2 - t0)) = make_float2(v.y, v.x);
+              } else {
+                row[MP - 2 - t0] = v.x;
+                row[(MP - 3 - t0 + MP) % MP] = v.y;  // lag MP (tap MP-1, zero: M < MP) lands on the lag-0 word
+              }
+            } else {
+              *reinterpret_cast<float2*>(dst + i) = v;
+            }
           }
         }
       }
@@ -257,6 +287,42 @@ __global__ void __launch_bounds__(32 * GOLF_RESP_WPB, (RespCfg<MP>::RES / GOLF_R
 #pragma unroll
     for (int s = 0; s < MP; ++s) {
       const float e = mye[s];
+      if constexpr (F2) {
+        // Ring slots 2k, 2k+1 share a 64-bit register (sp[cc][k]).  At step s (parity par) the lags of slots 2k and
+        // 2k+1 are L and L-1 with L = (s - 2k) mod MP of parity par, and the coefficient row was staged in descending
+        // lag order starting at lag MP - par: word pair m = lags (MP-par-2m, MP-1-par-2m) meets ring pair
+        // ((s+par)/2 + m) mod MP/2.  Lags 0 and > M carry zero coefficients.  11 or 12 packed FMAs per column and
+        // step for M = 22 instead of 22 scalar ones; two partial sums (even / odd lags), added at the end.
+        constexpr int HP = MP / 2;
+        const int par = s & 1;
+        f32x2 acc[NC];
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc) acc[cc] = pack2(zsr[cc] ? e : 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < MP / 4; ++q) {
+          // pairs 2q, 2q+1: lags MP-par-4q .. MP-3-par-4q; needed if any lag is in [1, MT]
+          const int lag_hi = MP - par - 4 * q, lag_lo = MP - 3 - par - 4 * q;
+          if (lag_lo > MT || lag_hi < 1) continue;
+          const float4 v = *reinterpret_cast<const float4*>(myc + s * MP + 4 * q);
+          const f32x2 c0 = pack2(v.x, v.y), c1 = pack2(v.z, v.w);
+          const bool use0 = lag_hi - 1 <= MT && lag_hi >= 1, use1 = lag_lo <= MT && lag_lo + 1 >= 1;
+          const int k0 = ((s + par) / 2 + 2 * q) % HP, k1 = ((s + par) / 2 + 2 * q + 1) % HP;
+#pragma unroll
+          for (int cc = 0; cc < NC; ++cc) {
+            if (use0) ffma2(acc[cc], c0, sp[cc][k0]);
+            if (use1) ffma2(acc[cc], c1, sp[cc][k1]);
+          }
+        }
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc) {
+          float a0, a1, lo, hi;
+          unpack2(acc[cc], a0, a1);
+          unpack2(sp[cc][s / 2], lo, hi);
+          const float y = a0 + a1;
+          sp[cc][s / 2] = par ? pack2(lo, y) : pack2(y, hi);
+        }
+        continue;
+      }
       float c[4 * NQ];
 #pragma unroll
       for (int i4 = 0; i4 < NQ; ++i4) {
@@ -287,6 +353,12 @@ __global__ void __launch_bounds__(32 * GOLF_RESP_WPB, (RespCfg<MP>::RES / GOLF_R
         for (int cc = 0; cc < NC; ++cc) st[cc][(s + MT) % MP] = __fmul_rn(c[MT - 1], u[cc]);  // slot consumed MP-MT steps ago (or just now)
       }
     }
+  }
+  if constexpr (F2) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int k = 0; k < MP / 2; ++k) unpack2(sp[c][k], st[c][2 * k], st[c][2 * k + 1]);
   }
   // ---- emit this lane's columns of [Phi | z]: W[col][k] = end-state component k
   if (chunk_on) {

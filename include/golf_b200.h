@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define GOLF_B200_ABI_VERSION 7
+#define GOLF_B200_ABI_VERSION 8
 
 enum {
   GOLF_OK = 0,
