@@ -271,6 +271,16 @@ def test_fir_stages_reference_golden(G, oracle, variant):
     assert rel_rms(r, T(g["out"])) < 1e-5
 
 
+@pytest.mark.parametrize("T_,n", [(1, 127), (5, 3), (1023, 127), (1024, 127), (1025, 127), (4099, 1), (47760, 127), (9001, 300)])
+def test_room_fir_ragged_sizes(G, oracle, T_, n):
+    """LTIAcousticFilter on lengths around the kernel's 1024-output tile, odd lengths and tap counts other than the shipped 127"""
+    gen = torch.Generator().manual_seed(T_ + n)
+    x, k = torch.randn(3, T_, generator=gen), 0.1 * torch.randn(n, generator=gen)
+    ref = oracle.room_fir(x, k)
+    y = G.room_fir(*cu(x, k))
+    assert y.shape == ref.shape and rel_rms(y, ref) < 1e-5
+
+
 def test_noise_fir_ragged_sizes(G, oracle):
     g = torch.Generator().manual_seed(0)
     for (Tn, H, K, Fr) in [(4801, 240, 510, 25), (2000, 120, 254, 10), (700, 100, 62, 9)]:
