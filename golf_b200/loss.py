@@ -55,6 +55,8 @@ def _rows2(t, name):
 class _MSS(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target, n_ffts, hops, alpha, ratio, eps, prec3):
+        if ctx.needs_input_grad[1]:
+            raise GolfError("mss_loss: the target is data (no gradient is computed for it); detach it")
         p, t = _rows2(pred, "pred"), _rows2(target, "target")
         if p.shape != t.shape:
             raise GolfError(f"mss_loss: pred {tuple(p.shape)} vs target {tuple(t.shape)}")

@@ -181,3 +181,30 @@ def test_library_contains_tcgen05_and_tma():
     assert "UTCHMMA" in sass or "UTCMMA" in sass or "UTC" in sass  # tcgen05.mma
     assert "UTMALDG" in sass  # tensor-map TMA loads
     assert "LDTM" in sass  # tcgen05.ld
+
+
+def test_mss_error_paths_are_loud():
+    """what the kernels do not implement raises instead of returning something else: shapes, the reflect-padding limit of
+    torch.stft (L > n_fft / 2), sizes outside 16..4096, windows other than Hann, a target that asks for a gradient, CPU tensors"""
+    from golf_b200 import GolfError
+    from golf_b200 import loss as GL
+
+    pred, true = (v.to(DEV) for v in signals(2, 4000, 3, "noise"))
+    with pytest.raises(GolfError, match="pred .* vs target"):
+        GL.mss_loss(pred, true[:, :-1], (512,))
+    with pytest.raises(GolfError, match="must be \\[B, L\\]"):
+        GL.mss_loss(pred[0], true[0], (512,))
+    with pytest.raises(GolfError, match="unsupported"):
+        GL.mss_loss(pred[:, :200], true[:, :200], (512,))  # torch.stft refuses this too: reflect pad 256 >= 200
+    with pytest.raises(GolfError, match="unsupported n_fft"):
+        GL.mss_loss(pred, true, (8192,))
+    with pytest.raises(GolfError, match="target is data"):
+        GL.mss_loss(pred, true.clone().requires_grad_(), (512,))
+    with pytest.raises(GolfError):
+        GL.mss_loss(pred.cpu(), true.cpu(), (512,))
+    with pytest.raises(ValueError, match="Hann"):
+        GL.MSSLoss([512], window="hamming")
+    with pytest.raises(ValueError, match="differs from the default"):
+        GL.MSSLoss([512], power=2)
+    # and the same call with supported arguments works
+    assert torch.isfinite(GL.MSSLoss([512], window="hann", center=True, power=1)(pred, true))
