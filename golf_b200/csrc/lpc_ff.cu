@@ -32,6 +32,12 @@
 
 namespace golf {
 
+#ifdef GOLF_FF_TIMING  // phase clocks of CTA 0 (variant builds only: tools/gpu/time_ff.py)
+__device__ long long g_ff_clk[8];
+#define FF_CLK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_ff_clk[i] = clock64(); } while (0)
+#else
+#define FF_CLK(i) do { } while (0)
+#endif
 
 // ---- forward ------------------------------------------------------------------------
 // ALIGNED: hop % TILE == 0 and win % TILE == 0 -> a tile never crosses a hop boundary, every
@@ -48,31 +54,57 @@ __global__ void __launch_bounds__(kFfThreads) ff_forward_kernel(FfParams p) {
   float* __restrict__ vt = wsm + p.win;                       // [32][TILE+1]    v tile (STORE_V)
   const int k = g.k0 + lane;
   const bool frame_ok = (k >= 0) && (k < p.n_frames);
+  FF_CLK(0);
 
   // ---- all warps: window, zeroed accumulators, excitation strip
-  for (int i = tid; i < p.win; i += kFfThreads) wsm[i] = __ldg(p.window + i);
-  for (int i = tid; i < g.NS * g.seg_stride; i += kFfThreads) acc[i] = 0.f;
   const float* __restrict__ exb = p.ex + (size_t)b * p.ex_stride;
   const float* __restrict__ gb = p.gain + (size_t)b * p.F;
-  for (int i = tid; i < g.NSTRIP * p.hop; i += kFfThreads) {
-    const int sg = i / p.hop, r = i - sg * p.hop;
-    const int pos = (g.k0 + sg) * p.hop - p.pad + r;  // signal position
-    float v = 0.f;
-    if (pos >= 0 && pos < p.Le) {
-      v = __ldg(exb + pos);
-      if (p.interp_gain) {
-        const Lerp lw = lerp_at(pos, p.scale, p.F);
-        v = __fmul_rn(v, lerp_apply(lw, __ldg(gb + lw.i0), __ldg(gb + lw.i1)));
+  // The strip is latency bound (66 elements per thread at hop 240): with a load -> multiply -> store loop every element
+  // paid its own L2 round trip (~20 us of an 80 us kernel).  All copies go out at once through cp.async (LDGSTS,
+  // zero-filled outside the signal); the gain envelope is applied in a second pass over shared memory.
+  constexpr int kWarps = kFfThreads / 32;
+  for (int sg = warp; sg < g.NSTRIP; sg += kWarps) {
+    const int pos0 = (g.k0 + sg) * p.hop - p.pad;  // signal position of the segment's first sample
+    float* __restrict__ row = strip + sg * g.seg_stride;
+    for (int r = lane; r < p.hop; r += 32) {
+      const int pos = pos0 + r;
+      const bool ok = pos >= 0 && pos < p.Le;
+      cp_async4(row + r, exb + min(max(pos, 0), p.Le - 1), ok);
+    }
+  }
+  for (int i = tid; i < p.win; i += kFfThreads) wsm[i] = __ldg(p.window + i);
+  for (int i = tid; i < g.NS * g.seg_stride; i += kFfThreads) acc[i] = 0.f;
+  cp_async_wait_all();
+  FF_CLK(1);
+  if (p.interp_gain) {  // each thread revisits the elements it copied itself: no barrier needed in between
+    for (int sg = warp; sg < g.NSTRIP; sg += kWarps) {
+      const int pos0 = (g.k0 + sg) * p.hop - p.pad;
+      float* __restrict__ row = strip + sg * g.seg_stride;
+      for (int r4 = lane; r4 < p.hop; r4 += 4 * 32) {  // four elements per round: their gain loads are issued together
+        Lerp lw[4];
+        float g0[4], g1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int pos = min(max(pos0 + r4 + 32 * u, 0), p.Le - 1);
+          lw[u] = lerp_at(pos, p.scale, p.F);
+          g0[u] = __ldg(gb + lw[u].i0), g1[u] = __ldg(gb + lw[u].i1);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r4 + 32 * u, pos = pos0 + r;
+          if (r < p.hop && pos >= 0 && pos < p.Le) row[r] = __fmul_rn(row[r], lerp_apply(lw[u], g0[u], g1[u]));
+        }
       }
     }
-    strip[sg * g.seg_stride + r] = v;
   }
   __syncthreads();
+  FF_CLK(2);
 
   // ---- warp 0: the serial part, `win` recurrence steps per lane
   if (warp == 0) {
     Filt f;
     f.load(p, b, k, frame_ok);
+    FF_CLK(3);
     const float gframe = (!p.interp_gain && frame_ok) ? __ldg(gb + k) : 1.f;
     int q0 = 0, r0 = 0;  // (n0 / hop, n0 % hop); hop >= TILE so a tile crosses at most one hop boundary
 #pragma unroll 1
@@ -131,17 +163,39 @@ __global__ void __launch_bounds__(kFfThreads) ff_forward_kernel(FfParams p) {
       if (r0 >= p.hop) r0 -= p.hop, ++q0;
     }
   }
+  FF_CLK(4);
   __syncthreads();
 
   // ---- all warps: normalise by the overlap-added window and store
+  // Interior segments (all NQ frames exist) share one normalisation row: it is summed once into the strip (free now)
+  // in ff_norm's order; edge segments take the generic path.  (Per-element index division + the norm loop made this
+  // phase 16 us of an 80 us kernel.)
   float* __restrict__ yb = p.y + (size_t)b * p.out_len;
-  for (int i = tid; i < g.NS * p.hop; i += kFfThreads) {
-    const int sj = i / p.hop, r = i - sj * p.hop;
-    const int P = g.P0 + sj;
-    const int o = P * p.hop + r - p.pad;
-    if (o < 0 || o >= p.out_len) continue;
-    yb[o] = acc[sj * g.seg_stride + r] / ff_norm(p, wsm, P, r);
+  float* __restrict__ nrow = strip;
+  for (int r = tid; r < p.hop; r += kFfThreads) {
+    float norm = 0.f;
+    for (int q = p.NQ - 1; q >= 0; --q) norm += wsm[q * p.hop + r];
+    nrow[r] = norm;
   }
+  __syncthreads();
+  for (int sj = warp; sj < g.NS; sj += kWarps) {
+    const int P = g.P0 + sj;
+    const int o0 = P * p.hop - p.pad;
+    const bool interior = P - (p.NQ - 1) >= 0 && P < p.n_frames;
+    const float* __restrict__ arow = acc + sj * g.seg_stride;
+    if (o0 >= p.out_len || o0 + p.hop <= 0) continue;
+    if (interior && o0 >= 0 && o0 + p.hop <= p.out_len) {  // the common case: no per-element checks
+#pragma unroll 4
+      for (int r = lane; r < p.hop; r += 32) yb[o0 + r] = __fdiv_rn(arow[r], nrow[r]);
+    } else {
+#pragma unroll 1
+      for (int r = lane; r < p.hop; r += 32) {
+        const int o = o0 + r;
+        if (o >= 0 && o < p.out_len) yb[o] = __fdiv_rn(arow[r], interior ? nrow[r] : ff_norm(p, wsm, P, r));
+      }
+    }
+  }
+  FF_CLK(5);
 }
 
 // ---- adjoint (all-pole only) ----------------------------------------------------------
@@ -168,17 +222,41 @@ __global__ void __launch_bounds__(kFfThreads) ff_backward_kernel(FfParams p) {
   for (int i = tid; i < p.win; i += kFfThreads) wsm[i] = __ldg(p.window + i);
   for (int i = tid; i < g.NS * g.seg_stride; i += kFfThreads) acc[i] = 0.f;
   __syncthreads();
+  // gy (and the excitation, FRAME_GAIN) go to the strips through cp.async, all copies in flight at once; the division
+  // by the overlap-added window follows in a pass over shared memory (interior segments share one norm row).  A load -> divide -> store loop paid one L2 round trip per element, 66 times per thread.
   const float* __restrict__ gyb = p.ex + (size_t)b * p.ex_stride;
-  for (int i = tid; i < g.NSTRIP * p.hop; i += kFfThreads) {
-    const int sg = i / p.hop, r = i - sg * p.hop;
+  constexpr int kWarps = kFfThreads / 32;
+  for (int sg = warp; sg < g.NSTRIP; sg += kWarps) {
+    const int o0 = (g.k0 + sg) * p.hop - p.pad;
+    float* __restrict__ row = strip + sg * g.seg_stride;
+    float* __restrict__ xrow = xstrip + sg * g.seg_stride;
+    for (int r = lane; r < p.hop; r += 32) {
+      const int o = o0 + r;
+      cp_async4(row + r, gyb + min(max(o, 0), p.out_len - 1), o >= 0 && o < p.out_len);
+      if (FRAME_GAIN) cp_async4(xrow + r, p.vws_ex + (size_t)b * p.ex_stride2 + min(max(o, 0), p.Le - 1), o >= 0 && o < p.Le);
+    }
+  }
+  float* __restrict__ nrow = xstrip + (FRAME_GAIN ? g.NSTRIP * g.seg_stride : 0);  // [hop], after the last buffer
+  for (int r = tid; r < p.hop; r += kFfThreads) {
+    float norm = 0.f;
+    for (int q = p.NQ - 1; q >= 0; --q) norm += wsm[q * p.hop + r];
+    nrow[r] = norm;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  for (int sg = warp; sg < g.NSTRIP; sg += kWarps) {
     const int P = g.k0 + sg;
-    const int o = P * p.hop + r - p.pad;
-    float v = 0.f;
-    if (o >= 0 && o < p.out_len) v = __ldg(gyb + o) / ff_norm(p, wsm, P, r);
-    strip[sg * g.seg_stride + r] = v;
-    if (FRAME_GAIN) {
-      const int pos = P * p.hop + r - p.pad;
-      xstrip[sg * g.seg_stride + r] = (pos >= 0 && pos < p.Le) ? __ldg(p.vws_ex + (size_t)b * p.ex_stride2 + pos) : 0.f;
+    const int o0 = P * p.hop - p.pad;
+    float* __restrict__ row = strip + sg * g.seg_stride;
+    if (P - (p.NQ - 1) >= 0 && P < p.n_frames) {
+#pragma unroll 4
+      for (int r = lane; r < p.hop; r += 32) row[r] = __fdiv_rn(row[r], nrow[r]);  // 0 / norm stays 0 outside the signal
+    } else {
+#pragma unroll 1
+      for (int r = lane; r < p.hop; r += 32) {
+        const int o = o0 + r;
+        if (o >= 0 && o < p.out_len) row[r] = __fdiv_rn(row[r], ff_norm(p, wsm, P, r));
+      }
     }
   }
   __syncthreads();
@@ -267,10 +345,14 @@ __global__ void __launch_bounds__(kFfThreads) ff_backward_kernel(FfParams p) {
   }
   __syncthreads();
   float* __restrict__ deb = p.y + (size_t)b * p.Le;
-  for (int i = tid; i < g.NS * p.hop; i += kFfThreads) {
-    const int sj = i / p.hop, r = i - sj * p.hop;
-    const int pos = (g.P0 + sj) * p.hop + r - p.pad;
-    if (pos >= 0 && pos < p.Le) deb[pos] = acc[sj * g.seg_stride + r];
+  for (int sj = warp; sj < g.NS; sj += kWarps) {
+    const int pos0 = (g.P0 + sj) * p.hop - p.pad;
+    const float* __restrict__ arow = acc + sj * g.seg_stride;
+#pragma unroll 4
+    for (int r = lane; r < p.hop; r += 32) {
+      const int pos = pos0 + r;
+      if (pos >= 0 && pos < p.Le) deb[pos] = arow[r];
+    }
   }
 }
 
@@ -375,7 +457,7 @@ static int launch_ff_bwd(const FfParams& pf, const FfParams& pb, cudaStream_t st
   int rc = launch_ff_fwd<AllPole<MP>, true>(pf, st);
   if (rc) return rc;
   const int NSTRIP = 32 + pb.NQ - 1;
-  const size_t sm = ff_smem_bytes(pb, 2 * 32 * (2 * MP + 1) + (FRAME_GAIN ? NSTRIP * (pb.hop + 1) : 0));
+  const size_t sm = ff_smem_bytes(pb, 2 * 32 * (2 * MP + 1) + (FRAME_GAIN ? NSTRIP * (pb.hop + 1) : 0) + pb.hop);
   if (sm > 220 * 1024) return GOLF_ERR_UNSUPPORTED;
   static size_t sm_allowed_dev[64];
   int dev_ = 0;
@@ -437,6 +519,14 @@ static int dispatch_ff_fwd(int M, const FfParams& p, cudaStream_t st) {
 }  // namespace golf
 
 using namespace golf;
+
+#ifdef GOLF_FF_TIMING
+GOLF_API int golf_debug_ff_clocks(long long* out8) {
+  GOLF_CUDA(cudaDeviceSynchronize());
+  GOLF_CUDA(cudaMemcpyFromSymbol(out8, g_ff_clk, sizeof(long long) * 8));
+  return GOLF_OK;
+}
+#endif
 
 GOLF_API void golf_lpc_ff_set_exact_order(int on) { g_ff_exact = on ? 1 : 0; }
 

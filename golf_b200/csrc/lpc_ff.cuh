@@ -5,7 +5,10 @@
 
 namespace golf {
 
-constexpr int kFfThreads = 128;
+#ifndef GOLF_FF_THREADS
+#define GOLF_FF_THREADS 128
+#endif
+constexpr int kFfThreads = GOLF_FF_THREADS;  // warp 0 runs the recurrences; all warps stage and write out
 
 struct FfParams {
   const float* ex;       // fwd: excitation [B, ex_stride]; bwd: gy [B, out_len]
