@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(kFfThreads) biquad_backward_kernel(FfParams p,
   float* __restrict__ strip = smem;                            // [NSTRIP][hop+1] gy / norm, padded coordinates
   float* __restrict__ xstrip = strip + g.NSTRIP * g.seg_stride;   // [NSTRIP][hop+1] ex
   float* __restrict__ acc = xstrip + g.NSTRIP * g.seg_stride;     // [NS][hop+1]     d_ex accumulators
-  float* __restrict__ wsm = acc + g.NS * g.seg_stride;            // [win]
+  float* __restrict__ wsm = acc + g.NS * g.seg_stride;            // [win], then the norm row [hop]
   const int K = p.M;
   const int k = g.k0 + lane;
   const bool frame_ok = (k >= 0) && (k < p.n_frames);
@@ -43,16 +43,8 @@ __global__ void __launch_bounds__(kFfThreads) biquad_backward_kernel(FfParams p,
   for (int i = tid; i < p.win; i += kFfThreads) wsm[i] = __ldg(p.window + i);
   for (int i = tid; i < g.NS * g.seg_stride; i += kFfThreads) acc[i] = 0.f;
   __syncthreads();
-  const float* __restrict__ gyb = p.ex + (size_t)b * p.ex_stride;
-  const float* __restrict__ exb = p.vws_ex + (size_t)b * p.ex_stride2;
-  for (int i = tid; i < g.NSTRIP * p.hop; i += kFfThreads) {
-    const int sg = i / p.hop, r = i - sg * p.hop;
-    const int P = g.k0 + sg;
-    const int o = P * p.hop + r - p.pad;  // output position == input position of this padded coordinate
-    strip[sg * g.seg_stride + r] = (o >= 0 && o < p.out_len) ? __ldg(gyb + o) / ff_norm(p, wsm, P, r) : 0.f;
-    xstrip[sg * g.seg_stride + r] = (o >= 0 && o < p.Le) ? __ldg(exb + o) : 0.f;
-  }
-  __syncthreads();
+  ff_stage_adjoint_strips<true>(p, g, p.ex + (size_t)b * p.ex_stride, p.vws_ex + (size_t)b * p.ex_stride2, strip, xstrip,
+                                wsm + p.win, wsm);
 
   if (warp == 0) {
     float b0[KP], na1[KP], na2[KP], s1[KP], s2[KP];
@@ -140,18 +132,13 @@ __global__ void __launch_bounds__(kFfThreads) biquad_backward_kernel(FfParams p,
     }
   }
   __syncthreads();
-  float* __restrict__ deb = p.y + (size_t)b * p.Le;
-  for (int i = tid; i < g.NS * p.hop; i += kFfThreads) {
-    const int sj = i / p.hop, r = i - sj * p.hop;
-    const int pos = (g.P0 + sj) * p.hop + r - p.pad;
-    if (pos >= 0 && pos < p.Le) deb[pos] = acc[sj * g.seg_stride + r];
-  }
+  ff_write_adjoint_rows(p, g, acc, p.y + (size_t)b * p.Le);
 }
 
 template <int KP>
 static int launch_biquad_bwd(const FfParams& pb, float* scratch, float* d_bq, cudaStream_t st) {
   const int NS = 33 - pb.NQ, NSTRIP = 32 + pb.NQ - 1;
-  const size_t sm = ((size_t)(NS + 2 * NSTRIP) * (pb.hop + 1) + pb.win) * sizeof(float);
+  const size_t sm = ((size_t)(NS + 2 * NSTRIP) * (pb.hop + 1) + pb.win + pb.hop) * sizeof(float);
   if (sm > 220 * 1024) return GOLF_ERR_UNSUPPORTED;
   static size_t sm_allowed_dev[64];
   int dev_ = 0;

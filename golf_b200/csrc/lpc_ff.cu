@@ -222,44 +222,8 @@ __global__ void __launch_bounds__(kFfThreads) ff_backward_kernel(FfParams p) {
   for (int i = tid; i < p.win; i += kFfThreads) wsm[i] = __ldg(p.window + i);
   for (int i = tid; i < g.NS * g.seg_stride; i += kFfThreads) acc[i] = 0.f;
   __syncthreads();
-  // gy (and the excitation, FRAME_GAIN) go to the strips through cp.async, all copies in flight at once; the division
-  // by the overlap-added window follows in a pass over shared memory (interior segments share one norm row).  A load -> divide -> store loop paid one L2 round trip per element, 66 times per thread.
-  const float* __restrict__ gyb = p.ex + (size_t)b * p.ex_stride;
-  constexpr int kWarps = kFfThreads / 32;
-  for (int sg = warp; sg < g.NSTRIP; sg += kWarps) {
-    const int o0 = (g.k0 + sg) * p.hop - p.pad;
-    float* __restrict__ row = strip + sg * g.seg_stride;
-    float* __restrict__ xrow = xstrip + sg * g.seg_stride;
-    for (int r = lane; r < p.hop; r += 32) {
-      const int o = o0 + r;
-      cp_async4(row + r, gyb + min(max(o, 0), p.out_len - 1), o >= 0 && o < p.out_len);
-      if (FRAME_GAIN) cp_async4(xrow + r, p.vws_ex + (size_t)b * p.ex_stride2 + min(max(o, 0), p.Le - 1), o >= 0 && o < p.Le);
-    }
-  }
-  float* __restrict__ nrow = xstrip + (FRAME_GAIN ? g.NSTRIP * g.seg_stride : 0);  // [hop], after the last buffer
-  for (int r = tid; r < p.hop; r += kFfThreads) {
-    float norm = 0.f;
-    for (int q = p.NQ - 1; q >= 0; --q) norm += wsm[q * p.hop + r];
-    nrow[r] = norm;
-  }
-  cp_async_wait_all();
-  __syncthreads();
-  for (int sg = warp; sg < g.NSTRIP; sg += kWarps) {
-    const int P = g.k0 + sg;
-    const int o0 = P * p.hop - p.pad;
-    float* __restrict__ row = strip + sg * g.seg_stride;
-    if (P - (p.NQ - 1) >= 0 && P < p.n_frames) {
-#pragma unroll 4
-      for (int r = lane; r < p.hop; r += 32) row[r] = __fdiv_rn(row[r], nrow[r]);  // 0 / norm stays 0 outside the signal
-    } else {
-#pragma unroll 1
-      for (int r = lane; r < p.hop; r += 32) {
-        const int o = o0 + r;
-        if (o >= 0 && o < p.out_len) row[r] = __fdiv_rn(row[r], ff_norm(p, wsm, P, r));
-      }
-    }
-  }
-  __syncthreads();
+  ff_stage_adjoint_strips<FRAME_GAIN>(p, g, p.ex + (size_t)b * p.ex_stride, FRAME_GAIN ? p.vws_ex + (size_t)b * p.ex_stride2 : nullptr,
+                                      strip, xstrip, xstrip + (FRAME_GAIN ? g.NSTRIP * g.seg_stride : 0), wsm);
 
   if (warp == 0) {
     AllPole<MP> f;
@@ -344,16 +308,7 @@ __global__ void __launch_bounds__(kFfThreads) ff_backward_kernel(FfParams p) {
     if (FRAME_GAIN && own && p.d_gain) p.d_gain[(size_t)b * p.F + k] = dg;
   }
   __syncthreads();
-  float* __restrict__ deb = p.y + (size_t)b * p.Le;
-  for (int sj = warp; sj < g.NS; sj += kWarps) {
-    const int pos0 = (g.P0 + sj) * p.hop - p.pad;
-    const float* __restrict__ arow = acc + sj * g.seg_stride;
-#pragma unroll 4
-    for (int r = lane; r < p.hop; r += 32) {
-      const int pos = pos0 + r;
-      if (pos >= 0 && pos < p.Le) deb[pos] = arow[r];
-    }
-  }
+  ff_write_adjoint_rows(p, g, acc, p.y + (size_t)b * p.Le);
 }
 
 // d_ex = d_e * up(gain); d_gain[b,k] = sum_t w_k(t) d_e[t] ex[t]; frames beyond n_frames get d_a = 0

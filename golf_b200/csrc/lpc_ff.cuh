@@ -132,6 +132,68 @@ __device__ __forceinline__ float ff_norm(const FfParams& p, const float* wsm, in
   return norm;
 }
 
+// ---- staging / write-out shared by the adjoint kernels (lpc_ff.cu, biquad.cu) ------------------------------------------
+// strip = gy / (overlap-added window), xstrip (optional) = excitation, both in padded coordinates.  The copies go out
+// through cp.async (LDGSTS), all in flight at once; the division follows in a pass over shared memory, interior segments
+// sharing the norm row `nrow` [hop].  (A load -> divide -> store loop paid one L2 round trip per element, 66 times per
+// thread at hop 240.)  wsm must be complete (barrier) on entry; ends with a barrier.
+template <bool WITH_EX>
+__device__ __forceinline__ void ff_stage_adjoint_strips(const FfParams& p, const FfGeom& g, const float* __restrict__ gyb,
+                                                        const float* __restrict__ exb, float* __restrict__ strip,
+                                                        float* __restrict__ xstrip, float* __restrict__ nrow,
+                                                        const float* __restrict__ wsm) {
+  constexpr int kWarps = kFfThreads / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int sg = warp; sg < g.NSTRIP; sg += kWarps) {
+    const int o0 = (g.k0 + sg) * p.hop - p.pad;
+    float* __restrict__ row = strip + sg * g.seg_stride;
+    for (int r = lane; r < p.hop; r += 32) {
+      const int o = o0 + r;
+      cp_async4(row + r, gyb + min(max(o, 0), p.out_len - 1), o >= 0 && o < p.out_len);
+      if (WITH_EX) cp_async4(xstrip + sg * g.seg_stride + r, exb + min(max(o, 0), p.Le - 1), o >= 0 && o < p.Le);
+    }
+  }
+  for (int r = tid; r < p.hop; r += kFfThreads) {
+    float norm = 0.f;
+    for (int q = p.NQ - 1; q >= 0; --q) norm += wsm[q * p.hop + r];  // ff_norm's order
+    nrow[r] = norm;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  for (int sg = warp; sg < g.NSTRIP; sg += kWarps) {
+    const int P = g.k0 + sg;
+    const int o0 = P * p.hop - p.pad;
+    float* __restrict__ row = strip + sg * g.seg_stride;
+    if (P - (p.NQ - 1) >= 0 && P < p.n_frames) {
+#pragma unroll 4
+      for (int r = lane; r < p.hop; r += 32) row[r] = __fdiv_rn(row[r], nrow[r]);  // 0 / norm stays 0 outside the signal
+    } else {
+#pragma unroll 1
+      for (int r = lane; r < p.hop; r += 32) {
+        const int o = o0 + r;
+        if (o >= 0 && o < p.out_len) row[r] = __fdiv_rn(row[r], ff_norm(p, wsm, P, r));
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// the CTA's NS accumulator rows -> d_e [Le] (positions outside the signal dropped)
+__device__ __forceinline__ void ff_write_adjoint_rows(const FfParams& p, const FfGeom& g, const float* __restrict__ acc,
+                                                      float* __restrict__ deb) {
+  constexpr int kWarps = kFfThreads / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int sj = warp; sj < g.NS; sj += kWarps) {
+    const int pos0 = (g.P0 + sj) * p.hop - p.pad;
+    const float* __restrict__ arow = acc + sj * g.seg_stride;
+#pragma unroll 4
+    for (int r = lane; r < p.hop; r += 32) {
+      const int pos = pos0 + r;
+      if (pos >= 0 && pos < p.Le) deb[pos] = arow[r];
+    }
+  }
+}
+
 static inline size_t ff_smem_bytes(const FfParams& p, int vt_floats) {
   const int NS = 33 - p.NQ, NSTRIP = 32 + p.NQ - 1;
   return ((size_t)(NS + NSTRIP) * (p.hop + 1) + p.win + vt_floats) * sizeof(float);
