@@ -202,3 +202,24 @@ def test_bench_reference_arm_prints_one_json_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
+
+
+@pytest.mark.parametrize("lf_v2", [True, False])
+@pytest.mark.parametrize("table_type", ["flow", "derivative"])
+@pytest.mark.parametrize("normalize_method", [None, "constant_power", "peak"])
+@pytest.mark.parametrize("align_peak", [True, False])
+def test_glottal_construction_options_match_the_reference(lf_v2, table_type, normalize_method, align_peak):
+    """the sweep of the reference's tests/test_glottal.py:7-15, with values: every option builds the reference's table
+    (golden from the unmodified GlottalFlowTable, tests/golden/make_golden_table_options.py)"""
+    import numpy as np
+
+    from conftest import golden
+    from golf_b200 import synth
+
+    g = golden("table_options")
+    osc = synth.GlottalFlowTable(table_size=6, table_type=table_type, normalize_method=normalize_method, align_peak=align_peak,
+                                 lf_v2=lf_v2, points=128)
+    ref = g[f"{'v2' if lf_v2 else 'v1'}|{table_type}|{normalize_method}|{int(align_peak)}"]
+    assert osc.table.shape == ref.shape
+    assert np.abs(osc.R_d_values.numpy() - g["R_d_values"]).max() == 0
+    assert np.abs(osc.table.numpy() - ref).max() <= 2e-6 * max(1.0, float(np.abs(ref).max()))
