@@ -276,7 +276,7 @@ def run_gpu(args):
 
     # decoder passes in flight (1, 2, 4 or 8); the host-to-host pipeline is bound by the H2D copy from two passes on
     IN_FLIGHT = int(os.environ.get("GOLF_BENCH_IN_FLIGHT", "8"))  # measured on B200: 2 -> 6.23e9, 4 -> 7.3e9, 8 -> 7.46e9 samples/s
-    DEPTH, E2E_STREAMS = 4, 2
+    DEPTH, E2E_STREAMS = int(os.environ.get("GOLF_BENCH_DEPTH", "8")), int(os.environ.get("GOLF_BENCH_E2E_STREAMS", "4"))  # e2e pipeline slots / replay streams; measured on B200 (slots, streams): (4, 2) e2e 5.52e9 / frame-rate-f0 e2e 6.07e9, (8, 4) 5.54e9 / 7.12e9
     with torch.no_grad():
         graphed = [GraphedSynth(dec, params_of(s)) for s in dev_sets]
         pipe = PipelinedSynth(dec, params_of(dev_sets[0]), depth=DEPTH, compute_streams=E2E_STREAMS, packed=True)
