@@ -22,7 +22,8 @@
 // key = seed) + Box-Muller: same distribution as torch.randn, not the same stream -- opt-in (the exact-stream mode
 // passes the torch.randn tensor as `ex`).  Neighbouring CTAs regenerate the same halo samples from the same counters.
 //
-// FIR.  The packed-FP32 register tile of fir_tile.cuh (16 outputs per lane, FFMA2, taps summed in sequential order).
+// FIR.  The packed-FP32 register tile of fir_tile.cuh (16 outputs per lane, FFMA2; fir_tile16_eo: even- and odd-tap partial sums
+// per output, taps stored once).
 #include <atomic>
 
 #include "fir_tile.cuh"
@@ -127,7 +128,7 @@ __global__ void rng_advance_kernel(unsigned long long* state) { state[1] += 1ull
 
 // ---- the fused kernel ------------------------------------------------------------------------------------
 // grid (ceil(n_blocks / 8), B), 128 threads (4 warps x 2 blocks of `hop` outputs; 128 < hop <= 256, hop % 4 == 0).
-// smem: xs0[XS] | xs1[XS] | kd[8][2*K20] | sx[256][8] (spectra, later raw[8][256])
+// smem: xs0[XS] | xs1[XS] | kd[8][K20] | sx[256][8] (spectra, later raw[8][256])
 template <bool PHILOX>
 __global__ void __launch_bounds__(128) noise_fir_design_kernel(const float* __restrict__ ex, int64_t ex_stride,
                                                                const unsigned long long* __restrict__ rng_state,
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(128) noise_fir_design_kernel(const float* __re
   float* xs0 = smem;
   float* xs1 = smem + XS;
   float* kd = smem + 2 * XS;
-  float* sx = kd + kDFB * 2 * kDK20;
+  float* sx = kd + kDFB * kDK20;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.y;
   const int k0 = blockIdx.x * kDFB;
   const int nb = min(kDFB, n_blocks - k0);
@@ -228,8 +229,7 @@ __global__ void __launch_bounds__(128) noise_fir_design_kernel(const float* __re
     const int dd = i < kDK ? abs(i - kDH) : 0;
 #pragma unroll
     for (int f = 0; f < kDFB; ++f) {
-      const float t = i < kDK ? sx[f * kDN + dd] * w : 0.f;
-      reinterpret_cast<float2*>(kd + (size_t)f * 2 * kDK20)[i] = make_float2(t, t);
+      kd[f * kDK20 + i] = i < kDK ? sx[f * kDN + dd] * w : 0.f;
     }
   }
   if (!PHILOX) cp_async_wait_all();
@@ -239,13 +239,17 @@ __global__ void __launch_bounds__(128) noise_fir_design_kernel(const float* __re
   const int blk = 2 * warp + bi;
   if (bi >= 2 || blk >= nb) return;
   const int r0 = c * kR2;
-  f32x2 acc[kR2 / 2];
+  f32x2 acc[kR2];  // (even-tap sum, odd-tap sum) per output
 #pragma unroll
-  for (int i = 0; i < kR2 / 2; ++i) acc[i] = 0ull;
-  fir_tile16_x2(xs0, xs1, blk * hop + r0, kd + (size_t)blk * 2 * kDK20, kDK20, acc);
+  for (int i = 0; i < kR2; ++i) acc[i] = 0ull;
+  fir_tile16_eo(xs0, xs1, blk * hop + r0, kd + blk * kDK20, kDK20, acc);
   float o[kR2];
 #pragma unroll
-  for (int i = 0; i < kR2 / 2; ++i) unpack2(acc[i], o[2 * i], o[2 * i + 1]);
+  for (int i = 0; i < kR2; ++i) {
+    float lo, hi;
+    unpack2(acc[i], lo, hi);
+    o[i] = lo + hi;
+  }
   float* yb = y + (size_t)b * n_blocks * hop + (size_t)(k0 + blk) * hop + r0;
   const float* ab = add ? add + (size_t)b * add_stride + (size_t)(k0 + blk) * hop + r0 : nullptr;
   if (vec_ok && r0 + kR2 <= hop) {
@@ -288,12 +292,12 @@ GOLF_API int golf_noise_fir_design_fwd(const float* ex, int64_t ex_stride, const
   const int TPB = ceil_div(hop, kR2);
   const int xs_len = (kDFB - 1) * hop + (TPB - 1) * kR2 + kDK20 + 24;
   const int XS = (int)align_up((size_t)xs_len + 1, 32);
-  const size_t sm = ((size_t)2 * XS + (size_t)kDFB * 2 * kDK20 + (size_t)kDFB * kDN) * sizeof(float);
+  const size_t sm = ((size_t)2 * XS + (size_t)kDFB * kDK20 + (size_t)kDFB * kDN) * sizeof(float);
   const bool aligned = ((uintptr_t)y % 16 == 0) && (!add || ((uintptr_t)add % 16 == 0 && add_stride % 4 == 0));
   static unsigned long long attr = 0;
   if (first_use_on_device(attr)) {  // sized for the largest supported hop (256), not for this call's
     const int xs_max = (kDFB - 1) * 256 + 15 * kR2 + kDK20 + 24;
-    const size_t sm_max = ((size_t)2 * align_up((size_t)xs_max + 1, 32) + (size_t)kDFB * 2 * kDK20 + (size_t)kDFB * kDN) * sizeof(float);
+    const size_t sm_max = ((size_t)2 * align_up((size_t)xs_max + 1, 32) + (size_t)kDFB * kDK20 + (size_t)kDFB * kDN) * sizeof(float);
     GOLF_CUDA(cudaFuncSetAttribute(noise_fir_design_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_max));
     GOLF_CUDA(cudaFuncSetAttribute(noise_fir_design_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_max));
     mark_used_on_device(attr);

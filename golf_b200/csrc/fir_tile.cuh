@@ -130,4 +130,43 @@ __device__ __forceinline__ void fir_tile16_x2(const float* __restrict__ xs0, con
   }
 }
 
+// Same strips and rings, taps NOT duplicated: a 64-bit accumulator holds the even-tap and the odd-tap partial sum of ONE
+// output, so the natural tap pair (k[j], k[j+1]), j even, meets the input pair (x[o+j], x[o+j+1]) -- the even-aligned ring for
+// even outputs, the shifted ring for odd ones.  The same 32 FFMA2 per 4 taps with 3 LDS.128 instead of 4, half the tap
+// staging and half the shared memory for taps (more CTAs per SM); the result is lo + hi of each accumulator.
+// acc[o] (output q0 + o) += sum_{j<ntaps20} k[j] * x[q0 + o + j];  k: ntaps20 floats, 16-B aligned.
+__device__ __forceinline__ void fir_tile16_eo(const float* __restrict__ xs0, const float* __restrict__ xs1, int q0,
+                                              const float* __restrict__ k, int ntaps20, f32x2 (&acc)[kR2]) {
+  f32x2 we[10], wo[10];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) {
+    const float4 a = *reinterpret_cast<const float4*>(xs0 + fir_sw16(q0 + 4 * v));
+    const float4 b = *reinterpret_cast<const float4*>(xs1 + fir_sw16(q0 + 4 * v));
+    we[2 * v] = pack2(a.x, a.y), we[2 * v + 1] = pack2(a.z, a.w);
+    wo[2 * v] = pack2(b.x, b.y), wo[2 * v + 1] = pack2(b.z, b.w);
+  }
+#pragma unroll 1
+  for (int j = 0; j < ntaps20; j += kTapStep) {
+#pragma unroll
+    for (int g = 0; g < 5; ++g) {
+      const float4 kq = *reinterpret_cast<const float4*>(k + j + 4 * g);
+      const f32x2 t0 = pack2(kq.x, kq.y), t1 = pack2(kq.z, kq.w);
+#pragma unroll
+      for (int i = 0; i < kR2 / 2; ++i) {
+        ffma2(acc[2 * i], t0, we[(2 * g + i) % 10]);
+        ffma2(acc[2 * i + 1], t0, wo[(2 * g + i) % 10]);
+      }
+#pragma unroll
+      for (int i = 0; i < kR2 / 2; ++i) {
+        ffma2(acc[2 * i], t1, we[(2 * g + 1 + i) % 10]);
+        ffma2(acc[2 * i + 1], t1, wo[(2 * g + 1 + i) % 10]);
+      }
+      const float4 a = *reinterpret_cast<const float4*>(xs0 + fir_sw16(q0 + j + 4 * g + 20));
+      const float4 b = *reinterpret_cast<const float4*>(xs1 + fir_sw16(q0 + j + 4 * g + 20));
+      we[(2 * g) % 10] = pack2(a.x, a.y), we[(2 * g + 1) % 10] = pack2(a.z, a.w);
+      wo[(2 * g) % 10] = pack2(b.x, b.y), wo[(2 * g + 1) % 10] = pack2(b.z, b.w);
+    }
+  }
+}
+
 }  // namespace golf
