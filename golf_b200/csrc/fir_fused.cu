@@ -129,8 +129,16 @@ __global__ void rng_advance_kernel(unsigned long long* state) { state[1] += 1ull
 // ---- the fused kernel ------------------------------------------------------------------------------------
 // grid (ceil(n_blocks / 8), B), 128 threads (4 warps x 2 blocks of `hop` outputs; 128 < hop <= 256, hop % 4 == 0).
 // smem: xs0[XS] | xs1[XS] | kd[8][K20] | sx[256][8] (spectra, later raw[8][256])
+// Resident CTAs per SM the register budget is set for.  The taps-stored-once tile leaves 44.5 KB of shared memory per CTA, so
+// five fit; that needs <= 102 registers (96 allocated, 8 bytes of spill) against 127 unconstrained.  Interleaved A/B on one
+// B200 (tools/gpu/ab_libs.sh, 3 rounds): value with 8 passes in flight 7.42-7.46e9 -> 7.73-7.80e9 samples/s, GOLF-ff decoder
+// 9.65e9 -> 1.00e10; one pass alone 0.3138 -> 0.3184 ms.  (The tile change by itself, 4 CTAs per SM at 127 registers, was
+// neutral against the duplicated-tap tile at 3 CTAs per SM.)
+#ifndef GOLF_FIRD_MINB
+#define GOLF_FIRD_MINB 5
+#endif
 template <bool PHILOX>
-__global__ void __launch_bounds__(128) noise_fir_design_kernel(const float* __restrict__ ex, int64_t ex_stride,
+__global__ void __launch_bounds__(128, GOLF_FIRD_MINB) noise_fir_design_kernel(const float* __restrict__ ex, int64_t ex_stride,
                                                                const unsigned long long* __restrict__ rng_state,
                                                                const float* __restrict__ log_mag, const float* __restrict__ window,
                                                                const float* __restrict__ add, int64_t add_stride,
