@@ -427,8 +427,12 @@ static int launch_ff_bwd(const FfParams& pf, const FfParams& pb, cudaStream_t st
   return GOLF_OK;
 }
 
-static inline int ff_padded_order(int M) {
-  return M <= 4 ? 4 : M <= 8 ? 8 : M <= 12 ? 12 : M <= 16 ? 16 : M <= 20 ? 20 : M <= 24 ? 24 : M <= 32 ? 32 : 40;
+// The adjoint keeps static ring slots / tile offsets, so its padded order must divide the window and the hop: the smallest
+// compiled order >= M that does (the extra taps are zero coefficients), e.g. window 1024 / hop 256 / order 22 -> 32.
+static inline int ff_adjoint_order(int M, int win, int hop) {
+  for (int mp : {4, 8, 12, 16, 20, 24, 32, 40})
+    if (mp >= M && win % mp == 0 && hop % mp == 0) return mp;
+  return 0;
 }
 
 template <bool FRAME_GAIN>
@@ -531,8 +535,8 @@ GOLF_API int golf_lpc_ff_bwd(const float* gy, const float* ex, int64_t ex_stride
   // the adjoint writes d_e over every input position [0, Le), which can reach past the last output
   pb.nseg = (pf.pad + pf.Le - 1) / hop - pf.nseg0 + 1;
   pb.ctas_per_seq = ceil_div(pb.nseg, 33 - pf.NQ);
-  const int mp = ff_padded_order(M);
-  if (win % mp != 0 || hop % mp != 0) return GOLF_ERR_UNSUPPORTED;  // the adjoint keeps static slots / offsets
+  const int mp = ff_adjoint_order(M, win, hop);
+  if (mp == 0) return GOLF_ERR_UNSUPPORTED;
   rc = dispatch_ff_bwd<false>(mp, pf, pb, st);
   if (rc) return rc;
   // d_ex covers the caller's full excitation row (zeros beyond the filtered span)
@@ -591,8 +595,8 @@ GOLF_API int golf_lpc_frames_bwd(const float* gy, const float* ex, int64_t ex_st
   if (rc) return rc;
   const size_t need = golf_lpc_frames_bwd_workspace_bytes(B, T_ex, F, hop, win);
   if (!workspace || workspace_bytes < need) return GOLF_ERR_WORKSPACE;
-  const int mp = ff_padded_order(M);
-  if (win % mp != 0 || hop % mp != 0) return GOLF_ERR_UNSUPPORTED;
+  const int mp = ff_adjoint_order(M, win, hop);
+  if (mp == 0) return GOLF_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = reinterpret_cast<char*>(workspace);
   pf.vws = reinterpret_cast<float*>(ws);

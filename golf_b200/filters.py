@@ -132,10 +132,9 @@ def _check_ff_geometry(hop: int, W: int, M: int, needs_grad: bool) -> None:
     elif W % hop != 0 or not 2 <= W // hop <= 8:
         why = f"window_length {W} must be 2..8 times the hop {hop}"
     elif needs_grad:
-        mp = next(m for m in (4, 8, 12, 16, 20, 24, 32, 40) if M <= m)
-        if W % mp != 0 or hop % mp != 0:
-            why = (f"training needs window_length {W} and hop {hop} to be multiples of the padded order {mp} (order {M}); "
-                   "inference (torch.no_grad) works")
+        if not any(m >= M and W % m == 0 and hop % m == 0 for m in (4, 8, 12, 16, 20, 24, 32, 40)):
+            why = (f"training needs a kernel order in 4, 8, 12, 16, 20, 24, 32, 40 that is >= {M} and divides both "
+                   f"window_length {W} and hop {hop}; inference (torch.no_grad) works")
     if why is not None:
         raise GolfError(f"LTVMinimumPhaseFilter: {why}; use LTVMinimumPhaseFilterPrecise (any hop, order <= 40) or the reference module")
 

@@ -396,3 +396,33 @@ def test_trainable_glottal_table_trains_through_the_decoder():
         osc.table -= 0.01 * loss / (g * g).sum() * g
         drop = float(loss - loss_fn()) / float(loss)
     assert 0.005 < drop < 0.0101
+
+
+def test_ff_module_training_geometries():
+    """window 1024 / hop 256 / order 22 trains (the adjoint runs at the padded order 32, which divides both); a geometry no
+    compiled order divides fails in forward() with the reason when gradients are requested, and runs under no_grad"""
+    from golf_b200 import GolfError, filters
+    from golf_b200.audiotensor import AudioTensor
+
+    gen = torch.Generator().manual_seed(5)
+
+    def run(W, hop, grad):
+        filt = filters.LTVMinimumPhaseFilter(window="hanning", window_length=W, lpc_order=22).to(DEV)
+        Fr = 12
+        ex = AudioTensor(torch.randn(2, (Fr - 1) * hop, generator=gen).to(DEV), hop_length=1)
+        lg = AudioTensor(torch.randn(2, Fr, generator=gen).to(DEV) * 0.1, hop_length=hop)
+        raw = (0.3 * torch.randn(2, Fr, 22, generator=gen)).to(DEV).requires_grad_(grad)
+        logits = AudioTensor(raw, hop_length=hop)
+        _, trsfms = filt.ctrl(lambda sizes, fns: (sizes, fns))((), ())  # the module's own .ctrl transform (exp, rc2lpc)
+        gain, a = trsfms[0](lg, logits)
+        y = filt(ex, gain, a).as_tensor()
+        if grad:
+            (g,) = torch.autograd.grad(y.square().mean(), raw)
+            assert torch.isfinite(g).all() and g.abs().sum() > 0
+        return y
+
+    run(1024, 256, True)
+    with torch.no_grad():
+        assert torch.isfinite(run(1000, 250, False)).all()
+    with pytest.raises(GolfError, match="divides both"):
+        run(1000, 250, True)
