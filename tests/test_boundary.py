@@ -223,3 +223,27 @@ def test_glottal_construction_options_match_the_reference(lf_v2, table_type, nor
     assert osc.table.shape == ref.shape
     assert np.abs(osc.R_d_values.numpy() - g["R_d_values"]).max() == 0
     assert np.abs(osc.table.numpy() - ref).max() <= 2e-6 * max(1.0, float(np.abs(ref).max()))
+
+
+@pytest.mark.parametrize("hop,W,M,grad,ok", [
+    (240, 960, 22, True, True),      # shipped GOLF-ff
+    (120, 480, 22, True, True),      # ISMIR-23
+    (256, 1024, 22, True, True),     # adjoint at the padded order 32
+    (250, 1000, 22, False, True),    # inference only needs the forward constraints
+    (250, 1000, 22, True, False),    # no compiled order >= 22 divides 250
+    (32, 128, 22, False, False),     # hop < 40
+    (240, 2400, 22, False, False),   # window / hop > 8
+    (240, 1000, 22, False, False),   # window not a multiple of the hop
+    (240, 960, 41, False, False),    # order > 40
+])
+def test_ff_geometry_validation_mirrors_the_kernels(hop, W, M, grad, ok):
+    """filters._check_ff_geometry is what LTVMinimumPhaseFilter.forward consults: it must say in forward() what the C entry
+    points (golf_lpc_ff_fwd / _bwd) would refuse later (csrc/lpc_ff.cu: fill_geometry, ff_adjoint_order)"""
+    from golf_b200 import GolfError
+    from golf_b200.filters import _check_ff_geometry
+
+    if ok:
+        _check_ff_geometry(hop, W, M, grad)
+    else:
+        with pytest.raises(GolfError, match="LTVMinimumPhaseFilter"):
+            _check_ff_geometry(hop, W, M, grad)
