@@ -109,7 +109,7 @@ __device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y
 #define GOLF_RESP_F2 0
 #endif
 #ifndef GOLF_RESP_WPB
-#define GOLF_RESP_WPB 4  // warps per CTA: they meet at a barrier every tile, which keeps them in the same part of the 48 KB loop body (81 -> 77 us; 8 per CTA: the same)
+#define GOLF_RESP_WPB 4  // warps per CTA: they meet at a barrier every tile, which keeps them in the same part of the 48 KB loop body (81 -> 77 us; 8 per CTA: the same; 2 per CTA: value with 8 passes in flight 7.76e9 -> 7.67e9 in an interleaved A/B)
 #endif
 #ifndef GOLF_RESP_RES_BIG
 #define GOLF_RESP_RES_BIG 8  // resident warps per SM the padded orders 32 / 40 are compiled for (4: 255 registers, one CTA)
